@@ -1,0 +1,575 @@
+// Tensor-core contraction core for the LRCN hot path (sm_100a only).
+//
+// One persistent, warp-specialised kernel: TMA (tiled or im2col mode) stages bf16 operand tiles in
+// 128B-swizzled shared memory, a single elected thread issues tcgen05.mma (UMMA 128 x BN x 16) into
+// double-buffered TMEM accumulators, four epilogue warps drain TMEM with tcgen05.ld and apply
+// bias / ReLU / ReLU-gradient mask before vectorised stores (or split-K red.add for filter gradients).
+//
+// It replaces the TensorFlow ops of the reference's hot path:
+//   tf.nn.conv2d (+ split/concat groups)   models/alexnet/alexnet.py:15-31
+//   tf.nn.relu_layer / xw_plus_b           models/alexnet/alexnet.py:228,248,275 ; tf_util.py:56
+//   BasicLSTMCell input projection         models/lstm/lstm.py:9-20,141
+//   and the conv2d / matmul gradients TF derives for train.py:210.
+#include "common.cuh"
+#include "../../include/vlb200.h"
+
+#include <atomic>
+
+namespace vl {
+extern std::atomic<long long> g_launches;
+}
+
+namespace {
+
+using namespace vl::ptx;
+typedef __nv_bfloat16 bf16;
+
+constexpr int BM = 128;                     // UMMA M (cta_group::1)
+constexpr int BK = 64;                      // bf16 elements per k-block = one 128B swizzle row
+constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
+constexpr int NUM_THREADS = 192;            // warp0 TMA, warp1 MMA (+TMEM alloc), warps 2..5 epilogue
+constexpr int TMEM_COLS = 512;              // 2 accumulator stages x 256 fp32 columns
+constexpr int ACC_STRIDE_COLS = 256;
+constexpr int MAX_STAGES = 8;
+constexpr int SMEM_LIMIT = 232448;          // 227 KB opt-in maximum per CTA
+constexpr int BAR_REGION = 1024;
+
+struct KParams {
+  int M, N;  // valid extents per group
+  int groups, num_m_blk, num_n_blk, split_k, kb_total, kb_per_split, total_tiles;
+  int BN;
+  int a_mode, b_mode;
+  int a_goff, b_goff, c_goff;
+  int b_tap_stride;
+  int taps, cchunks, kw, flip;
+  int P, Q, PQ, stride_h, stride_w, lower_h, lower_w, cin_g;
+  void* C;
+  int c_ld, c_dtype, c_atomic, relu;
+  const float* bias;
+  const bf16* mask;
+  int mask_ld;
+  int num_stages, b_stage_bytes, stage_bytes;
+  uint32_t idesc;
+  uint32_t a_desc_hi, b_desc_hi;      // upper 32 bits of the smem descriptors (SBO, version, swizzle)
+  uint32_t a_lbo_enc, b_lbo_enc;      // encoded leading byte offset (bits 16..29 of the low word)
+  uint32_t a_kstep_enc, b_kstep_enc;  // encoded start-address advance per UMMA_K (=16 elements)
+};
+
+struct TileCoord {
+  int m_blk, n_blk, g, kb_begin, kb_end;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const KParams& p, int tile) {
+  TileCoord t;
+  t.n_blk = tile % p.num_n_blk;
+  int r = tile / p.num_n_blk;
+  t.m_blk = r % p.num_m_blk;
+  r /= p.num_m_blk;
+  t.g = r % p.groups;
+  int split = r / p.groups;
+  t.kb_begin = split * p.kb_per_split;
+  t.kb_end = min(p.kb_total, t.kb_begin + p.kb_per_split);
+  return t;
+}
+
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_enc, uint32_t hi) {
+  uint32_t lo = ((smem_addr >> 4) & 0x3FFFu) | (lbo_enc << 16);
+  return (static_cast<uint64_t>(hi) << 32) | lo;
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+    umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                     const __grid_constant__ KParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  // 128B swizzle atoms need 1024B-aligned tiles.
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* tiles = smem + BAR_REGION;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* empty_bar = full_bar + MAX_STAGES;
+  uint64_t* tmem_full = empty_bar + MAX_STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    for (int s = 0; s < p.num_stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_base_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(p, tile);
+        const int m0 = t.m_blk * BM;
+        const int n0 = t.n_blk * p.BN;
+        int pn = 0, pp = 0, pq = 0;
+        if (p.a_mode == VL_A_IM2COL_K) {
+          pn = m0 / p.PQ;
+          int rem = m0 - pn * p.PQ;
+          pp = rem / p.Q;
+          pq = rem - pp * p.Q;
+        }
+        for (int kb = t.kb_begin; kb < t.kb_end; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          uint8_t* sA = tiles + stage * p.stage_bytes;
+          uint8_t* sB = sA + A_STAGE_BYTES;
+          // ---- expected bytes ----
+          uint32_t bytes = p.b_stage_bytes;
+          int a_valid = 2;
+          if (p.a_mode == VL_A_IM2COL_MN) {
+            int chunks = p.taps * p.cchunks;
+            a_valid = min(2, chunks - t.m_blk * 2);
+            bytes += 8192u * a_valid;
+          } else {
+            bytes += A_STAGE_BYTES;
+          }
+          mbar_expect_tx(&full_bar[stage], bytes);
+          // ---- A ----
+          if (p.a_mode == VL_A_TILED_K) {
+            tma_load_2d(sA, &tmA, &full_bar[stage], t.g * p.a_goff + kb * BK, m0);
+          } else if (p.a_mode == VL_A_TILED_MN) {
+            tma_load_2d(sA, &tmA, &full_bar[stage], t.g * p.a_goff + m0, kb * BK);
+            tma_load_2d(sA + 8192, &tmA, &full_bar[stage], t.g * p.a_goff + m0 + 64, kb * BK);
+          } else if (p.a_mode == VL_A_IM2COL_K) {
+            int tap = kb / p.cchunks;
+            int cc = kb - tap * p.cchunks;
+            int r = tap / p.kw;
+            int s = tap - r * p.kw;
+            tma_load_im2col_4d(sA, &tmA, &full_bar[stage], t.g * p.a_goff + cc * BK, pq * p.stride_w + p.lower_w,
+                               pp * p.stride_h + p.lower_h, pn, (uint16_t)s, (uint16_t)r);
+          } else {  // VL_A_IM2COL_MN
+            int pix = kb * BK;
+            int n_ = pix / p.PQ;
+            int rem = pix - n_ * p.PQ;
+            int p_ = rem / p.Q;
+            int q_ = rem - p_ * p.Q;
+            for (int j = 0; j < a_valid; ++j) {
+              int mc = t.m_blk * 2 + j;
+              int tap = mc / p.cchunks;
+              int cc = mc - tap * p.cchunks;
+              int r = tap / p.kw;
+              int s = tap - r * p.kw;
+              tma_load_im2col_4d(sA + j * 8192, &tmA, &full_bar[stage], t.g * p.a_goff + cc * BK,
+                                 q_ * p.stride_w + p.lower_w, p_ * p.stride_h + p.lower_h, n_, (uint16_t)s,
+                                 (uint16_t)r);
+            }
+          }
+          // ---- B ----
+          if (p.b_mode == VL_B_TILED_K) {
+            int tap = kb / p.cchunks;
+            int cc = kb - tap * p.cchunks;
+            int tapb = p.flip ? (p.taps - 1 - tap) : tap;
+            tma_load_2d(sB, &tmB, &full_bar[stage], t.g * p.b_goff + cc * BK, n0 + tapb * p.b_tap_stride);
+          } else {
+            for (int j = 0; j < p.BN / 64; ++j)
+              tma_load_2d(sB + j * 8192, &tmB, &full_bar[stage], t.g * p.b_goff + n0 + j * 64, kb * BK);
+          }
+          if (++stage == p.num_stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (single thread) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int local = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++local) {
+        const TileCoord t = decode_tile(p, tile);
+        const int acc = local & 1;
+        const uint32_t acc_phase = (local >> 1) & 1;
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * ACC_STRIDE_COLS;
+        for (int kb = t.kb_begin; kb < t.kb_end; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sA = smem_u32(tiles + stage * p.stage_bytes);
+          const uint32_t sB = sA + A_STAGE_BYTES;
+          uint64_t adesc = make_desc(sA, p.a_lbo_enc, p.a_desc_hi);
+          uint64_t bdesc = make_desc(sB, p.b_lbo_enc, p.b_desc_hi);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            umma_bf16(tmem_d, adesc, bdesc, p.idesc, (kb > t.kb_begin || k > 0) ? 1u : 0u);
+            adesc += p.a_kstep_enc;
+            bdesc += p.b_kstep_enc;
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot once the MMAs have read it
+          if (++stage == p.num_stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ===================== epilogue warps (TMEM -> registers -> HBM) =====================
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    int local = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++local) {
+      const TileCoord t = decode_tile(p, tile);
+      const int acc = local & 1;
+      const uint32_t acc_phase = (local >> 1) & 1;
+      const int m0 = t.m_blk * BM;
+      const int n0 = t.n_blk * p.BN;
+      const int row_in_tile = quad * 32 + lane;
+      long long grow;
+      bool row_ok;
+      if (p.a_mode == VL_A_IM2COL_MN) {
+        int mc = t.m_blk * 2 + (row_in_tile >> 6);
+        int tap = mc / p.cchunks;
+        int cc = mc - tap * p.cchunks;
+        int ci = cc * 64 + (row_in_tile & 63);
+        row_ok = (mc < p.taps * p.cchunks) && (ci < p.cin_g);
+        grow = (long long)tap * p.cin_g + ci;
+      } else {
+        grow = m0 + row_in_tile;
+        row_ok = grow < p.M;
+      }
+      const int gcol0 = t.g * p.c_goff + n0;  // global column of tile column 0
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + acc * ACC_STRIDE_COLS;
+      const bool vec_ok = (p.c_ld % 8 == 0) && (gcol0 % 8 == 0) && !p.c_atomic &&
+                          (p.mask == nullptr || p.mask_ld % 8 == 0);
+      for (int c0 = 0; c0 < p.BN; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld_x16(taddr + c0, v);
+        tmem_ld_wait();
+        if (!row_ok) continue;
+        const int ncols = min(16, p.N - (n0 + c0));
+        if (ncols <= 0) continue;
+        float f[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+        if (p.bias != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (j < ncols) f[j] += __ldg(p.bias + gcol0 + c0 + j);
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.0f);
+        }
+        if (p.mask != nullptr) {
+          const bf16* mrow = p.mask + grow * p.mask_ld + gcol0 + c0;
+          if (vec_ok && ncols == 16) {
+            uint4 m0v = *reinterpret_cast<const uint4*>(mrow);
+            uint4 m1v = *reinterpret_cast<const uint4*>(mrow + 8);
+            const bf16* mv0 = reinterpret_cast<const bf16*>(&m0v);
+            const bf16* mv1 = reinterpret_cast<const bf16*>(&m1v);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              if (!(__bfloat162float(mv0[j]) > 0.0f)) f[j] = 0.0f;
+              if (!(__bfloat162float(mv1[j]) > 0.0f)) f[8 + j] = 0.0f;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (j < ncols && !(__bfloat162float(mrow[j]) > 0.0f)) f[j] = 0.0f;
+          }
+        }
+        const long long off = grow * p.c_ld + gcol0 + c0;
+        if (p.c_dtype == VL_DT_BF16) {
+          bf16* out = reinterpret_cast<bf16*>(p.C) + off;
+          if (vec_ok && ncols == 16) {
+            uint32_t w[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+              w[j] = *reinterpret_cast<uint32_t*>(&h);
+            }
+            *reinterpret_cast<uint4*>(out) = make_uint4(w[0], w[1], w[2], w[3]);
+            *reinterpret_cast<uint4*>(out + 8) = make_uint4(w[4], w[5], w[6], w[7]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (j < ncols) out[j] = __float2bfloat16_rn(f[j]);
+          }
+        } else {
+          float* out = reinterpret_cast<float*>(p.C) + off;
+          if (p.c_atomic) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (j < ncols) atomicAdd(out + j, f[j]);
+          } else if (vec_ok && ncols == 16) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<float4*>(out + 4 * j) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (j < ncols) out[j] = f[j];
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host side: tensor-map encoding through the driver entry points (no link-time libcuda dependency).
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t,
+                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn g_encode_tiled = nullptr;
+EncodeIm2colFn g_encode_im2col = nullptr;
+
+int load_driver_fns() {
+  if (g_encode_tiled && g_encode_im2col) return 0;
+  cudaDriverEntryPointQueryResult q;
+  void* fn = nullptr;
+  VL_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+  VL_REQUIRE(fn != nullptr && q == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available");
+  g_encode_tiled = reinterpret_cast<EncodeTiledFn>(fn);
+  fn = nullptr;
+  VL_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &fn, cudaEnableDefault, &q));
+  VL_REQUIRE(fn != nullptr && q == cudaDriverEntryPointSuccess, "cuTensorMapEncodeIm2col not available");
+  g_encode_im2col = reinterpret_cast<EncodeIm2colFn>(fn);
+  return 0;
+}
+
+// 2D bf16 row-major tensor [outer][inner] with row pitch `ld` elements, 128B-swizzled boxes.
+int make_tiled_map(CUtensorMap* m, const void* base, long long inner, long long outer, long long ld, int box_inner,
+                   int box_outer) {
+  VL_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base pointer must be 16B aligned");
+  VL_REQUIRE((ld * 2) % 16 == 0, "TMA row pitch must be a multiple of 16 bytes (ld=%lld)", ld);
+  VL_REQUIRE(box_inner * 2 <= 128 && box_outer <= 256 && box_outer >= 1, "bad TMA box %dx%d", box_inner, box_outer);
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode_tiled(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box,
+                              estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  VL_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d): inner=%lld outer=%lld ld=%lld box=%dx%d", (int)r,
+             inner, outer, ld, box_inner, box_outer);
+  return 0;
+}
+
+// NHWC bf16 tensor seen as (C, W, H, N); im2col boxes of `pixels` x 64 channels, 128B swizzle.
+int make_im2col_map(CUtensorMap* m, const void* base, const vl_conv_geom& g, int pixels) {
+  VL_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base pointer must be 16B aligned");
+  VL_REQUIRE(g.c % 8 == 0, "im2col TMA needs a channel count that is a multiple of 8 (c=%d)", g.c);
+  cuuint64_t dims[4] = {(cuuint64_t)g.c, (cuuint64_t)g.w, (cuuint64_t)g.h, (cuuint64_t)g.n};
+  cuuint64_t strides[3] = {(cuuint64_t)g.c * 2, (cuuint64_t)g.c * g.w * 2, (cuuint64_t)g.c * g.w * g.h * 2};
+  // TF SAME/VALID geometry: base pixel of output (p,q) is (p*stride - pad_top, q*stride - pad_left); the upper
+  // corner bounds the last base pixel so that exactly P x Q positions are traversed per image.
+  int lower[2] = {-g.pad_left, -g.pad_top};
+  int upper[2] = {(g.q - 1) * g.stride_w - g.pad_left - (g.w - 1), (g.p - 1) * g.stride_h - g.pad_top - (g.h - 1)};
+  cuuint32_t estr[4] = {1, (cuuint32_t)g.stride_w, (cuuint32_t)g.stride_h, 1};
+  CUresult r = g_encode_im2col(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, lower,
+                               upper, 64, (cuuint32_t)pixels, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  VL_REQUIRE(r == CUDA_SUCCESS,
+             "cuTensorMapEncodeIm2col failed (%d): nhwc=%dx%dx%dx%d lower=(%d,%d) upper=(%d,%d) stride=(%d,%d)", (int)r,
+             g.n, g.h, g.w, g.c, lower[0], lower[1], upper[0], upper[1], g.stride_w, g.stride_h);
+  return 0;
+}
+
+int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+}  // namespace
+
+extern "C" int vl_gemm(const vl_gemm_desc* d, const void* a, const void* b, void* c, const float* bias,
+                       const void* relu_mask, vl_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  VL_REQUIRE(d && a && b && c, "vl_gemm: null argument");
+  VL_REQUIRE(d->m > 0 && d->n > 0 && d->k > 0 && d->groups >= 1, "vl_gemm: bad extents m=%d n=%d k=%d groups=%d",
+             d->m, d->n, d->k, d->groups);
+  if (load_driver_fns() != 0) return -1;
+
+  KParams p;
+  memset(&p, 0, sizeof(p));
+  const bool a_im2col = d->a_mode == VL_A_IM2COL_K || d->a_mode == VL_A_IM2COL_MN;
+  const bool a_mn = d->a_mode == VL_A_TILED_MN || d->a_mode == VL_A_IM2COL_MN;
+  const bool b_mn = d->b_mode == VL_B_TILED_MN;
+  const vl_conv_geom& cg = d->conv;
+
+  p.groups = d->groups;
+  p.a_mode = d->a_mode;
+  p.b_mode = d->b_mode;
+  p.a_goff = d->a_goff;
+  p.b_goff = d->b_goff;
+  p.c_goff = d->c_goff;
+  p.b_tap_stride = d->b_tap_stride;
+  p.taps = 1;
+  p.kw = 1;
+  p.flip = 0;
+
+  // ---- block_n ----
+  int BN = d->block_n;
+  if (BN == 0) {
+    int nb = ceil_div(d->n, 256);
+    int per = ceil_div(d->n, nb);
+    int gran = b_mn ? 64 : 16;
+    BN = ceil_div(per, gran) * gran;
+  }
+  VL_REQUIRE(BN >= 16 && BN <= 256 && BN % 16 == 0, "vl_gemm: block_n %d invalid", BN);
+  VL_REQUIRE(!b_mn || BN % 64 == 0, "vl_gemm: N-major B needs block_n %% 64 == 0 (got %d)", BN);
+  p.BN = BN;
+  p.N = d->n;
+
+  // ---- contraction decomposition ----
+  if (a_im2col) {
+    VL_REQUIRE(cg.kh > 0 && cg.kw > 0 && cg.p > 0 && cg.q > 0 && cg.cin_g > 0, "vl_gemm: bad conv geometry");
+    p.taps = cg.kh * cg.kw;
+    p.kw = cg.kw;
+    p.cchunks = ceil_div(cg.cin_g, 64);
+    p.flip = cg.flip_taps;
+    p.P = cg.p;
+    p.Q = cg.q;
+    p.PQ = cg.p * cg.q;
+    p.stride_h = cg.stride_h;
+    p.stride_w = cg.stride_w;
+    p.lower_h = -cg.pad_top;
+    p.lower_w = -cg.pad_left;
+    p.cin_g = cg.cin_g;
+  }
+  if (d->a_mode == VL_A_IM2COL_K) {
+    p.M = cg.n * cg.p * cg.q;
+    VL_REQUIRE(d->m == p.M, "vl_gemm: m (%d) must equal n*p*q (%d) for im2col A", d->m, p.M);
+    p.kb_total = p.taps * p.cchunks;
+    p.num_m_blk = ceil_div(p.M, BM);
+  } else if (d->a_mode == VL_A_IM2COL_MN) {
+    // M axis = (tap, 64-channel chunk); K axis = output pixels.
+    p.M = p.taps * cg.cin_g;
+    VL_REQUIRE(d->k == cg.n * cg.p * cg.q, "vl_gemm: k (%d) must equal n*p*q for transposed im2col A", d->k);
+    p.kb_total = ceil_div(d->k, BK);
+    p.num_m_blk = ceil_div(p.taps * p.cchunks, 2);
+  } else {
+    p.M = d->m;
+    p.kb_total = ceil_div(d->k, BK);
+    p.num_m_blk = ceil_div(p.M, BM);
+    if (d->b_mode == VL_B_TILED_K && d->b_tap_stride > 0) {
+      VL_REQUIRE(false, "vl_gemm: b_tap_stride needs an im2col A operand");
+    }
+  }
+  if (!a_im2col) p.cchunks = p.kb_total;  // dense k-block walk: tap = 0, cc = kb
+  // B_TILED_K decodes (tap, cc) from kb with p.cchunks; for transposed-im2col A the B operand is always N-major.
+  VL_REQUIRE(!(d->a_mode == VL_A_IM2COL_MN && d->b_mode == VL_B_TILED_K),
+             "vl_gemm: transposed im2col A requires an N-major B");
+  p.num_n_blk = ceil_div(d->n, BN);
+  p.split_k = d->split_k < 1 ? 1 : d->split_k;
+  if (p.split_k > p.kb_total) p.split_k = p.kb_total;
+  p.kb_per_split = ceil_div(p.kb_total, p.split_k);
+  p.split_k = ceil_div(p.kb_total, p.kb_per_split);  // no empty splits
+  VL_REQUIRE(p.split_k == 1 || (d->c_atomic && d->c_dtype == VL_DT_F32), "vl_gemm: split_k needs fp32 atomic output");
+  p.total_tiles = p.num_m_blk * p.num_n_blk * p.groups * p.split_k;
+
+  // ---- epilogue ----
+  p.C = c;
+  p.c_ld = d->c_ld;
+  p.c_dtype = d->c_dtype;
+  p.c_atomic = d->c_atomic;
+  p.relu = d->relu;
+  p.bias = bias;
+  p.mask = reinterpret_cast<const bf16*>(relu_mask);
+  p.mask_ld = d->mask_ld;
+  VL_REQUIRE(!d->c_atomic || d->c_dtype == VL_DT_F32, "vl_gemm: atomic output must be fp32");
+
+  // ---- smem pipeline ----
+  p.b_stage_bytes = BN * 128;
+  p.stage_bytes = A_STAGE_BYTES + ((p.b_stage_bytes + 1023) / 1024) * 1024;
+  int stages = (SMEM_LIMIT - 1024 - BAR_REGION) / p.stage_bytes;
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  VL_REQUIRE(stages >= 2, "vl_gemm: not enough shared memory for 2 stages");
+  p.num_stages = stages;
+  const int smem_bytes = 1024 + BAR_REGION + stages * p.stage_bytes;
+
+  // ---- descriptors ----
+  // instruction descriptor: D=f32, A=B=bf16, majors, N>>3 at bit 17, M>>4 at bit 24
+  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+            ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+  // smem descriptor high word: SBO = 1024B (8 rows x 128B) at bits 32..45, version 1 at bit 46, SWIZZLE_128B (2) at 61
+  const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+  p.a_desc_hi = hi;
+  p.b_desc_hi = hi;
+  p.a_lbo_enc = a_mn ? (8192u >> 4) : 1u;
+  p.b_lbo_enc = b_mn ? (8192u >> 4) : 1u;
+  p.a_kstep_enc = a_mn ? (2048u >> 4) : (32u >> 4);
+  p.b_kstep_enc = b_mn ? (2048u >> 4) : (32u >> 4);
+
+  // ---- tensor maps ----
+  CUtensorMap tmA, tmB;
+  if (d->a_mode == VL_A_TILED_K) {
+    long long inner = (long long)d->a_goff * (d->groups - 1) + d->k;
+    if (make_tiled_map(&tmA, a, inner, d->m, d->a_ld, 64, BM) != 0) return -1;
+  } else if (d->a_mode == VL_A_TILED_MN) {
+    long long inner = (long long)d->a_goff * (d->groups - 1) + d->m;
+    if (make_tiled_map(&tmA, a, inner, d->k, d->a_ld, 64, 64) != 0) return -1;
+  } else {
+    if (make_im2col_map(&tmA, a, cg, d->a_mode == VL_A_IM2COL_K ? BM : 64) != 0) return -1;
+  }
+  if (d->b_mode == VL_B_TILED_K) {
+    // rows = n (x taps for conv data-gradients), inner = contraction (+ group offsets)
+    long long inner, outer;
+    if (d->a_mode == VL_A_IM2COL_K) {
+      inner = (long long)d->b_goff * (d->groups - 1) + (long long)p.cchunks * 64;
+      outer = (long long)p.taps * (d->b_tap_stride > 0 ? d->b_tap_stride : d->n);
+      if (d->b_tap_stride == 0) p.b_tap_stride = d->n;
+    } else {
+      inner = (long long)d->b_goff * (d->groups - 1) + d->k;
+      outer = d->n;
+    }
+    if (make_tiled_map(&tmB, b, inner, outer, d->b_ld, 64, BN) != 0) return -1;
+  } else {
+    long long inner = (long long)d->b_goff * (d->groups - 1) + d->n;
+    long long outer = (d->a_mode == VL_A_IM2COL_K) ? (long long)p.kb_total * 64 : d->k;
+    if (make_tiled_map(&tmB, b, inner, outer, d->b_ld, 64, 64) != 0) return -1;
+  }
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    VL_CHECK_CUDA(cudaFuncSetAttribute(umma_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    attr_set = true;
+  }
+  int grid = p.total_tiles < vl::num_sms() ? p.total_tiles : vl::num_sms();
+  umma_gemm_kernel<<<grid, NUM_THREADS, smem_bytes, stream>>>(tmA, tmB, p);
+  vl::g_launches.fetch_add(1);
+  VL_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -1,0 +1,39 @@
+// Host runtime glue of the C-ABI: error channel, device query, launch counter.
+#include "common.cuh"
+#include "../../include/vlb200.h"
+
+#include <atomic>
+#include <stdarg.h>
+
+namespace vl {
+
+std::atomic<long long> g_launches{0};
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* last_error() { return g_err; }
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return 148;
+    n = prop.multiProcessorCount;
+  }
+  return n;
+}
+
+}  // namespace vl
+
+extern "C" const char* vl_last_error(void) { return vl::last_error(); }
+extern "C" int vl_version(void) { return 100; }
+extern "C" int vl_device_sm_count(void) { return vl::num_sms(); }
+extern "C" int64_t vl_launch_count(void) { return vl::g_launches.load(); }

@@ -1,0 +1,199 @@
+"""Host-side launch wrappers: build the POD descriptors of include/vlb200.h and enqueue the sm_100a kernels.
+
+PyTorch tensors are used only as device buffers (`data_ptr()`) and for the current stream; every FLOP of
+the hot path runs in the hand-written kernels of `csrc/`.  Each wrapper names the TensorFlow op of the
+reference it stands in for (file:line into /root/reference).
+"""
+import math
+
+import torch
+
+from . import _native as nv
+
+BF16 = torch.bfloat16
+F32 = torch.float32
+
+
+# ----------------------------------------------------------------------------------------------------
+# geometry helpers
+# ----------------------------------------------------------------------------------------------------
+def same_padding(in_size, k, stride):
+    """TF `padding="SAME"` (alexnet.py:76,117,159,180,201): out = ceil(in/stride), pad split low/high."""
+    out = -(-in_size // stride)
+    total = max((out - 1) * stride + k - in_size, 0)
+    return out, total // 2, total - total // 2
+
+
+def valid_out(in_size, k, stride):
+    """TF `padding="VALID"` (alexnet.py:98,139,211)."""
+    return (in_size - k) // stride + 1
+
+
+class ConvSpec(object):
+    """Static description of one (possibly grouped) SAME convolution of the AlexNet encoder."""
+
+    def __init__(self, h, w, cin, cout, kh, kw, stride, groups):
+        self.h, self.w, self.cin, self.cout = h, w, cin, cout
+        self.kh, self.kw, self.stride, self.groups = kh, kw, stride, groups
+        self.p, self.pad_top, self.pad_bottom = same_padding(h, kh, stride)
+        self.q, self.pad_left, self.pad_right = same_padding(w, kw, stride)
+        self.cin_g = cin // groups
+        self.cout_g = cout // groups
+        self.taps = kh * kw
+        self.cchunks = -(-self.cin_g // 64)
+        self.k_packed = self.taps * self.cchunks * 64  # rows of the packed (zero padded) filter matrix
+
+    def geom(self, n):
+        g = nv.ConvGeom()
+        g.n, g.h, g.w, g.c = n, self.h, self.w, self.cin
+        g.kh, g.kw = self.kh, self.kw
+        g.stride_h = g.stride_w = self.stride
+        g.pad_top, g.pad_left = self.pad_top, self.pad_left
+        g.p, g.q = self.p, self.q
+        g.cin_g = self.cin_g
+        g.flip_taps = 0
+        return g
+
+    def geom_dgrad(self, n):
+        """im2col walk over dY for the data gradient (stride 1 only): pad' = k-1-pad, taps flipped."""
+        assert self.stride == 1
+        g = nv.ConvGeom()
+        g.n, g.h, g.w, g.c = n, self.p, self.q, self.cout
+        g.kh, g.kw = self.kh, self.kw
+        g.stride_h = g.stride_w = 1
+        g.pad_top, g.pad_left = self.kh - 1 - self.pad_top, self.kw - 1 - self.pad_left
+        g.p, g.q = self.h, self.w
+        g.cin_g = self.cout_g
+        g.flip_taps = 1
+        return g
+
+
+def _ld(t):
+    assert t.dim() == 2 and t.stride(1) == 1
+    return t.stride(0)
+
+
+# ----------------------------------------------------------------------------------------------------
+# dense layers: tf.nn.relu_layer / tf.nn.xw_plus_b (alexnet.py:228,248,275; tf_util.py:56; lstm.py:141 x-part)
+# ----------------------------------------------------------------------------------------------------
+def linear_fwd(x, w, bias, out, relu=False, n=None, block_n=0):
+    """out[M,N] = act(x[M,K] @ w[K,N] + bias).  x, w bf16 (w in TF [in,out] layout, row pitch % 8 == 0)."""
+    m, k = x.shape
+    n = out.shape[1] if n is None else n
+    d = nv.GemmDesc()
+    d.m, d.n, d.k, d.groups = m, n, k, 1
+    d.a_mode, d.b_mode = nv.A_TILED_K, nv.B_TILED_MN
+    d.a_ld, d.b_ld = _ld(x), _ld(w)
+    d.c_ld = _ld(out)
+    d.c_dtype = nv.DT_BF16 if out.dtype == BF16 else nv.DT_F32
+    d.relu = 1 if relu else 0
+    d.split_k = 1
+    d.block_n = block_n
+    nv.gemm(d, x, w, out, bias)
+    return out
+
+
+def linear_dgrad(dy, w, dx, relu_mask=None, n_contract=None, block_n=0):
+    """dx[M,K] = dy[M,N] @ w[K,N]^T, optionally masked by (relu_mask > 0) (tf ReluGrad of the producer)."""
+    m = dy.shape[0]
+    nn = dy.shape[1] if n_contract is None else n_contract
+    k = dx.shape[1]
+    d = nv.GemmDesc()
+    d.m, d.n, d.k, d.groups = m, k, nn, 1
+    d.a_mode, d.b_mode = nv.A_TILED_K, nv.B_TILED_K
+    d.a_ld, d.b_ld = _ld(dy), _ld(w)
+    d.c_ld = _ld(dx)
+    d.c_dtype = nv.DT_BF16 if dx.dtype == BF16 else nv.DT_F32
+    d.split_k = 1
+    d.block_n = block_n
+    if relu_mask is not None:
+        d.mask_ld = _ld(relu_mask)
+    nv.gemm(d, dy, w, dx, None, relu_mask)
+    return dx
+
+
+def linear_wgrad(x, dy, dw, split_k=1, n=None, block_n=0):
+    """dw[K,N] (fp32) += x[M,K]^T @ dy[M,N]; the contraction runs over the batch rows M (split-K red.add)."""
+    m, k = x.shape
+    n = dy.shape[1] if n is None else n
+    d = nv.GemmDesc()
+    d.m, d.n, d.k, d.groups = k, n, m, 1
+    d.a_mode, d.b_mode = nv.A_TILED_MN, nv.B_TILED_MN
+    d.a_ld, d.b_ld = _ld(x), _ld(dy)
+    d.c_ld = _ld(dw)
+    d.c_dtype = nv.DT_F32
+    d.c_atomic = 1
+    d.split_k = split_k
+    d.block_n = block_n
+    assert dw.dtype == F32
+    nv.gemm(d, x, dy, dw)
+    return dw
+
+
+# ----------------------------------------------------------------------------------------------------
+# convolutions: dcnn.conv (alexnet.py:15-31) and its gradients
+# ----------------------------------------------------------------------------------------------------
+def conv_fwd(spec, x, w_packed, bias, out, relu=True, block_n=0):
+    """out[N,P,Q,Cout] = act(conv2d_SAME(x[N,H,W,Cin], W) + bias); w_packed = bf16 [taps*cchunks*64, Cout]."""
+    n = x.shape[0]
+    d = nv.GemmDesc()
+    d.m, d.n, d.k, d.groups = n * spec.p * spec.q, spec.cout_g, spec.k_packed, spec.groups
+    d.a_mode, d.b_mode = nv.A_IM2COL_K, nv.B_TILED_MN
+    d.a_goff, d.b_goff, d.c_goff = spec.cin_g, spec.cout_g, spec.cout_g
+    d.b_ld = spec.cout
+    d.c_ld = spec.cout
+    d.c_dtype = nv.DT_BF16 if out.dtype == BF16 else nv.DT_F32
+    d.relu = 1 if relu else 0
+    d.split_k = 1
+    d.block_n = block_n
+    d.conv = spec.geom(n)
+    nv.gemm(d, x, w_packed, out, bias)
+    return out
+
+
+def conv_dgrad(spec, dy, w_hwio, dx, relu_mask=None, block_n=0):
+    """dx[N,H,W,Cin] = conv2d_backprop_input(dy[N,P,Q,Cout], W); w_hwio = bf16 [taps*cin_g, Cout] (HWIO as 2D)."""
+    n = dy.shape[0]
+    d = nv.GemmDesc()
+    d.m, d.n, d.k, d.groups = n * spec.h * spec.w, spec.cin_g, spec.taps * spec.cout_g, spec.groups
+    d.a_mode, d.b_mode = nv.A_IM2COL_K, nv.B_TILED_K
+    d.a_goff, d.b_goff, d.c_goff = spec.cout_g, spec.cout_g, spec.cin_g
+    d.b_ld = spec.cout
+    d.b_tap_stride = spec.cin_g
+    d.c_ld = spec.cin
+    d.c_dtype = nv.DT_BF16 if dx.dtype == BF16 else nv.DT_F32
+    d.split_k = 1
+    d.block_n = block_n
+    d.conv = spec.geom_dgrad(n)
+    if relu_mask is not None:
+        d.mask_ld = spec.cin
+    nv.gemm(d, dy, w_hwio, dx, None, relu_mask)
+    return dx
+
+
+def conv_wgrad(spec, x, dy, dw, split_k=1, block_n=0):
+    """dw[taps*cin_g, Cout] (fp32, HWIO as 2D) += conv2d_backprop_filter(x, dy); split-K over output pixels."""
+    n = x.shape[0]
+    d = nv.GemmDesc()
+    d.m, d.n, d.k, d.groups = spec.taps * spec.cin_g, spec.cout_g, n * spec.p * spec.q, spec.groups
+    d.a_mode, d.b_mode = nv.A_IM2COL_MN, nv.B_TILED_MN
+    d.a_goff, d.b_goff, d.c_goff = spec.cin_g, spec.cout_g, spec.cout_g
+    d.b_ld = spec.cout
+    d.c_ld = spec.cout
+    d.c_dtype = nv.DT_F32
+    d.c_atomic = 1
+    d.split_k = split_k
+    d.block_n = block_n
+    d.conv = spec.geom(n)
+    assert dw.dtype == F32
+    nv.gemm(d, x, dy, dw)
+    return dw
+
+
+def pack_conv_weight_host(spec, w_hwio):
+    """HWIO fp32 -> bf16 [taps*cchunks*64, Cout] with each tap's cin_g rows zero-padded to a 64 multiple."""
+    kh, kw, cin_g, cout = w_hwio.shape
+    w = w_hwio.reshape(kh * kw, cin_g, cout)
+    packed = torch.zeros(kh * kw, spec.cchunks * 64, cout, dtype=BF16, device=w_hwio.device)
+    packed[:, :cin_g, :] = w.to(BF16)
+    return packed.reshape(spec.k_packed, cout).contiguous()
