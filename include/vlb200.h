@@ -83,6 +83,109 @@ typedef struct vl_gemm_desc {
 int vl_gemm(const vl_gemm_desc* desc, const void* a, const void* b, void* c, const float* bias,
             const void* relu_mask, vl_stream_t stream);
 
+
+/* ------------------------------------------------------------------------------------------------
+ * Memory-bound kernels of the AlexNet encoder (HBM roofline).
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Input staging for conv1 (alexnet.py:76): frames [n][h][w][3] (uint8 with the per-channel mean subtracted
+ * here -- dataset_.py:521-530 -- when `is_u8`, else fp32 already mean-subtracted as fed by feeder.py:97-100)
+ * -> bf16 patch matrix col[n*p*q][k_ld], column (r*kw+s)*3+c, zero filled up to k_ld and outside the image
+ * (TF SAME padding). */
+int vl_conv1_patches(const void* frames, int is_u8, const float* mean3, void* col, int32_t n, int32_t h,
+                     int32_t w, int32_t kh, int32_t kw, int32_t stride, int32_t pad_top, int32_t pad_left,
+                     int32_t p, int32_t q, int32_t k_ld, vl_stream_t stream);
+
+/* tf.nn.local_response_normalization(depth_radius=2, alpha=2e-5, beta=.75, bias=1) (alexnet.py:85,126) over
+ * the channel axis of x[rows][c] (bf16). */
+int vl_lrn_fwd(const void* x, void* y, int64_t rows, int32_t c, int32_t radius, float alpha, float beta,
+               float bias, vl_stream_t stream);
+/* Gradient of the above w.r.t. x, multiplied by the ReLU mask (x > 0) of the producing conv (relu1/relu_2). */
+int vl_lrn_bwd(const void* x, const void* dy, void* dx, int64_t rows, int32_t c, int32_t radius, float alpha,
+               float beta, float bias, int32_t relu_mask, vl_stream_t stream);
+
+/* tf.nn.max_pool(ksize 3x3, stride 2, VALID) (alexnet.py:98,139,211) on NHWC bf16; `argmax` (uint8, window
+ * local index r*3+s of the first maximum) is kept for the gradient. */
+int vl_maxpool_fwd(const void* x, void* y, void* argmax, int32_t n, int32_t h, int32_t w, int32_t c,
+                   vl_stream_t stream);
+/* MaxPoolGrad: dx[n][h][w][c] = sum of dy over the windows whose argmax is (h,w); optional ReLU mask
+ * (relu_of > 0, same shape as dx) for pool5 whose input is relu5. */
+int vl_maxpool_bwd(const void* dy, const void* argmax, void* dx, const void* relu_of, int32_t n, int32_t h,
+                   int32_t w, int32_t c, vl_stream_t stream);
+
+/* bias gradient: out[c] += sum_rows dy[row][c]  (bf16 in, fp32 accumulate; `out` must be zeroed). */
+int vl_colsum(const void* dy, float* out, int64_t rows, int32_t c, int32_t ld, vl_stream_t stream);
+
+/* fp32 master weights -> bf16 operand copy: dst[(r/src_grp)*dst_grp + r%src_grp][col] = src[r][col], zero
+ * elsewhere (dst has dst_rows x dst_ld elements).  Used for the zero-padded conv1/conv2 filter matrices and
+ * for padding the class dimension of fc8/output_fc to a multiple of 8. */
+int vl_pack_bf16(const float* src, int32_t rows, int32_t cols, void* dst, int32_t dst_rows, int32_t dst_ld,
+                 int32_t src_grp, int32_t dst_grp, vl_stream_t stream);
+int vl_cast_f32_to_bf16(const float* src, void* dst, int64_t n, vl_stream_t stream);
+/* dst[cols][rows] = src[rows][cols]^T (fp32): recurrent weights for the BPTT kernel. */
+int vl_transpose_f32(const float* src, float* dst, int32_t rows, int32_t cols, vl_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * LSTM (models/lstm/lstm.py:9-20,102-143): MultiRNNCell([BasicLSTMCell]) under dynamic_rnn, zero state.
+ * gx[b*t_len+t][4h] (fp32) = x_t * kernel[:d] + bias, produced by vl_gemm; this kernel runs the recurrent
+ * part for all timesteps: g = gx + h_{t-1} * w_h ; i,j,f,o = split(g) ; c = c*sig(f+forget_bias)+sig(i)*tanh(j);
+ * h = tanh(c)*sig(o).  Saved for BPTT: acts[b][t][4h] (post-nonlinearity i,j,f,o), cs[b][t][h] (c_t),
+ * h_seq[b][t][h] fp32 outputs, h_prev_bf16[b][t][h] (h_{t-1}, the filter-gradient operand).
+ * ---------------------------------------------------------------------------------------------- */
+int vl_lstm_fwd(const float* gx, const float* w_h, float* acts, float* cs, float* h_seq, void* h_seq_bf16,
+                void* h_prev_bf16, int32_t batch, int32_t t_len, int32_t hidden, float forget_bias,
+                vl_stream_t stream);
+/* BPTT: dh_seq[b][t][h] (fp32) is d(loss)/d(h_t) from above; writes dg[b*t_len+t][4h] (bf16, gradient w.r.t.
+ * the pre-activation gates) which feeds the tensor-core data/filter gradient GEMMs.  w_h_t = w_h^T [4h][h]. */
+int vl_lstm_bwd(const float* dh_seq, const float* acts, const float* cs, const float* w_h_t, void* dg,
+                int32_t batch, int32_t t_len, int32_t hidden, vl_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Pooling / loss head.
+ * ---------------------------------------------------------------------------------------------- */
+enum { VL_POOL_AVG = 0, VL_POOL_LAST = 1, VL_POOL_MAX = 2 /* extension: not in the reference */ };
+
+/* Segmented reduction over rows: y[s][d] = pool(x[seg[s] .. seg[s+1])[d]).  Serves apply_temporal_fusion
+ * (tf_util.py:4-30), aggregate_clip_vectors (tf_util.py:126-133) and the clip->video fusion of
+ * val.py:158-167.  Rows are accumulated sequentially in fp32 and divided once, i.e. the operation order of
+ * numpy's mean(axis=0), so video-level results are bit-exact with the reference's host code.
+ * seg == NULL means equal segments of `fixed_len` rows. */
+int vl_segment_pool_fwd(const float* x, const int32_t* seg, int32_t fixed_len, int32_t num_seg, int32_t d,
+                        int32_t mode, float* y, void* y_bf16, vl_stream_t stream);
+int vl_segment_pool_bwd(const float* dy, const int32_t* seg, int32_t fixed_len, int32_t num_seg, int32_t d,
+                        int32_t mode, float* dx, vl_stream_t stream);
+
+/* tf.nn.dropout (lstm.py:50-56): y = x * mask, mask in {0, 1/keep}.  The mask is generated on device from
+ * (seed, offset) with Philox4x32-10 and returned so that the backward pass (and the oracle) can reuse it. */
+int vl_dropout_mask(float* mask, int64_t n, float keep_prob, uint64_t seed, uint64_t offset, vl_stream_t stream);
+int vl_mul(const float* a, const float* b, float* y, void* y_bf16, int64_t n, vl_stream_t stream);
+
+/* mean(softmax_cross_entropy_with_logits) (train.py:121-123) + accuracy (train.py:145-147) + d(loss)/d(logits).
+ * logits[rows][c] fp32, labels[rows][c] int32 one/multi-hot; row_loss is a scratch/result buffer of 2*rows floats
+ * (per-row loss, then per-row correct flag); out_scalars[0] = mean loss over `rows`, [1] = #correct;
+ * dlogits = (softmax * sum(labels) - labels) * grad_scale  (grad_scale = 1/global_rows). */
+int vl_softmax_ce(const float* logits, const int32_t* labels, int32_t rows, int32_t c, float grad_scale,
+                  float* row_loss, float* out_scalars, float* dlogits, void* dlogits_bf16, int32_t dl_ld,
+                  vl_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Optimiser (train.py:199-222) on one flat fp32 parameter / gradient arena.
+ * seg_offsets[num_vars+1] (DEVICE array) delimit the variables inside the arena of n floats.
+ * vl_grad_sqnorms writes sum(g^2) per variable (fp32).
+ * vl_sgd_update / vl_adam_update apply  g' = g * clip_scale  where clip_scale = clip/max(gnorm, clip) is read
+ * from DEVICE memory (scale_dev[0]) so the step needs no host sync.
+ * ---------------------------------------------------------------------------------------------- */
+int vl_grad_sqnorms(const float* grads, int64_t n, const int64_t* seg_offsets, int32_t num_vars, float* sqnorms,
+                    vl_stream_t stream);
+/* scalars[0]=global norm, [1]=clip scale, [2]=mean_i ||g_i * scale||  (grads_norm summary). clip<=0: no clip. */
+int vl_clip_scalars(const float* sqnorms, int32_t num_vars, float clip_norm, float grad_prescale, float* scalars,
+                    vl_stream_t stream);
+int vl_sgd_update(float* params, const float* grads, int64_t n, float lr, const float* scalars,
+                  float grad_prescale, vl_stream_t stream);
+int vl_adam_update(float* params, const float* grads, float* m, float* v, int64_t n, float lr, float beta1,
+                   float beta2, float eps, int32_t step, const float* scalars, float grad_prescale,
+                   vl_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -55,8 +55,41 @@ def _declare(L):
     L.vl_version.restype = i32
     L.vl_device_sm_count.restype = i32
     L.vl_launch_count.restype = i64
-    L.vl_gemm.restype = i32
-    L.vl_gemm.argtypes = [ctypes.POINTER(GemmDesc), vp, vp, vp, vp, vp, vp]
+    u64 = ctypes.c_uint64
+    sigs = {
+        "vl_gemm": [ctypes.POINTER(GemmDesc), vp, vp, vp, vp, vp, vp],
+        "vl_conv1_patches": [vp, i32, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp],
+        "vl_lrn_fwd": [vp, vp, i64, i32, i32, f32, f32, f32, vp],
+        "vl_lrn_bwd": [vp, vp, vp, i64, i32, i32, f32, f32, f32, i32, vp],
+        "vl_maxpool_fwd": [vp, vp, vp, i32, i32, i32, i32, vp],
+        "vl_maxpool_bwd": [vp, vp, vp, vp, i32, i32, i32, i32, vp],
+        "vl_colsum": [vp, vp, i64, i32, i32, vp],
+        "vl_pack_bf16": [vp, i32, i32, vp, i32, i32, i32, i32, vp],
+        "vl_cast_f32_to_bf16": [vp, vp, i64, vp],
+        "vl_transpose_f32": [vp, vp, i32, i32, vp],
+        "vl_lstm_fwd": [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, f32, vp],
+        "vl_lstm_bwd": [vp, vp, vp, vp, vp, i32, i32, i32, vp],
+        "vl_segment_pool_fwd": [vp, vp, i32, i32, i32, i32, vp, vp, vp],
+        "vl_segment_pool_bwd": [vp, vp, i32, i32, i32, i32, vp, vp],
+        "vl_dropout_mask": [vp, i64, f32, u64, u64, vp],
+        "vl_mul": [vp, vp, vp, vp, i64, vp],
+        "vl_softmax_ce": [vp, vp, i32, i32, f32, vp, vp, vp, vp, i32, vp],
+        "vl_grad_sqnorms": [vp, i64, vp, i32, vp, vp],
+        "vl_clip_scalars": [vp, i32, f32, f32, vp, vp],
+        "vl_sgd_update": [vp, vp, i64, f32, vp, f32, vp],
+        "vl_adam_update": [vp, vp, vp, vp, i64, f32, f32, f32, f32, i32, vp, f32, vp],
+    }
+    for name, argtypes in sigs.items():
+        fn = getattr(L, name)
+        fn.restype = i32
+        fn.argtypes = argtypes
+
+
+EXPORTS = ["vl_last_error", "vl_version", "vl_device_sm_count", "vl_launch_count", "vl_gemm", "vl_conv1_patches",
+           "vl_lrn_fwd", "vl_lrn_bwd", "vl_maxpool_fwd", "vl_maxpool_bwd", "vl_colsum", "vl_pack_bf16",
+           "vl_cast_f32_to_bf16", "vl_transpose_f32", "vl_lstm_fwd", "vl_lstm_bwd", "vl_segment_pool_fwd",
+           "vl_segment_pool_bwd", "vl_dropout_mask", "vl_mul", "vl_softmax_ce", "vl_grad_sqnorms",
+           "vl_clip_scalars", "vl_sgd_update", "vl_adam_update"]
 
 
 def check(status):
@@ -76,3 +109,16 @@ def stream_handle():
 
 def gemm(desc, a, b, c, bias=None, relu_mask=None):
     check(lib().vl_gemm(ctypes.byref(desc), ptr(a), ptr(b), ptr(c), ptr(bias), ptr(relu_mask), stream_handle()))
+
+
+def call(name, *args):
+    """Invoke `name(*args, stream)` on the current torch stream and raise on a non-zero status."""
+    conv = []
+    for a in args:
+        if a is None:
+            conv.append(None)
+        elif hasattr(a, "data_ptr"):
+            conv.append(ctypes.c_void_p(a.data_ptr()))
+        else:
+            conv.append(a)
+    check(getattr(lib(), name)(*conv, stream_handle()))

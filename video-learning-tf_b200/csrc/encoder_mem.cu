@@ -1,0 +1,518 @@
+// HBM-bound kernels of the AlexNet encoder: conv1 patch staging, LRN, 3x3/2 max-pool, bias gradients and
+// the fp32 -> bf16 operand packing.  All loads/stores are 16-byte vectors over the channel axis (NHWC), grids
+// are plain 1-D sweeps (these kernels have no reuse to tile for; they are judged on achieved GB/s).
+//
+// Reference call sites: models/alexnet/alexnet.py:76 (conv1 input), :85-89,:126-130 (LRN), :98,:139,:211
+// (max_pool), bias_add gradients of :31, make_w_b (:40-46) variables feeding the tensor-core operands.
+#include "common.cuh"
+#include "../../include/vlb200.h"
+
+#include <atomic>
+
+namespace vl {
+extern std::atomic<long long> g_launches;
+}
+
+namespace {
+
+typedef __nv_bfloat16 bf16;
+
+struct alignas(16) Bf16x8 {
+  __nv_bfloat162 v[4];
+};
+
+__device__ __forceinline__ void unpack8(const Bf16x8& in, float (&f)[8]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __bfloat1622float2(in.v[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ Bf16x8 pack8(const float (&f)[8]) {
+  Bf16x8 o;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) o.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return o;
+}
+
+// ------------------------------------------------------------------------------------------------
+// conv1 patch matrix
+// ------------------------------------------------------------------------------------------------
+template <bool U8>
+__global__ void conv1_patches_kernel(const void* __restrict__ frames_, const float* __restrict__ mean3,
+                                     bf16* __restrict__ col, int n, int h, int w, int kh, int kw, int stride,
+                                     int pad_top, int pad_left, int p, int q, int k_ld, long long total_chunks) {
+  const int chunks_per_row = k_ld >> 3;
+  const int kvalid = kh * kw * 3;
+  float m0 = 0.f, m1 = 0.f, m2 = 0.f;
+  if (U8 && mean3 != nullptr) {
+    m0 = mean3[0];
+    m1 = mean3[1];
+    m2 = mean3[2];
+  }
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total_chunks;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long row = idx / chunks_per_row;
+    const int ch = (int)(idx - row * chunks_per_row);
+    const int qq = (int)(row % q);
+    const long long t = row / q;
+    const int pp = (int)(t % p);
+    const int nn = (int)(t / p);
+    const int y0 = pp * stride - pad_top;
+    const int x0 = qq * stride - pad_left;
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int kk = ch * 8 + j;
+      float v = 0.f;
+      if (kk < kvalid) {
+        const int tap = kk / 3;
+        const int c = kk - tap * 3;
+        const int r = tap / kw;
+        const int s = tap - r * kw;
+        const int y = y0 + r, x = x0 + s;
+        if (y >= 0 && y < h && x >= 0 && x < w) {
+          const long long off = (((long long)nn * h + y) * w + x) * 3 + c;
+          if (U8) {
+            v = (float)reinterpret_cast<const uint8_t*>(frames_)[off] - (c == 0 ? m0 : (c == 1 ? m1 : m2));
+          } else {
+            v = reinterpret_cast<const float*>(frames_)[off];
+          }
+        }
+      }
+      f[j] = v;
+    }
+    *reinterpret_cast<Bf16x8*>(col + row * k_ld + ch * 8) = pack8(f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LRN
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float pow_neg_beta(float s, float beta) {
+  if (beta == 0.75f) {
+    float r = rsqrtf(s);
+    return r * sqrtf(r);
+  }
+  return __powf(s, -beta);
+}
+
+template <int R>
+__global__ void lrn_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, long long rows, int c, int radius_rt,
+                               float alpha, float beta, float bias, long long total_chunks) {
+  const int radius = R > 0 ? R : radius_rt;  // R = 2 (the reference's value) keeps the window in registers
+  const int cpr = c >> 3;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total_chunks;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long row = idx / cpr;
+    const int c0 = (int)(idx - row * cpr) * 8;
+    const bf16* xr = x + row * c;
+    float v[8 + 8];  // window [c0-4, c0+12), only [c0-radius, c0+8+radius) is used (radius <= 4)
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = 0.f;
+    {
+      float own[8];
+      unpack8(*reinterpret_cast<const Bf16x8*>(xr + c0), own);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[4 + j] = own[j];
+    }
+#pragma unroll
+    for (int j = 1; j <= 4; ++j) {
+      if (j <= radius) {
+        if (c0 - j >= 0) v[4 - j] = __bfloat162float(xr[c0 - j]);
+        if (c0 + 7 + j < c) v[11 + j] = __bfloat162float(xr[c0 + 7 + j]);
+      }
+    }
+    float out[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float acc = 0.f;
+#pragma unroll
+      for (int o = -4; o <= 4; ++o)
+        if (o >= -radius && o <= radius) acc += v[4 + j + o] * v[4 + j + o];
+      const float s = bias + alpha * acc;
+      out[j] = v[4 + j] * pow_neg_beta(s, beta);
+    }
+    *reinterpret_cast<Bf16x8*>(y + row * c + c0) = pack8(out);
+  }
+}
+
+// radius is fixed to 2 in the gradient kernel (the only value the reference uses).
+__global__ void lrn_bwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy, bf16* __restrict__ dx,
+                               long long rows, int c, float alpha, float beta, float bias, int relu_mask,
+                               long long total_chunks) {
+  const int cpr = c >> 3;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total_chunks;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long row = idx / cpr;
+    const int c0 = (int)(idx - row * cpr) * 8;
+    const bf16* xr = x + row * c;
+    const bf16* gr = dy + row * c;
+    float xv[16];  // channels [c0-4, c0+12)
+    float gv[12];  // channels [c0-2, c0+10)
+#pragma unroll
+    for (int j = 0; j < 16; ++j) xv[j] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 12; ++j) gv[j] = 0.f;
+    {
+      float own[8];
+      unpack8(*reinterpret_cast<const Bf16x8*>(xr + c0), own);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) xv[4 + j] = own[j];
+      unpack8(*reinterpret_cast<const Bf16x8*>(gr + c0), own);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) gv[2 + j] = own[j];
+    }
+#pragma unroll
+    for (int j = 1; j <= 4; ++j) {
+      if (c0 - j >= 0) xv[4 - j] = __bfloat162float(xr[c0 - j]);
+      if (c0 + 7 + j < c) xv[11 + j] = __bfloat162float(xr[c0 + 7 + j]);
+    }
+#pragma unroll
+    for (int j = 1; j <= 2; ++j) {
+      if (c0 - j >= 0) gv[2 - j] = __bfloat162float(gr[c0 - j]);
+      if (c0 + 7 + j < c) gv[9 + j] = __bfloat162float(gr[c0 + 7 + j]);
+    }
+    // t_d = dy_d * x_d * s_d^(-beta-1) for d in [c0-2, c0+10); s_i^-beta for the 8 own channels
+    float t[12];
+    float sp[8];
+#pragma unroll
+    for (int d = 0; d < 12; ++d) {
+      // channel c0-2+d sits at xv[2+d]; its window is xv[d .. d+4]
+      float acc = 0.f;
+#pragma unroll
+      for (int o = 0; o < 5; ++o) acc += xv[d + o] * xv[d + o];
+      const float s = bias + alpha * acc;
+      const float pw = pow_neg_beta(s, beta);
+      t[d] = gv[d] * xv[2 + d] * pw / s;
+      if (d >= 2 && d < 10) sp[d - 2] = pw;
+    }
+    float out[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float sum = t[j] + t[j + 1] + t[j + 2] + t[j + 3] + t[j + 4];
+      float g = gv[2 + j] * sp[j] - 2.0f * alpha * beta * xv[4 + j] * sum;
+      if (relu_mask && !(xv[4 + j] > 0.f)) g = 0.f;
+      out[j] = g;
+    }
+    *reinterpret_cast<Bf16x8*>(dx + row * c + c0) = pack8(out);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// max-pool 3x3 stride 2 VALID
+// ------------------------------------------------------------------------------------------------
+__global__ void maxpool_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, uint8_t* __restrict__ arg, int n,
+                                   int h, int w, int c, int p, int q, long long total_chunks) {
+  const int cpr = c >> 3;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total_chunks;
+       idx += (long long)gridDim.x * blockDim.x) {
+    long long pix = idx / cpr;
+    const int c0 = (int)(idx - pix * cpr) * 8;
+    const int qq = (int)(pix % q);
+    const long long t = pix / q;
+    const int pp = (int)(t % p);
+    const int nn = (int)(t / p);
+    float best[8];
+    int bi[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      best[j] = -INFINITY;
+      bi[j] = 0;
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const bf16* src = x + (((long long)nn * h + (pp * 2 + r)) * w + (qq * 2 + s)) * c + c0;
+        float v[8];
+        unpack8(*reinterpret_cast<const Bf16x8*>(src), v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (v[j] > best[j]) {  // strict: the first maximum in (h, w) scan order wins, like TF
+            best[j] = v[j];
+            bi[j] = r * 3 + s;
+          }
+        }
+      }
+    }
+    *reinterpret_cast<Bf16x8*>(y + pix * c + c0) = pack8(best);
+    if (arg != nullptr) {
+      uint32_t lo = bi[0] | (bi[1] << 8) | (bi[2] << 16) | (bi[3] << 24);
+      uint32_t hi = bi[4] | (bi[5] << 8) | (bi[6] << 16) | (bi[7] << 24);
+      *reinterpret_cast<uint2*>(arg + pix * c + c0) = make_uint2(lo, hi);
+    }
+  }
+}
+
+__global__ void maxpool_bwd_kernel(const bf16* __restrict__ dy, const uint8_t* __restrict__ arg, bf16* __restrict__ dx,
+                                   const bf16* __restrict__ relu_of, int n, int h, int w, int c, int p, int q,
+                                   long long total_chunks) {
+  const int cpr = c >> 3;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total_chunks;
+       idx += (long long)gridDim.x * blockDim.x) {
+    long long pix = idx / cpr;
+    const int c0 = (int)(idx - pix * cpr) * 8;
+    const int ww = (int)(pix % w);
+    const long long t = pix / w;
+    const int hh = (int)(t % h);
+    const int nn = (int)(t / h);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    const int p_lo = max(0, (hh - 1) >> 1), p_hi = min(p - 1, hh >> 1);
+    const int q_lo = max(0, (ww - 1) >> 1), q_hi = min(q - 1, ww >> 1);
+    for (int pp = p_lo; pp <= p_hi; ++pp) {
+      const int r = hh - 2 * pp;
+      if (r < 0 || r > 2) continue;
+      for (int qq = q_lo; qq <= q_hi; ++qq) {
+        const int s = ww - 2 * qq;
+        if (s < 0 || s > 2) continue;
+        const long long opix = ((long long)nn * p + pp) * q + qq;
+        const uint2 a = *reinterpret_cast<const uint2*>(arg + opix * c + c0);
+        float g[8];
+        unpack8(*reinterpret_cast<const Bf16x8*>(dy + opix * c + c0), g);
+        const uint32_t code = r * 3 + s;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t aj = ((j < 4 ? a.x : a.y) >> (8 * (j & 3))) & 0xffu;
+          if (aj == code) acc[j] += g[j];
+        }
+      }
+    }
+    if (relu_of != nullptr) {
+      float m[8];
+      unpack8(*reinterpret_cast<const Bf16x8*>(relu_of + pix * c + c0), m);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (!(m[j] > 0.f)) acc[j] = 0.f;
+    }
+    *reinterpret_cast<Bf16x8*>(dx + pix * c + c0) = pack8(acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// column sums (bias gradients)
+// ------------------------------------------------------------------------------------------------
+constexpr int COLSUM_THREADS = 256;
+
+__global__ void colsum_kernel(const bf16* __restrict__ dy, float* __restrict__ out, long long rows, int c, int ld,
+                              int ct, int ty_count, long long rows_per_block) {
+  __shared__ float2 red[COLSUM_THREADS];
+  const int tx = threadIdx.x % ct;
+  const int ty = threadIdx.x / ct;
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  const long long r1 = min(rows, r0 + rows_per_block);
+  for (int cbase = 0; cbase < c; cbase += 2 * ct) {
+    const int col = cbase + 2 * tx;
+    float2 acc = make_float2(0.f, 0.f);
+    if (ty < ty_count && col < c) {
+      if (col + 1 < c && (ld & 1) == 0) {
+        for (long long r = r0 + ty; r < r1; r += ty_count) {
+          float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(dy + r * ld + col));
+          acc.x += v.x;
+          acc.y += v.y;
+        }
+      } else {
+        for (long long r = r0 + ty; r < r1; r += ty_count) {
+          acc.x += __bfloat162float(dy[r * ld + col]);
+          if (col + 1 < c) acc.y += __bfloat162float(dy[r * ld + col + 1]);
+        }
+      }
+    }
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    if (ty == 0 && col < c) {
+      float2 s = red[tx];
+      for (int j = 1; j < ty_count; ++j) {
+        s.x += red[j * ct + tx].x;
+        s.y += red[j * ct + tx].y;
+      }
+      atomicAdd(out + col, s.x);
+      if (col + 1 < c) atomicAdd(out + col + 1, s.y);
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// operand packing
+// ------------------------------------------------------------------------------------------------
+__global__ void pack_bf16_kernel(const float* __restrict__ src, int rows, int cols, bf16* __restrict__ dst,
+                                 int dst_rows, int dst_ld, int src_grp, int dst_grp, long long total) {
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int R = (int)(idx / dst_ld);
+    const int col = (int)(idx - (long long)R * dst_ld);
+    const int grp = R / dst_grp;
+    const int rr = R - grp * dst_grp;
+    float v = 0.f;
+    const long long r = (long long)grp * src_grp + rr;
+    if (rr < src_grp && col < cols && r < rows) v = src[r * cols + col];
+    dst[idx] = __float2bfloat16_rn(v);
+  }
+}
+
+__global__ void cast_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long long n) {
+  const long long n8 = n >> 3;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n8;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const float4 a = reinterpret_cast<const float4*>(src)[2 * idx];
+    const float4 b = reinterpret_cast<const float4*>(src)[2 * idx + 1];
+    float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    reinterpret_cast<Bf16x8*>(dst)[idx] = pack8(f);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    for (long long i = n8 << 3; i < n; ++i) dst[i] = __float2bfloat16_rn(src[i]);
+}
+
+// dst[c][r] = src[r][c]  (fp32, 32x32 smem tiles; used for the recurrent weights w_h -> w_h^T of the BPTT kernel)
+__global__ void transpose_f32_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    if (r < rows && c < cols) tile[i][threadIdx.x] = src[(long long)r * cols + c];
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (r < rows && c < cols) dst[(long long)c * rows + r] = tile[threadIdx.x][i];
+  }
+}
+
+int sweep_grid(long long work_items, int block) {
+  long long g = (work_items + block - 1) / block;
+  long long cap = (long long)vl::num_sms() * 16;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+}  // namespace
+
+#define VL_LAUNCHED()            \
+  do {                           \
+    vl::g_launches.fetch_add(1); \
+    VL_CHECK_CUDA(cudaGetLastError()); \
+  } while (0)
+
+extern "C" int vl_conv1_patches(const void* frames, int is_u8, const float* mean3, void* col, int32_t n, int32_t h,
+                                int32_t w, int32_t kh, int32_t kw, int32_t stride, int32_t pad_top, int32_t pad_left,
+                                int32_t p, int32_t q, int32_t k_ld, vl_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  VL_REQUIRE(frames && col && k_ld % 8 == 0 && k_ld >= kh * kw * 3, "vl_conv1_patches: bad arguments");
+  const long long total = (long long)n * p * q * (k_ld / 8);
+  const int block = 256;
+  if (is_u8)
+    conv1_patches_kernel<true><<<sweep_grid(total, block), block, 0, stream>>>(
+        frames, mean3, reinterpret_cast<bf16*>(col), n, h, w, kh, kw, stride, pad_top, pad_left, p, q, k_ld, total);
+  else
+    conv1_patches_kernel<false><<<sweep_grid(total, block), block, 0, stream>>>(
+        frames, mean3, reinterpret_cast<bf16*>(col), n, h, w, kh, kw, stride, pad_top, pad_left, p, q, k_ld, total);
+  VL_LAUNCHED();
+  return 0;
+}
+
+extern "C" int vl_lrn_fwd(const void* x, void* y, int64_t rows, int32_t c, int32_t radius, float alpha, float beta,
+                          float bias, vl_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  VL_REQUIRE(x && y && c % 8 == 0 && radius >= 0 && radius <= 4, "vl_lrn_fwd: c must be a multiple of 8, radius <= 4");
+  const long long total = rows * (c / 8);
+  if (radius == 2)
+    lrn_fwd_kernel<2><<<sweep_grid(total, 256), 256, 0, stream>>>(
+        reinterpret_cast<const bf16*>(x), reinterpret_cast<bf16*>(y), rows, c, radius, alpha, beta, bias, total);
+  else
+    lrn_fwd_kernel<0><<<sweep_grid(total, 256), 256, 0, stream>>>(
+        reinterpret_cast<const bf16*>(x), reinterpret_cast<bf16*>(y), rows, c, radius, alpha, beta, bias, total);
+  VL_LAUNCHED();
+  return 0;
+}
+
+extern "C" int vl_lrn_bwd(const void* x, const void* dy, void* dx, int64_t rows, int32_t c, int32_t radius,
+                          float alpha, float beta, float bias, int32_t relu_mask, vl_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  VL_REQUIRE(x && dy && dx && c % 8 == 0, "vl_lrn_bwd: c must be a multiple of 8");
+  VL_REQUIRE(radius == 2, "vl_lrn_bwd: only depth_radius 2 (alexnet.py:80,121) is implemented");
+  const long long total = rows * (c / 8);
+  lrn_bwd_kernel<<<sweep_grid(total, 256), 256, 0, stream>>>(
+      reinterpret_cast<const bf16*>(x), reinterpret_cast<const bf16*>(dy), reinterpret_cast<bf16*>(dx), rows, c, alpha,
+      beta, bias, relu_mask, total);
+  VL_LAUNCHED();
+  return 0;
+}
+
+extern "C" int vl_maxpool_fwd(const void* x, void* y, void* argmax, int32_t n, int32_t h, int32_t w, int32_t c,
+                              vl_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  VL_REQUIRE(x && y && c % 8 == 0 && h >= 3 && w >= 3, "vl_maxpool_fwd: bad arguments");
+  const int p = (h - 3) / 2 + 1, q = (w - 3) / 2 + 1;
+  const long long total = (long long)n * p * q * (c / 8);
+  maxpool_fwd_kernel<<<sweep_grid(total, 256), 256, 0, stream>>>(reinterpret_cast<const bf16*>(x),
+                                                                 reinterpret_cast<bf16*>(y),
+                                                                 reinterpret_cast<uint8_t*>(argmax), n, h, w, c, p, q,
+                                                                 total);
+  VL_LAUNCHED();
+  return 0;
+}
+
+extern "C" int vl_maxpool_bwd(const void* dy, const void* argmax, void* dx, const void* relu_of, int32_t n, int32_t h,
+                              int32_t w, int32_t c, vl_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  VL_REQUIRE(dy && argmax && dx && c % 8 == 0, "vl_maxpool_bwd: bad arguments");
+  const int p = (h - 3) / 2 + 1, q = (w - 3) / 2 + 1;
+  const long long total = (long long)n * h * w * (c / 8);
+  maxpool_bwd_kernel<<<sweep_grid(total, 256), 256, 0, stream>>>(
+      reinterpret_cast<const bf16*>(dy), reinterpret_cast<const uint8_t*>(argmax), reinterpret_cast<bf16*>(dx),
+      reinterpret_cast<const bf16*>(relu_of), n, h, w, c, p, q, total);
+  VL_LAUNCHED();
+  return 0;
+}
+
+extern "C" int vl_colsum(const void* dy, float* out, int64_t rows, int32_t c, int32_t ld, vl_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  VL_REQUIRE(dy && out && rows > 0 && c > 0 && ld >= c, "vl_colsum: bad arguments");
+  int ct = (c + 1) / 2;
+  if (ct > 128) ct = 128;
+  int ty = COLSUM_THREADS / ct;
+  long long blocks = (long long)vl::num_sms() * 4;
+  long long min_rows = (long long)ty * 8;
+  long long rpb = (rows + blocks - 1) / blocks;
+  if (rpb < min_rows) rpb = min_rows;
+  blocks = (rows + rpb - 1) / rpb;
+  colsum_kernel<<<(int)blocks, COLSUM_THREADS, 0, stream>>>(reinterpret_cast<const bf16*>(dy), out, rows, c, ld, ct, ty,
+                                                            rpb);
+  VL_LAUNCHED();
+  return 0;
+}
+
+extern "C" int vl_pack_bf16(const float* src, int32_t rows, int32_t cols, void* dst, int32_t dst_rows, int32_t dst_ld,
+                            int32_t src_grp, int32_t dst_grp, vl_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  VL_REQUIRE(src && dst && src_grp > 0 && dst_grp >= src_grp && dst_ld >= cols, "vl_pack_bf16: bad arguments");
+  const long long total = (long long)dst_rows * dst_ld;
+  pack_bf16_kernel<<<sweep_grid(total, 256), 256, 0, stream>>>(src, rows, cols, reinterpret_cast<bf16*>(dst), dst_rows,
+                                                               dst_ld, src_grp, dst_grp, total);
+  VL_LAUNCHED();
+  return 0;
+}
+
+extern "C" int vl_cast_f32_to_bf16(const float* src, void* dst, int64_t n, vl_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  VL_REQUIRE(src && dst && n >= 0, "vl_cast_f32_to_bf16: bad arguments");
+  VL_REQUIRE((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0,
+             "vl_cast_f32_to_bf16: pointers must be 16B aligned");
+  cast_bf16_kernel<<<sweep_grid((n + 7) / 8, 256), 256, 0, stream>>>(src, reinterpret_cast<bf16*>(dst), n);
+  VL_LAUNCHED();
+  return 0;
+}
+
+extern "C" int vl_transpose_f32(const float* src, float* dst, int32_t rows, int32_t cols, vl_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  VL_REQUIRE(src && dst && rows > 0 && cols > 0, "vl_transpose_f32: bad arguments");
+  dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
+  transpose_f32_kernel<<<grid, block, 0, stream>>>(src, dst, rows, cols);
+  VL_LAUNCHED();
+  return 0;
+}

@@ -1,0 +1,634 @@
+"""Engine: the device-side replacement of the two `sess.run` calls of the reference.
+
+  run_task.py:44   sess.run([summaries, loss, lr, global_step, optimizer], feed_dict)  -> Engine.train_step
+  run_task.py:95   sess.run(model.logits, feed_dict)                                   -> Engine.forward
+
+The engine owns one flat fp32 parameter arena (variables keyed by the reference's TF names), the
+bf16 operand copies the tensor-core kernels read, all activation buffers, and the launch sequence of the
+hand-written kernels (csrc/) through the C-ABI.  PyTorch provides device memory, streams and (for W > 1) the
+NCCL process group; it performs no arithmetic of the model.
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import _native as nv
+from . import kernels as K
+
+BF16, F32 = torch.bfloat16, torch.float32
+POOL = {"avg": 0, "last": 1, "max": 2}
+LRN = dict(radius=2, alpha=2e-05, beta=0.75, bias=1.0)  # alexnet.py:80-89,121-130
+
+
+def _align(n, a=64):
+    return -(-n // a) * a
+
+
+class EngineConfig(object):
+    """The subset of `Settings` (settings_.py) the device path depends on."""
+
+    def __init__(self, num_classes=101, fpc=16, workflow="lrcn", frame_encoding_layer="fc7", lstm_hidden=256,
+                 lstm_layers=1, fusion="avg", optimizer="sgd", clip_norm=None, dropout_keep_prob=0.0,
+                 height=227, width=227, mean=None, seed=1234):
+        assert workflow in ("lrcn", "singleframe")
+        self.num_classes = int(num_classes)
+        self.fpc = int(fpc)
+        self.workflow = workflow
+        self.frame_encoding_layer = frame_encoding_layer if workflow == "lrcn" else "fc8"
+        self.lstm_hidden = int(lstm_hidden)
+        self.lstm_layers = int(lstm_layers)
+        self.fusion = fusion
+        self.optimizer = optimizer
+        self.clip_norm = clip_norm
+        self.dropout_keep_prob = float(dropout_keep_prob or 0.0)
+        self.height, self.width = int(height), int(width)
+        self.mean = tuple(mean) if mean is not None else None
+        self.seed = int(seed)
+        if fusion not in ("avg", "last"):
+            raise ValueError("Undefined frame fusion type : %s" % fusion)
+        if optimizer not in ("sgd", "adam"):
+            raise ValueError("Undefined optimizer %s" % optimizer)
+
+
+def variable_shapes(cfg):
+    """(name, shape) of every trainable variable in the reference's creation order."""
+    sp = encoder_specs(cfg.height, cfg.width)
+    out = []
+    for name in ("conv1", "conv2", "conv3", "conv4", "conv5"):
+        s = sp[name]
+        out.append(("dcnn/%sW" % name, (s.kh, s.kw, s.cin_g, s.cout)))
+        out.append(("dcnn/%sb" % name, (s.cout,)))
+    out.append(("dcnn/fc6W", (sp["flat"], 4096)))
+    out.append(("dcnn/fc6b", (4096,)))
+    feat = 4096
+    fl = cfg.frame_encoding_layer
+    if fl != "fc6":
+        out.append(("dcnn/fc7W", (4096, 4096)))
+        out.append(("dcnn/fc7b", (4096,)))
+        if fl != "fc7":
+            out.append(("dcnn/fc8W", (4096, cfg.num_classes)))
+            out.append(("dcnn/fc8b", (cfg.num_classes,)))
+            feat = cfg.num_classes
+    if cfg.workflow == "lrcn":
+        d_in = feat
+        for layer in range(cfg.lstm_layers):
+            out.append(("rnn/multi_rnn_cell/cell_%d/basic_lstm_cell/kernel" % layer,
+                        (d_in + cfg.lstm_hidden, 4 * cfg.lstm_hidden)))
+            out.append(("rnn/multi_rnn_cell/cell_%d/basic_lstm_cell/bias" % layer, (4 * cfg.lstm_hidden,)))
+            d_in = cfg.lstm_hidden
+        if cfg.lstm_hidden != cfg.num_classes:
+            out.append(("output_fc_w", (cfg.lstm_hidden, cfg.num_classes)))
+            out.append(("output_fc_b", (cfg.num_classes,)))
+    return out
+
+
+def encoder_specs(h, w):
+    """Layer geometry of dcnn.create (alexnet.py:60-211) for an h x w input."""
+    sp = {}
+    sp["conv1"] = K.ConvSpec(h, w, 3, 96, 11, 11, 4, 1)
+    p1h, p1w = K.valid_out(sp["conv1"].p, 3, 2), K.valid_out(sp["conv1"].q, 3, 2)
+    sp["conv2"] = K.ConvSpec(p1h, p1w, 96, 256, 5, 5, 1, 2)
+    p2h, p2w = K.valid_out(sp["conv2"].p, 3, 2), K.valid_out(sp["conv2"].q, 3, 2)
+    sp["conv3"] = K.ConvSpec(p2h, p2w, 256, 384, 3, 3, 1, 1)
+    sp["conv4"] = K.ConvSpec(p2h, p2w, 384, 384, 3, 3, 1, 2)
+    sp["conv5"] = K.ConvSpec(p2h, p2w, 384, 256, 3, 3, 1, 2)
+    p5h, p5w = K.valid_out(p2h, 3, 2), K.valid_out(p2w, 3, 2)
+    sp["pool1"] = (p1h, p1w)
+    sp["pool2"] = (p2h, p2w)
+    sp["pool5"] = (p5h, p5w)
+    sp["flat"] = p5h * p5w * 256
+    return sp
+
+
+def init_variables(cfg, seed=None):
+    """Random init following make_w_b (alexnet.py:40-46), convert_dim_fc (tf_util.py:44-45) and the
+    BasicLSTMCell defaults (glorot-uniform kernel, zero bias); numpy Generator(seed) in creation order."""
+    rng = np.random.default_rng(cfg.seed if seed is None else seed)
+
+    def trunc_normal(shape, std=0.05):
+        out = rng.standard_normal(size=shape)
+        bad = np.abs(out) > 2.0
+        while bad.any():
+            out[bad] = rng.standard_normal(size=int(bad.sum()))
+            bad = np.abs(out) > 2.0
+        return (out * std).astype(np.float32)
+
+    params = {}
+    for name, shape in variable_shapes(cfg):
+        if name.endswith("basic_lstm_cell/kernel"):
+            lim = math.sqrt(6.0 / (shape[0] + shape[1]))
+            params[name] = rng.uniform(-lim, lim, size=shape).astype(np.float32)
+        elif name.endswith("basic_lstm_cell/bias"):
+            params[name] = np.zeros(shape, np.float32)
+        elif len(shape) == 1:
+            params[name] = np.full(shape, 0.1, np.float32)
+        else:
+            params[name] = trunc_normal(shape)
+    return params
+
+
+class Engine(object):
+    def __init__(self, cfg, max_clips, device="cuda:0", params=None, rank=0, world=1, group=None):
+        nv.lib()  # fail loudly when the CUDA library is missing: there is no CPU fallback
+        if not torch.cuda.is_available():
+            raise nv.NativeError("vlb200.Engine needs a CUDA device (sm_100a); no CPU fallback exists")
+        self.cfg = cfg
+        self.dev = torch.device(device)
+        torch.cuda.set_device(self.dev)
+        self.rank, self.world, self.group = rank, world, group
+        self.max_clips = int(max_clips)
+        self.max_frames = self.max_clips * cfg.fpc
+        self.sp = encoder_specs(cfg.height, cfg.width)
+        self.global_step = 0
+        self.adam_t = 0
+        self.c_pad = _align(cfg.num_classes, 8)
+
+        # ---- parameter / gradient arenas ----
+        self.var_shapes = variable_shapes(cfg)
+        self.var_off = {}
+        off = 0
+        offsets = [0]
+        for name, shape in self.var_shapes:
+            self.var_off[name] = off
+            off += _align(int(np.prod(shape)))
+            offsets.append(off)
+        self.arena_n = off
+        self.params = torch.zeros(off, dtype=F32, device=self.dev)
+        self.grads = torch.zeros(off, dtype=F32, device=self.dev)
+        self.seg_offsets = torch.tensor(offsets, dtype=torch.int64, device=self.dev)
+        self.sqnorms = torch.zeros(len(self.var_shapes), dtype=F32, device=self.dev)
+        self.scalars = torch.zeros(8, dtype=F32, device=self.dev)  # [0..2] clip scalars, [4] loss, [5] correct
+        self.adam_m = self.adam_v = None
+        if cfg.optimizer == "adam":
+            self.adam_m = torch.zeros(off, dtype=F32, device=self.dev)
+            self.adam_v = torch.zeros(off, dtype=F32, device=self.dev)
+        self._alloc_shadows()
+        self._alloc_activations()
+        self.load_state_dict(params if params is not None else init_variables(cfg))
+
+    # ------------------------------------------------------------------------------------------
+    # variables
+    # ------------------------------------------------------------------------------------------
+    def var(self, name, arena=None):
+        arena = self.params if arena is None else arena
+        shape = dict(self.var_shapes)[name]
+        o = self.var_off[name]
+        return arena[o:o + int(np.prod(shape))].view(*shape)
+
+    def var2d(self, name, arena=None):
+        v = self.var(name, arena)
+        return v.reshape(-1, v.shape[-1])
+
+    def state_dict(self):
+        """Variables as float32 numpy arrays keyed by the reference's TF variable names (+ global_step)."""
+        out = {name: self.var(name).detach().cpu().numpy().copy() for name, _ in self.var_shapes}
+        out["global_step"] = np.int32(self.global_step)
+        return out
+
+    def load_state_dict(self, sd, strict=True):
+        for name, shape in self.var_shapes:
+            if name not in sd:
+                if strict:
+                    raise KeyError("missing variable %s" % name)
+                continue
+            arr = np.asarray(sd[name], dtype=np.float32)
+            if tuple(arr.shape) != tuple(shape):
+                raise ValueError("variable %s: shape %s does not match %s" % (name, arr.shape, shape))
+            self.var(name).copy_(torch.from_numpy(arr))
+        if "global_step" in sd:
+            self.global_step = int(sd["global_step"])
+        self.refresh_shadows()
+
+    def gradient_dict(self):
+        return {name: self.var(name, self.grads).detach().cpu().numpy().copy() for name, _ in self.var_shapes}
+
+    # ------------------------------------------------------------------------------------------
+    # bf16 operand copies of the weights
+    # ------------------------------------------------------------------------------------------
+    def _alloc_shadows(self):
+        cfg, sp, dev = self.cfg, self.sp, self.dev
+        sh = {}
+        s1 = sp["conv1"]
+        self.k1 = s1.taps * 3
+        self.k1_ld = _align(self.k1, 64)
+        sh["conv1"] = torch.zeros(self.k1_ld, 96, dtype=BF16, device=dev)
+        for name in ("conv2", "conv3", "conv4", "conv5"):
+            s = sp[name]
+            sh[name] = torch.zeros(s.taps * s.cin_g, s.cout, dtype=BF16, device=dev)  # HWIO as 2D
+            if s.cin_g % 64 != 0:
+                sh[name + "_packed"] = torch.zeros(s.k_packed, s.cout, dtype=BF16, device=dev)
+        sh["fc6"] = torch.zeros(sp["flat"], 4096, dtype=BF16, device=dev)
+        names = dict(self.var_shapes)
+        if "dcnn/fc7W" in names:
+            sh["fc7"] = torch.zeros(4096, 4096, dtype=BF16, device=dev)
+        if "dcnn/fc8W" in names:
+            sh["fc8"] = torch.zeros(4096, self.c_pad, dtype=BF16, device=dev)
+        if cfg.workflow == "lrcn":
+            for layer in range(cfg.lstm_layers):
+                kn = "rnn/multi_rnn_cell/cell_%d/basic_lstm_cell/kernel" % layer
+                rows, cols = names[kn]
+                sh["lstm%d" % layer] = torch.zeros(rows, cols, dtype=BF16, device=dev)
+                sh["lstm%d_wht" % layer] = torch.zeros(cols, cfg.lstm_hidden, dtype=F32, device=dev)
+            if "output_fc_w" in names:
+                sh["output_fc"] = torch.zeros(cfg.lstm_hidden, self.c_pad, dtype=BF16, device=dev)
+        self.sh = sh
+
+    def refresh_shadows(self):
+        """fp32 master -> bf16 tensor-core operands (after load and after every optimiser step)."""
+        sh, sp = self.sh, self.sp
+        w1 = self.var2d("dcnn/conv1W")
+        nv.call("vl_pack_bf16", w1, self.k1, 96, sh["conv1"], self.k1_ld, 96, self.k1, self.k1_ld)
+        for name in ("conv2", "conv3", "conv4", "conv5"):
+            s = sp[name]
+            w = self.var2d("dcnn/%sW" % name)
+            nv.call("vl_cast_f32_to_bf16", w, sh[name], w.numel())
+            if name + "_packed" in sh:
+                nv.call("vl_pack_bf16", w, s.taps * s.cin_g, s.cout, sh[name + "_packed"], s.k_packed, s.cout,
+                        s.cin_g, s.cchunks * 64)
+        for name in ("fc6", "fc7"):
+            if name in sh:
+                w = self.var("dcnn/%sW" % name)
+                nv.call("vl_cast_f32_to_bf16", w, sh[name], w.numel())
+        if "fc8" in sh:
+            w = self.var("dcnn/fc8W")
+            nv.call("vl_pack_bf16", w, 4096, self.cfg.num_classes, sh["fc8"], 4096, self.c_pad, 4096, 4096)
+        if self.cfg.workflow == "lrcn":
+            hdim = self.cfg.lstm_hidden
+            for layer in range(self.cfg.lstm_layers):
+                kern = self.var("rnn/multi_rnn_cell/cell_%d/basic_lstm_cell/kernel" % layer)
+                nv.call("vl_cast_f32_to_bf16", kern, sh["lstm%d" % layer], kern.numel())
+                d_in = kern.shape[0] - hdim
+                nv.call("vl_transpose_f32", kern[d_in:], sh["lstm%d_wht" % layer], hdim, 4 * hdim)
+            if "output_fc" in sh:
+                w = self.var("output_fc_w")
+                nv.call("vl_pack_bf16", w, hdim, self.cfg.num_classes, sh["output_fc"], hdim, self.c_pad, hdim, hdim)
+
+    # ------------------------------------------------------------------------------------------
+    # buffers
+    # ------------------------------------------------------------------------------------------
+    def _alloc_activations(self):
+        cfg, sp, dev = self.cfg, self.sp, self.dev
+        n, b = self.max_frames, self.max_clips
+        s1, s2, s3 = sp["conv1"], sp["conv2"], sp["conv3"]
+        (p1h, p1w), (p2h, p2w), (p5h, p5w) = sp["pool1"], sp["pool2"], sp["pool5"]
+
+        def act(*shape, dtype=BF16):
+            return torch.empty(*shape, dtype=dtype, device=dev)
+
+        A = {}
+        A["frames_u8"] = act(n, cfg.height, cfg.width, 3, dtype=torch.uint8)
+        A["frames_f32"] = None  # allocated lazily: only the reference-compatible fp32 feed needs it
+        A["col1"] = act(n * s1.p * s1.q, self.k1_ld)
+        A["a1"] = act(n, s1.p, s1.q, 96)
+        A["n1"] = act(n, s1.p, s1.q, 96)
+        A["p1"] = act(n, p1h, p1w, 96)
+        A["arg1"] = act(n, p1h, p1w, 96, dtype=torch.uint8)
+        A["a2"] = act(n, s2.p, s2.q, 256)
+        A["n2"] = act(n, s2.p, s2.q, 256)
+        A["p2"] = act(n, p2h, p2w, 256)
+        A["arg2"] = act(n, p2h, p2w, 256, dtype=torch.uint8)
+        A["a3"] = act(n, s3.p, s3.q, 384)
+        A["a4"] = act(n, s3.p, s3.q, 384)
+        A["a5"] = act(n, s3.p, s3.q, 256)
+        A["p5"] = act(n, p5h, p5w, 256)
+        A["arg5"] = act(n, p5h, p5w, 256, dtype=torch.uint8)
+        A["f6"] = act(n, 4096)
+        A["f7"] = act(n, 4096)
+        c, cp, hd = cfg.num_classes, self.c_pad, cfg.lstm_hidden
+        if cfg.workflow == "singleframe":
+            A["frame_logits"] = act(n, c, dtype=F32)
+            A["d_frame_logits"] = act(n, cp, dtype=F32)
+            A["d_frame_logits_bf16"] = act(n, cp)
+        else:
+            for layer in range(cfg.lstm_layers):
+                A["gx%d" % layer] = act(n, 4 * hd, dtype=F32)
+                A["acts%d" % layer] = act(n, 4 * hd, dtype=F32)
+                A["cs%d" % layer] = act(n, hd, dtype=F32)
+                A["hseq%d" % layer] = act(n, hd, dtype=F32)
+                A["hseq_bf%d" % layer] = act(n, hd)
+                A["hprev_bf%d" % layer] = act(n, hd)
+                A["dhseq%d" % layer] = act(n, hd, dtype=F32)
+            A["dg"] = act(n, 4 * hd)
+            A["fused"] = act(b, hd, dtype=F32)
+            A["fused_bf"] = act(b, hd)
+            A["mask"] = act(b, hd, dtype=F32)
+            A["dropped"] = act(b, hd, dtype=F32)
+            A["dropped_bf"] = act(b, hd)
+            A["ddropped"] = act(b, hd, dtype=F32)
+            A["dfused"] = act(b, hd, dtype=F32)
+        A["logits"] = act(b, c, dtype=F32)
+        A["labels"] = act(b, c, dtype=torch.int32)
+        A["row_loss"] = act(2 * b, dtype=F32)
+        A["dlogits"] = torch.zeros(b, cp, dtype=F32, device=dev)
+        A["dlogits_bf"] = torch.zeros(b, cp, dtype=BF16, device=dev)
+        self.A = A
+        self.G = None  # gradient-side activation buffers, allocated on the first train_step
+        self._pinned = {}
+
+    def _alloc_backward(self):
+        sp, dev = self.sp, self.dev
+        n = self.max_frames
+        s1, s2, s3 = sp["conv1"], sp["conv2"], sp["conv3"]
+        (p1h, p1w), (p2h, p2w), (p5h, p5w) = sp["pool1"], sp["pool2"], sp["pool5"]
+
+        def act(*shape):
+            return torch.empty(*shape, dtype=BF16, device=dev)
+
+        G = {}
+        G["df7"] = act(n, 4096)
+        G["df6"] = act(n, 4096)
+        G["dp5"] = act(n, p5h, p5w, 256)
+        G["da5"] = act(n, s3.p, s3.q, 256)
+        G["da4"] = act(n, s3.p, s3.q, 384)
+        G["da3"] = act(n, s3.p, s3.q, 384)
+        G["dp2"] = act(n, p2h, p2w, 256)
+        G["dn2"] = act(n, s2.p, s2.q, 256)
+        G["da2"] = act(n, s2.p, s2.q, 256)
+        G["dp1"] = act(n, p1h, p1w, 96)
+        G["dn1"] = act(n, s1.p, s1.q, 96)
+        G["da1"] = act(n, s1.p, s1.q, 96)
+        self.G = G
+
+    # ------------------------------------------------------------------------------------------
+    # input staging
+    # ------------------------------------------------------------------------------------------
+    def _stage_frames(self, frames):
+        """Accept what `feeder.get_feed_dict` produces (a list / array of float32 HWC frames, feeder.py:97-100),
+        a uint8 array (mean subtracted on device), or a device tensor.  Returns (tensor, is_u8, n_frames)."""
+        cfg = self.cfg
+        if isinstance(frames, (list, tuple)):
+            frames = np.stack([np.asarray(f) for f in frames], axis=0)
+        if isinstance(frames, np.ndarray):
+            n = frames.shape[0]
+            if n > self.max_frames:
+                raise ValueError("batch of %d frames exceeds the engine capacity %d" % (n, self.max_frames))
+            is_u8 = frames.dtype == np.uint8
+            if not is_u8:
+                frames = np.ascontiguousarray(frames, dtype=np.float32)
+                if self.A["frames_f32"] is None:
+                    self.A["frames_f32"] = torch.empty(self.max_frames, cfg.height, cfg.width, 3, dtype=F32,
+                                                       device=self.dev)
+            key = ("u8" if is_u8 else "f32")
+            pin = self._pinned.get(key)
+            if pin is None:
+                pin = torch.empty(self.max_frames, cfg.height, cfg.width, 3,
+                                  dtype=torch.uint8 if is_u8 else F32).pin_memory()
+                self._pinned[key] = pin
+            pin[:n].copy_(torch.from_numpy(np.ascontiguousarray(frames)))
+            dst = self.A["frames_u8"] if is_u8 else self.A["frames_f32"]
+            dst[:n].copy_(pin[:n], non_blocking=True)
+            return dst[:n], is_u8, n
+        assert isinstance(frames, torch.Tensor) and frames.is_cuda and frames.is_contiguous()
+        assert frames.dtype in (torch.uint8, F32)
+        return frames, frames.dtype == torch.uint8, frames.shape[0]
+
+    # ------------------------------------------------------------------------------------------
+    # forward
+    # ------------------------------------------------------------------------------------------
+    def _mean_dev(self):
+        if not hasattr(self, "_mean_t"):
+            m = self.cfg.mean if self.cfg.mean is not None else (0.0, 0.0, 0.0)
+            self._mean_t = torch.tensor(m, dtype=F32, device=self.dev)
+        return self._mean_t
+
+    def _encoder_fwd(self, frames, is_u8, n, training):
+        A, sp, sh = self.A, self.sp, self.sh
+        s1 = sp["conv1"]
+        (p1h, p1w), (p2h, p2w), (p5h, p5w) = sp["pool1"], sp["pool2"], sp["pool5"]
+        m1 = n * s1.p * s1.q
+        col = A["col1"][:m1]
+        nv.call("vl_conv1_patches", frames, 1 if is_u8 else 0, self._mean_dev(), col, n, self.cfg.height,
+                self.cfg.width, s1.kh, s1.kw, s1.stride, s1.pad_top, s1.pad_left, s1.p, s1.q, self.k1_ld)
+        a1 = A["a1"][:n]
+        K.linear_fwd(col, sh["conv1"], self.var("dcnn/conv1b"), a1.view(m1, 96), relu=True)
+        nv.call("vl_lrn_fwd", a1, A["n1"][:n], m1, 96, LRN["radius"], LRN["alpha"], LRN["beta"], LRN["bias"])
+        nv.call("vl_maxpool_fwd", A["n1"][:n], A["p1"][:n], A["arg1"][:n], n, s1.p, s1.q, 96)
+        s2 = sp["conv2"]
+        K.conv_fwd(s2, A["p1"][:n], sh["conv2_packed"], self.var("dcnn/conv2b"), A["a2"][:n], relu=True)
+        m2 = n * s2.p * s2.q
+        nv.call("vl_lrn_fwd", A["a2"][:n], A["n2"][:n], m2, 256, LRN["radius"], LRN["alpha"], LRN["beta"], LRN["bias"])
+        nv.call("vl_maxpool_fwd", A["n2"][:n], A["p2"][:n], A["arg2"][:n], n, s2.p, s2.q, 256)
+        K.conv_fwd(sp["conv3"], A["p2"][:n], sh["conv3"], self.var("dcnn/conv3b"), A["a3"][:n], relu=True)
+        K.conv_fwd(sp["conv4"], A["a3"][:n], sh["conv4"], self.var("dcnn/conv4b"), A["a4"][:n], relu=True)
+        K.conv_fwd(sp["conv5"], A["a4"][:n], sh["conv5"], self.var("dcnn/conv5b"), A["a5"][:n], relu=True)
+        s3 = sp["conv3"]
+        nv.call("vl_maxpool_fwd", A["a5"][:n], A["p5"][:n], A["arg5"][:n], n, s3.p, s3.q, 256)
+        flat = A["p5"][:n].view(n, sp["flat"])  # HWC-major flatten (alexnet.py:228)
+        K.linear_fwd(flat, sh["fc6"], self.var("dcnn/fc6b"), A["f6"][:n], relu=True)
+        feat = A["f6"][:n]
+        if "fc7" in sh:
+            K.linear_fwd(A["f6"][:n], sh["fc7"], self.var("dcnn/fc7b"), A["f7"][:n], relu=True)
+            feat = A["f7"][:n]
+        return feat
+
+    def _head_fwd(self, feat, n, training):
+        cfg, A, sh = self.cfg, self.A, self.sh
+        b = n // cfg.fpc
+        c = cfg.num_classes
+        logits = A["logits"][:b]
+        if cfg.workflow == "singleframe":
+            fl = A["frame_logits"][:n]
+            K.linear_fwd(feat, sh["fc8"], self.var("dcnn/fc8b"), fl, relu=False, n=c)
+            nv.call("vl_segment_pool_fwd", fl, None, cfg.fpc, b, c, POOL[cfg.fusion], logits, None)
+            return logits
+        hd, t_len = cfg.lstm_hidden, cfg.fpc
+        x = feat
+        for layer in range(cfg.lstm_layers):
+            kern = self.var("rnn/multi_rnn_cell/cell_%d/basic_lstm_cell/kernel" % layer)
+            bias = self.var("rnn/multi_rnn_cell/cell_%d/basic_lstm_cell/bias" % layer)
+            d_in = kern.shape[0] - hd
+            gx = A["gx%d" % layer][:n]
+            K.linear_fwd(x, sh["lstm%d" % layer][:d_in], bias, gx, relu=False)
+            nv.call("vl_lstm_fwd", gx, kern[d_in:], A["acts%d" % layer][:n], A["cs%d" % layer][:n],
+                    A["hseq%d" % layer][:n], A["hseq_bf%d" % layer][:n], A["hprev_bf%d" % layer][:n], b, t_len, hd,
+                    1.0)
+            x = A["hseq_bf%d" % layer][:n]
+        hseq = A["hseq%d" % (cfg.lstm_layers - 1)][:n]
+        nv.call("vl_segment_pool_fwd", hseq, None, t_len, b, hd, POOL[cfg.fusion], A["fused"][:b], A["fused_bf"][:b])
+        top, top_bf = A["fused"][:b], A["fused_bf"][:b]
+        self._dropout_on = bool(training and cfg.dropout_keep_prob > 0)  # lstm.py:52
+        if self._dropout_on:
+            if self._injected_mask is not None:
+                A["mask"][:b].copy_(self._injected_mask)
+            else:
+                nv.call("vl_dropout_mask", A["mask"][:b], b * hd, cfg.dropout_keep_prob, cfg.seed + 7919 * self.rank,
+                        self.global_step * ((self.max_clips * hd + 3) // 4))
+            nv.call("vl_mul", top, A["mask"][:b], A["dropped"][:b], A["dropped_bf"][:b], b * hd)
+            top, top_bf = A["dropped"][:b], A["dropped_bf"][:b]
+        self._top_bf = top_bf
+        if "output_fc" in sh:
+            K.linear_fwd(top_bf, sh["output_fc"], self.var("output_fc_b"), logits, relu=False, n=c)
+        else:
+            logits.copy_(top)
+        return logits
+
+    _injected_mask = None
+
+    def forward_device(self, frames, training=False):
+        """Enqueue the forward pass; returns the device logits [clips, C] (fp32)."""
+        frames, is_u8, n = self._stage_frames(frames)
+        if n % self.cfg.fpc != 0:
+            raise ValueError("number of frames (%d) is not a multiple of num_frames_per_clip (%d)" % (n, self.cfg.fpc))
+        feat = self._encoder_fwd(frames, is_u8, n, training)
+        return self._head_fwd(feat, n, training)
+
+    def forward(self, frames):
+        """`sess.run(model.logits, fdict)` (run_task.py:95): float32 ndarray [clips, C] on the host."""
+        return self.forward_device(frames, training=False).cpu().numpy()
+
+    # ------------------------------------------------------------------------------------------
+    # backward
+    # ------------------------------------------------------------------------------------------
+    def _split_k(self, out_rows, out_cols, contraction, groups=1, block_n=None):
+        tiles = -(-out_rows // 128) * -(-out_cols // (block_n or min(256, _align(out_cols, 64)))) * groups
+        kb = -(-contraction // 64)
+        want = max(1, (2 * nv.lib().vl_device_sm_count()) // max(tiles, 1))
+        return int(max(1, min(want, kb // 4 if kb >= 8 else 1)))
+
+    def _dense_bwd(self, x, dy, wname, bname, n_valid=None):
+        """Filter / bias gradient of y = x @ W + b into the gradient arena."""
+        dw = self.var2d(wname, self.grads)
+        n_cols = dw.shape[1]
+        K.linear_wgrad(x, dy, dw, split_k=self._split_k(dw.shape[0], n_cols, x.shape[0]), n=n_cols)
+        nv.call("vl_colsum", dy, self.var(bname, self.grads), dy.shape[0], n_cols, dy.stride(0))
+
+    def _conv_bwd(self, name, x, dy, dx, relu_mask):
+        s = self.sp[name]
+        n = x.shape[0]
+        dw = self.var2d("dcnn/%sW" % name, self.grads)
+        K.conv_wgrad(s, x, dy, dw, split_k=self._split_k(s.taps * s.cchunks * 64, s.cout_g, n * s.p * s.q, s.groups))
+        nv.call("vl_colsum", dy, self.var("dcnn/%sb" % name, self.grads), n * s.p * s.q, s.cout, s.cout)
+        if dx is not None:
+            K.conv_dgrad(s, dy, self.sh[name], dx, relu_mask=relu_mask)
+
+    def _head_bwd(self, n):
+        """From d(loss)/d(logits) down to d(loss)/d(frame features); returns the bf16 feature gradient."""
+        cfg, A, G, sh = self.cfg, self.A, self.G, self.sh
+        b, c = n // cfg.fpc, cfg.num_classes
+        feat_name = "f7" if "fc7" in sh else "f6"
+        feat = A[feat_name][:n]
+        dfeat = G["d" + feat_name][:n]
+        if cfg.workflow == "singleframe":
+            dfl = A["d_frame_logits"][:n]
+            nv.call("vl_segment_pool_bwd", A["dlogits"][:b], None, cfg.fpc, b, self.c_pad, POOL[cfg.fusion], dfl)
+            nv.call("vl_mul", dfl, None, None, A["d_frame_logits_bf16"][:n], n * self.c_pad)
+            dfl_bf = A["d_frame_logits_bf16"][:n]
+            self._dense_bwd(feat, dfl_bf, "dcnn/fc8W", "dcnn/fc8b")
+            K.linear_dgrad(dfl_bf, sh["fc8"], dfeat, relu_mask=feat, n_contract=c)
+            return dfeat
+        hd, t_len = cfg.lstm_hidden, cfg.fpc
+        dl_bf = A["dlogits_bf"][:b]
+        if "output_fc" in sh:
+            self._dense_bwd(self._top_bf, dl_bf, "output_fc_w", "output_fc_b")
+            K.linear_dgrad(dl_bf, sh["output_fc"], A["ddropped"][:b], n_contract=c)
+            dtop = A["ddropped"][:b]
+        else:
+            dtop = A["dlogits"][:b, :c].contiguous()
+        if self._dropout_on:
+            nv.call("vl_mul", dtop, A["mask"][:b], A["dfused"][:b], None, b * hd)
+            dtop = A["dfused"][:b]
+        top = cfg.lstm_layers - 1
+        nv.call("vl_segment_pool_bwd", dtop, None, t_len, b, hd, POOL[cfg.fusion], A["dhseq%d" % top][:n])
+        for layer in range(top, -1, -1):
+            kn = "rnn/multi_rnn_cell/cell_%d/basic_lstm_cell/kernel" % layer
+            bn = "rnn/multi_rnn_cell/cell_%d/basic_lstm_cell/bias" % layer
+            kern_g = self.var(kn, self.grads)
+            d_in = kern_g.shape[0] - hd
+            dg = A["dg"][:n]
+            nv.call("vl_lstm_bwd", A["dhseq%d" % layer][:n], A["acts%d" % layer][:n], A["cs%d" % layer][:n],
+                    sh["lstm%d_wht" % layer], dg, b, t_len, hd)
+            x = feat if layer == 0 else A["hseq_bf%d" % (layer - 1)][:n]
+            K.linear_wgrad(x, dg, kern_g[:d_in], split_k=self._split_k(d_in, 4 * hd, n))
+            K.linear_wgrad(A["hprev_bf%d" % layer][:n], dg, kern_g[d_in:], split_k=self._split_k(hd, 4 * hd, n))
+            nv.call("vl_colsum", dg, self.var(bn, self.grads), n, 4 * hd, 4 * hd)
+            if layer > 0:
+                K.linear_dgrad(dg, sh["lstm%d" % layer][:d_in], A["dhseq%d" % (layer - 1)][:n])
+            else:
+                K.linear_dgrad(dg, sh["lstm0"][:d_in], dfeat, relu_mask=feat)
+        return dfeat
+
+    def _encoder_bwd(self, dfeat, n):
+        A, G, sp, sh = self.A, self.G, self.sp, self.sh
+        s1, s2, s3 = sp["conv1"], sp["conv2"], sp["conv3"]
+        if "fc7" in sh:
+            self._dense_bwd(A["f6"][:n], dfeat, "dcnn/fc7W", "dcnn/fc7b")
+            K.linear_dgrad(dfeat, sh["fc7"], G["df6"][:n], relu_mask=A["f6"][:n])
+        df6 = G["df6"][:n]
+        flat = A["p5"][:n].view(n, sp["flat"])
+        self._dense_bwd(flat, df6, "dcnn/fc6W", "dcnn/fc6b")
+        K.linear_dgrad(df6, sh["fc6"], G["dp5"][:n].view(n, sp["flat"]))
+        nv.call("vl_maxpool_bwd", G["dp5"][:n], A["arg5"][:n], G["da5"][:n], A["a5"][:n], n, s3.p, s3.q, 256)
+        self._conv_bwd("conv5", A["a4"][:n], G["da5"][:n], G["da4"][:n], A["a4"][:n])
+        self._conv_bwd("conv4", A["a3"][:n], G["da4"][:n], G["da3"][:n], A["a3"][:n])
+        self._conv_bwd("conv3", A["p2"][:n], G["da3"][:n], G["dp2"][:n], None)
+        nv.call("vl_maxpool_bwd", G["dp2"][:n], A["arg2"][:n], G["dn2"][:n], None, n, s2.p, s2.q, 256)
+        nv.call("vl_lrn_bwd", A["a2"][:n], G["dn2"][:n], G["da2"][:n], n * s2.p * s2.q, 256, LRN["radius"],
+                LRN["alpha"], LRN["beta"], LRN["bias"], 1)
+        self._conv_bwd("conv2", A["p1"][:n], G["da2"][:n], G["dp1"][:n], None)
+        nv.call("vl_maxpool_bwd", G["dp1"][:n], A["arg1"][:n], G["dn1"][:n], None, n, s1.p, s1.q, 96)
+        m1 = n * s1.p * s1.q
+        nv.call("vl_lrn_bwd", A["a1"][:n], G["dn1"][:n], G["da1"][:n], m1, 96, LRN["radius"], LRN["alpha"],
+                LRN["beta"], LRN["bias"], 1)
+        da1 = G["da1"][:n].view(m1, 96)
+        dw1 = self.var2d("dcnn/conv1W", self.grads)
+        K.linear_wgrad(A["col1"][:m1], da1, dw1, split_k=self._split_k(self.k1, 96, m1), n=96)
+        nv.call("vl_colsum", da1, self.var("dcnn/conv1b", self.grads), m1, 96, 96)
+
+    # ------------------------------------------------------------------------------------------
+    # training step
+    # ------------------------------------------------------------------------------------------
+    def train_step(self, frames, onehot, lr, dropout_mask=None, apply_update=True):
+        """One `sess.run([loss, lr, global_step, optimizer])` (run_task.py:44, train.py:199-222).
+
+        frames: host/device frames of `clips * fpc` images; onehot: int32 [clips, C] (utils_.labels_to_one_hot).
+        Returns (loss, lr, global_step, accuracy, grads_norm) with global_step already incremented."""
+        cfg, A = self.cfg, self.A
+        if self.G is None:
+            self._alloc_backward()
+        self._injected_mask = None
+        if dropout_mask is not None:
+            self._injected_mask = torch.as_tensor(np.asarray(dropout_mask, dtype=np.float32)).to(self.dev)
+        frames, is_u8, n = self._stage_frames(frames)
+        if n % cfg.fpc != 0:
+            raise ValueError("number of frames (%d) is not a multiple of num_frames_per_clip (%d)" % (n, cfg.fpc))
+        b, c = n // cfg.fpc, cfg.num_classes
+        if isinstance(onehot, torch.Tensor):
+            A["labels"][:b].copy_(onehot.to(torch.int32), non_blocking=True)
+        else:
+            lab = np.ascontiguousarray(np.asarray(onehot, dtype=np.int32))
+            if lab.shape != (b, c):
+                raise ValueError("labels shape %s does not match [%d, %d]" % (lab.shape, b, c))
+            A["labels"][:b].copy_(torch.from_numpy(lab), non_blocking=True)
+        feat = self._encoder_fwd(frames, is_u8, n, True)
+        logits = self._head_fwd(feat, n, True)
+        nv.call("vl_softmax_ce", logits, A["labels"][:b], b, c, 1.0 / (b * self.world), A["row_loss"],
+                self.scalars[4:6], A["dlogits"][:b], A["dlogits_bf"][:b], self.c_pad)
+        self.grads.zero_()
+        dfeat = self._head_bwd(n)
+        self._encoder_bwd(dfeat, n)
+        if self.world > 1:
+            torch.distributed.all_reduce(self.grads, group=self.group)
+            torch.distributed.all_reduce(self.scalars[4:6], group=self.group)
+        nv.call("vl_grad_sqnorms", self.grads, self.arena_n, self.seg_offsets, len(self.var_shapes), self.sqnorms)
+        clip = float(cfg.clip_norm) if cfg.clip_norm else 0.0
+        nv.call("vl_clip_scalars", self.sqnorms, len(self.var_shapes), clip, 1.0, self.scalars)
+        if apply_update:
+            if cfg.optimizer == "sgd":
+                nv.call("vl_sgd_update", self.params, self.grads, self.arena_n, float(lr), self.scalars, 1.0)
+            else:
+                self.adam_t += 1
+                nv.call("vl_adam_update", self.params, self.grads, self.adam_m, self.adam_v, self.arena_n, float(lr),
+                        0.9, 0.999, 1e-8, self.adam_t, self.scalars, 1.0)
+            self.refresh_shadows()
+            self.global_step += 1
+        self._last_clips = b
+        return self.read_step_scalars(lr)
+
+    def read_step_scalars(self, lr):
+        """Device -> host read of the step results (the only synchronisation point of a step)."""
+        s = self.scalars.cpu().numpy()
+        b = self._last_clips
+        loss = float(s[4]) / self.world
+        acc = float(s[5]) / (b * self.world)
+        return loss, float(lr), self.global_step, acc, float(s[2])

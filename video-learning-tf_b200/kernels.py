@@ -117,7 +117,8 @@ def linear_wgrad(x, dy, dw, split_k=1, n=None, block_n=0):
     m, k = x.shape
     n = dy.shape[1] if n is None else n
     d = nv.GemmDesc()
-    d.m, d.n, d.k, d.groups = k, n, m, 1
+    d.m, d.n, d.k, d.groups = dw.shape[0], n, m, 1  # dw may have fewer rows than x has (zero padded) columns
+    assert dw.shape[0] <= k
     d.a_mode, d.b_mode = nv.A_TILED_MN, nv.B_TILED_MN
     d.a_ld, d.b_ld = _ld(x), _ld(dy)
     d.c_ld = _ld(dw)
