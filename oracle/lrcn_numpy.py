@@ -23,6 +23,24 @@ import numpy as np
 
 F32 = np.float32
 
+
+def bf16_round(x):
+    """Round-to-nearest-even to bfloat16 precision, returned as float32 (what the device path stores)."""
+    u = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32)
+    r = ((u >> 16) & 1) + np.uint32(0x7FFF)
+    return ((u + r) & np.uint32(0xFFFF0000)).view(np.float32)
+
+
+def _ident(x):
+    return x
+
+
+# Storage-precision model.  Every function below that takes `q` applies it exactly where the device path
+# stores a tensor in bf16 (GEMM operands, activations and activation gradients; accumulation, biases, LSTM
+# state and weight gradients stay fp32).  q=None is the plain fp32 restatement of the TensorFlow graph (the
+# numbers the north_star tolerance for logits/losses refers to); q=bf16_round makes hard decisions (ReLU masks,
+# max-pool argmax) coincide with the device path so gradients can be compared tightly.
+
 LRN_RADIUS, LRN_ALPHA, LRN_BETA, LRN_BIAS = 2, 2e-05, 0.75, 1.0  # alexnet.py:80-89,121-130
 
 
@@ -203,48 +221,55 @@ def sigmoid(x):
     return (1.0 / (1.0 + np.exp(-x))).astype(F32)
 
 
-def lstm_forward(x, kernels, biases, forget_bias=1.0):
+def lstm_forward(x, kernels, biases, forget_bias=1.0, q=None):
     """MultiRNNCell([BasicLSTMCell]) under dynamic_rnn, zero initial state, full-length sequences.
 
-    x [B,T,D]; gate order i, j, f, o (BasicLSTMCell); returns top-layer outputs [B,T,H] and the cache."""
+    x [B,T,D]; gate order i, j, f, o (BasicLSTMCell); returns top-layer outputs [B,T,H] and the cache.
+    [x_t, h] @ kernel is evaluated as x_t @ kernel[:D] + h @ kernel[D:] (same sum; the device path runs the first
+    term as one tensor-core GEMM over all t with bf16 operands and keeps the recurrent term in fp32)."""
+    q = q or _ident
     b, t_len, _ = x.shape
     caches = []
     inp = x
     for kern, bias in zip(kernels, biases):
+        d_in = inp.shape[2]
         hdim = kern.shape[1] // 4
+        xin = q(inp)
+        wx, wh = q(kern[:d_in]), kern[d_in:]
         h = np.zeros((b, hdim), F32)
         c = np.zeros((b, hdim), F32)
         outs = np.zeros((b, t_len, hdim), F32)
         steps = []
         for t in range(t_len):
-            xh = np.concatenate([inp[:, t, :], h], axis=1)
-            g = xh @ kern + bias
+            g = (xin[:, t, :] @ wx + h @ wh + bias).astype(F32)
             i, j, f, o = np.split(g, 4, axis=1)
             si, sf, so, tj = sigmoid(i), sigmoid(f + forget_bias), sigmoid(o), np.tanh(j).astype(F32)
             c_new = (c * sf + si * tj).astype(F32)
             tc = np.tanh(c_new).astype(F32)
             h_new = (tc * so).astype(F32)
-            steps.append((xh, si, sf, so, tj, c, tc))
+            steps.append((xin[:, t, :], h, si, sf, so, tj, c, tc))
             h, c = h_new, c_new
             outs[:, t, :] = h
-        caches.append((inp, steps, kern))
+        caches.append((inp.shape, steps, kern))
         inp = outs
     return inp, caches
 
 
-def lstm_backward(caches, dout):
+def lstm_backward(caches, dout, q=None):
     """BPTT through lstm_forward; dout [B,T,H] is the gradient w.r.t. the top-layer outputs."""
+    q = q or _ident
     dkernels, dbiases = [], []
-    for inp, steps, kern in reversed(caches):
-        b, t_len, d_in = inp.shape
+    for inp_shape, steps, kern in reversed(caches):
+        b, t_len, d_in = inp_shape
         hdim = kern.shape[1] // 4
+        wx, wh = q(kern[:d_in]), kern[d_in:]
         dk = np.zeros_like(kern)
         db = np.zeros((4 * hdim,), F32)
-        dinp = np.zeros_like(inp)
+        dinp = np.zeros(inp_shape, F32)
         dh_next = np.zeros((b, hdim), F32)
         dc_next = np.zeros((b, hdim), F32)
         for t in reversed(range(t_len)):
-            xh, si, sf, so, tj, c_prev, tc = steps[t]
+            x_t, h_prev, si, sf, so, tj, c_prev, tc = steps[t]
             dh = dout[:, t, :] + dh_next
             do = dh * tc * so * (1 - so)
             dc = dh * so * (1 - tc * tc) + dc_next
@@ -253,11 +278,12 @@ def lstm_backward(caches, dout):
             df = dc * c_prev * sf * (1 - sf)
             dc_next = dc * sf
             dg = np.concatenate([di, dj, df, do], axis=1).astype(F32)
-            dk += xh.T @ dg
-            db += dg.sum(axis=0)
-            dxh = dg @ kern.T
-            dinp[:, t, :] = dxh[:, :d_in]
-            dh_next = dxh[:, d_in:]
+            dgq = q(dg)
+            dk[:d_in] += x_t.T @ dgq
+            dk[d_in:] += q(h_prev).T @ dgq
+            db += dgq.sum(axis=0)
+            dinp[:, t, :] = dgq @ wx.T
+            dh_next = dg @ wh.T
         dkernels.append(dk)
         dbiases.append(db)
         dout = dinp
@@ -304,70 +330,71 @@ def accuracy(logits, onehot):
 # --------------------------------------------------------------------------------------------------
 # AlexNet encoder (alexnet.py:49-280)
 # --------------------------------------------------------------------------------------------------
-def alexnet_forward(params, frames, final_layer="fc7", keep_cache=False):
+def alexnet_forward(params, frames, final_layer="fc7", keep_cache=False, q=None):
     """frames [N,227,227,3] fp32 (BGR, mean subtracted) -> features [N,4096] (fc6/fc7) or fc8 logits [N,C]."""
+    q = q or _ident
     c = {}
     P = params
-    x0 = frames.astype(F32)
-    a1 = relu(conv2d_same(x0, P["dcnn/conv1W"], P["dcnn/conv1b"], 4, 1))
-    n1 = lrn(a1)
+    x0 = q(frames.astype(F32))
+    a1 = q(relu(conv2d_same(x0, q(P["dcnn/conv1W"]), P["dcnn/conv1b"], 4, 1)))
+    n1 = q(lrn(a1))
     p1, arg1 = maxpool_3x3s2(n1)
-    a2 = relu(conv2d_same(p1, P["dcnn/conv2W"], P["dcnn/conv2b"], 1, 2))
-    n2 = lrn(a2)
+    a2 = q(relu(conv2d_same(p1, q(P["dcnn/conv2W"]), P["dcnn/conv2b"], 1, 2)))
+    n2 = q(lrn(a2))
     p2, arg2 = maxpool_3x3s2(n2)
-    a3 = relu(conv2d_same(p2, P["dcnn/conv3W"], P["dcnn/conv3b"], 1, 1))
-    a4 = relu(conv2d_same(a3, P["dcnn/conv4W"], P["dcnn/conv4b"], 1, 2))
-    a5 = relu(conv2d_same(a4, P["dcnn/conv5W"], P["dcnn/conv5b"], 1, 2))
+    a3 = q(relu(conv2d_same(p2, q(P["dcnn/conv3W"]), P["dcnn/conv3b"], 1, 1)))
+    a4 = q(relu(conv2d_same(a3, q(P["dcnn/conv4W"]), P["dcnn/conv4b"], 1, 2)))
+    a5 = q(relu(conv2d_same(a4, q(P["dcnn/conv5W"]), P["dcnn/conv5b"], 1, 2)))
     p5, arg5 = maxpool_3x3s2(a5)
     flat = p5.reshape(p5.shape[0], -1)  # HWC-major flatten (alexnet.py:228)
-    f6 = relu(flat @ P["dcnn/fc6W"] + P["dcnn/fc6b"])
+    f6 = q(relu(flat @ q(P["dcnn/fc6W"]) + P["dcnn/fc6b"]))
     out = f6
     f7 = None
     if final_layer != "fc6":
-        f7 = relu(f6 @ P["dcnn/fc7W"] + P["dcnn/fc7b"])
+        f7 = q(relu(f6 @ q(P["dcnn/fc7W"]) + P["dcnn/fc7b"]))
         out = f7
         if final_layer != "fc7":
-            out = (f7 @ P["dcnn/fc8W"] + P["dcnn/fc8b"]).astype(F32)
+            out = (f7 @ q(P["dcnn/fc8W"]) + P["dcnn/fc8b"]).astype(F32)
     if keep_cache:
         c.update(x0=x0, a1=a1, n1=n1, p1=p1, arg1=arg1, a2=a2, n2=n2, p2=p2, arg2=arg2, a3=a3, a4=a4, a5=a5, p5=p5,
                  arg5=arg5, flat=flat, f6=f6, f7=f7, final_layer=final_layer)
     return out.astype(F32), c
 
 
-def alexnet_backward(params, c, dout):
-    """Gradients of every dcnn/* variable given d(loss)/d(output of alexnet_forward)."""
+def alexnet_backward(params, c, dout, q=None):
+    """Gradients of every dcnn/* variable given d(loss)/d(output of alexnet_forward) (post-ReLU for fc6/fc7)."""
+    q = q or _ident
     P = params
     g = {}
     fl = c["final_layer"]
     if fl == "fc6":
-        df6 = dout
+        df6 = q(dout * (c["f6"] > 0))
     else:
         if fl != "fc7":
+            dout = q(dout)
             g["dcnn/fc8W"] = c["f7"].T @ dout
             g["dcnn/fc8b"] = dout.sum(axis=0)
-            df7 = dout @ P["dcnn/fc8W"].T
+            df7 = q((dout @ q(P["dcnn/fc8W"]).T) * (c["f7"] > 0))
         else:
-            df7 = dout
-        df7 = df7 * (c["f7"] > 0)
+            df7 = q(dout * (c["f7"] > 0))
         g["dcnn/fc7W"] = c["f6"].T @ df7
         g["dcnn/fc7b"] = df7.sum(axis=0)
-        df6 = df7 @ P["dcnn/fc7W"].T
-    df6 = df6 * (c["f6"] > 0)
+        df6 = q((df7 @ q(P["dcnn/fc7W"]).T) * (c["f6"] > 0))
     g["dcnn/fc6W"] = c["flat"].T @ df6
     g["dcnn/fc6b"] = df6.sum(axis=0)
-    dp5 = (df6 @ P["dcnn/fc6W"].T).reshape(c["p5"].shape)
-    da5 = maxpool_3x3s2_backward(c["a5"].shape, c["arg5"], dp5) * (c["a5"] > 0)
-    da4, g["dcnn/conv5W"], g["dcnn/conv5b"] = conv2d_same_backward(c["a4"], P["dcnn/conv5W"], da5, 1, 2)
-    da4 = da4 * (c["a4"] > 0)
-    da3, g["dcnn/conv4W"], g["dcnn/conv4b"] = conv2d_same_backward(c["a3"], P["dcnn/conv4W"], da4, 1, 2)
-    da3 = da3 * (c["a3"] > 0)
-    dp2, g["dcnn/conv3W"], g["dcnn/conv3b"] = conv2d_same_backward(c["p2"], P["dcnn/conv3W"], da3, 1, 1)
-    dn2 = maxpool_3x3s2_backward(c["n2"].shape, c["arg2"], dp2)
-    da2 = lrn_backward(c["a2"], dn2) * (c["a2"] > 0)
-    dp1, g["dcnn/conv2W"], g["dcnn/conv2b"] = conv2d_same_backward(c["p1"], P["dcnn/conv2W"], da2, 1, 2)
-    dn1 = maxpool_3x3s2_backward(c["n1"].shape, c["arg1"], dp1)
-    da1 = lrn_backward(c["a1"], dn1) * (c["a1"] > 0)
-    _, g["dcnn/conv1W"], g["dcnn/conv1b"] = conv2d_same_backward(c["x0"], P["dcnn/conv1W"], da1, 4, 1, need_dx=False)
+    dp5 = q(df6 @ q(P["dcnn/fc6W"]).T).reshape(c["p5"].shape)
+    da5 = q(maxpool_3x3s2_backward(c["a5"].shape, c["arg5"], dp5) * (c["a5"] > 0))
+    da4, g["dcnn/conv5W"], g["dcnn/conv5b"] = conv2d_same_backward(c["a4"], q(P["dcnn/conv5W"]), da5, 1, 2)
+    da4 = q(da4 * (c["a4"] > 0))
+    da3, g["dcnn/conv4W"], g["dcnn/conv4b"] = conv2d_same_backward(c["a3"], q(P["dcnn/conv4W"]), da4, 1, 2)
+    da3 = q(da3 * (c["a3"] > 0))
+    dp2, g["dcnn/conv3W"], g["dcnn/conv3b"] = conv2d_same_backward(c["p2"], q(P["dcnn/conv3W"]), da3, 1, 1)
+    dn2 = q(maxpool_3x3s2_backward(c["n2"].shape, c["arg2"], q(dp2)))
+    da2 = q(lrn_backward(c["a2"], dn2) * (c["a2"] > 0))
+    dp1, g["dcnn/conv2W"], g["dcnn/conv2b"] = conv2d_same_backward(c["p1"], q(P["dcnn/conv2W"]), da2, 1, 2)
+    dn1 = q(maxpool_3x3s2_backward(c["n1"].shape, c["arg1"], q(dp1)))
+    da1 = q(lrn_backward(c["a1"], dn1) * (c["a1"] > 0))
+    _, g["dcnn/conv1W"], g["dcnn/conv1b"] = conv2d_same_backward(c["x0"], q(P["dcnn/conv1W"]), da1, 4, 1, need_dx=False)
     return {k: v.astype(F32) for k, v in g.items()}
 
 
@@ -385,18 +412,19 @@ def _lstm_vars(params):
 
 
 def lrcn_forward(params, frames, fpc, fusion="avg", frame_encoding_layer="fc7", dropout_mask=None,
-                 keep_cache=False):
+                 keep_cache=False, q=None):
     """LRCN: dcnn(fc6|fc7) -> LSTM -> temporal fusion -> dropout -> output_fc  => logits [clips, C].
 
     dropout_mask: None (validation / keep_prob <= 0) or an array [clips,H] already scaled by 1/keep_prob."""
-    feats, ac = alexnet_forward(params, frames, frame_encoding_layer, keep_cache)
+    qq = q or _ident
+    feats, ac = alexnet_forward(params, frames, frame_encoding_layer, keep_cache, q)
     seq = feats.reshape(-1, fpc, feats.shape[1])  # lstm.py:120
     kernels, biases = _lstm_vars(params)
-    outs, lc = lstm_forward(seq, kernels, biases)
+    outs, lc = lstm_forward(seq, kernels, biases, q=q)
     fused = temporal_fusion(outs, fusion)
     dropped = fused if dropout_mask is None else (fused * dropout_mask).astype(F32)
     if "output_fc_w" in params:
-        logits = (dropped @ params["output_fc_w"] + params["output_fc_b"]).astype(F32)
+        logits = (qq(dropped) @ qq(params["output_fc_w"]) + params["output_fc_b"]).astype(F32)
     else:
         logits = dropped
     cache = dict(ac=ac, lc=lc, outs_shape=outs.shape, dropped=dropped, fusion=fusion, mask=dropout_mask,
@@ -404,38 +432,40 @@ def lrcn_forward(params, frames, fpc, fusion="avg", frame_encoding_layer="fc7", 
     return logits, cache
 
 
-def lrcn_backward(params, cache, dlogits):
+def lrcn_backward(params, cache, dlogits, q=None):
+    qq = q or _ident
     g = {}
     if "output_fc_w" in params:
-        g["output_fc_w"] = cache["dropped"].T @ dlogits
-        g["output_fc_b"] = dlogits.sum(axis=0)
-        dd = dlogits @ params["output_fc_w"].T
+        dl = qq(dlogits)
+        g["output_fc_w"] = qq(cache["dropped"]).T @ dl
+        g["output_fc_b"] = dl.sum(axis=0)
+        dd = dl @ qq(params["output_fc_w"]).T
     else:
         dd = dlogits
     if cache["mask"] is not None:
         dd = dd * cache["mask"]
     douts = temporal_fusion_backward(cache["outs_shape"], cache["fusion"], dd.astype(F32))
-    dseq, dks, dbs = lstm_backward(cache["lc"], douts)
+    dseq, dks, dbs = lstm_backward(cache["lc"], douts, q=q)
     for layer, (dk, db) in enumerate(zip(dks, dbs)):
         g["rnn/multi_rnn_cell/cell_%d/basic_lstm_cell/kernel" % layer] = dk
         g["rnn/multi_rnn_cell/cell_%d/basic_lstm_cell/bias" % layer] = db
     dfeat = dseq.reshape(cache["feat_shape"])
-    g.update(alexnet_backward(params, cache["ac"], dfeat))
+    g.update(alexnet_backward(params, cache["ac"], dfeat, q))
     return {k: v.astype(F32) for k, v in g.items()}
 
 
-def singleframe_forward(params, frames, fpc, fusion="avg", keep_cache=False):
+def singleframe_forward(params, frames, fpc, fusion="avg", keep_cache=False, q=None):
     """Single-frame workflow: dcnn -> fc8 logits per frame -> late fusion over fpc (model.py:149-151)."""
-    fl, ac = alexnet_forward(params, frames, "fc8", keep_cache)
+    fl, ac = alexnet_forward(params, frames, "fc8", keep_cache, q)
     seq = fl.reshape(-1, fpc, fl.shape[1])
     logits = temporal_fusion(seq, fusion)
     cache = dict(ac=ac, seq_shape=seq.shape, fusion=fusion) if keep_cache else None
     return logits, cache
 
 
-def singleframe_backward(params, cache, dlogits):
+def singleframe_backward(params, cache, dlogits, q=None):
     dseq = temporal_fusion_backward(cache["seq_shape"], cache["fusion"], dlogits)
-    return alexnet_backward(params, cache["ac"], dseq.reshape(-1, dseq.shape[2]))
+    return alexnet_backward(params, cache["ac"], dseq.reshape(-1, dseq.shape[2]), q)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -475,20 +505,20 @@ def adam_update(params, grads, state, lr, beta1=0.9, beta2=0.999, eps=1e-8):
 
 
 def train_step(params, frames, onehot, fpc, lr, workflow="lrcn", fusion="avg", frame_encoding_layer="fc7",
-               clip_norm=None, optimizer="sgd", opt_state=None, dropout_mask=None):
+               clip_norm=None, optimizer="sgd", opt_state=None, dropout_mask=None, q=None):
     """One `sess.run([loss, lr, global_step, optimizer])` (run_task.py:44) on the CPU.
 
     Returns dict(loss, accuracy, grads_norm, global_norm, logits, grads); updates `params` in place."""
     if workflow == "lrcn":
-        logits, cache = lrcn_forward(params, frames, fpc, fusion, frame_encoding_layer, dropout_mask, True)
+        logits, cache = lrcn_forward(params, frames, fpc, fusion, frame_encoding_layer, dropout_mask, True, q)
     else:
-        logits, cache = singleframe_forward(params, frames, fpc, fusion, True)
+        logits, cache = singleframe_forward(params, frames, fpc, fusion, True, q)
     loss, dlogits, _ = softmax_ce(logits, onehot)
     acc = accuracy(logits, onehot)
     if workflow == "lrcn":
-        grads = lrcn_backward(params, cache, dlogits)
+        grads = lrcn_backward(params, cache, dlogits, q)
     else:
-        grads = singleframe_backward(params, cache, dlogits)
+        grads = singleframe_backward(params, cache, dlogits, q)
     gn = global_norm(grads)
     if clip_norm:
         grads, gn = clip_by_global_norm(grads, clip_norm)
