@@ -1,0 +1,73 @@
+"""GPU: the reference-facing workflow (run_task loops, validation fusion on the device) end to end."""
+import os
+import types
+
+import numpy as np
+import pytest
+import yaml
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+VAL = np.load(os.path.join(ROOT, "tests", "golden", "reference_val_golden.npz"))
+
+
+@pytest.mark.parametrize("method", ["avg", "last"])
+def test_device_clip_fusion_bit_exact_vs_reference_golden(method, tmp_path):
+    """Pooled video logits and labels computed by the CUDA segmented reduction == the reference's own
+    Validation.apply_clip_fusion output (golden vectors), bit for bit."""
+    import vlb200  # noqa: F401
+    from vlb200.val import Validation
+    st = types.SimpleNamespace(num_classes=101, run_id="t", run_folder=str(tmp_path), val=None)
+    v = Validation(st, use_device=True)
+    v.process_validation_logits(VAL["logits"], VAL["labels"], [int(c) for c in VAL["cpv"]], method)
+    assert np.array_equal(v.item_logits, VAL["video_logits_" + method])
+    assert np.array_equal(v.item_logits.argmax(1), VAL["video_logits_" + method].argmax(1))
+    assert v.get_accuracy() == float(VAL["get_accuracy_" + method])
+
+
+def _cfg(name, tmp_path, mutate):
+    with open(os.path.join(ROOT, "configs", name)) as f:
+        cfg = yaml.safe_load(f)
+    cfg["run"]["run_folder"] = str(tmp_path / "run")
+    mutate(cfg["run"])
+    p = tmp_path / name
+    with open(p, "w") as f:
+        yaml.safe_dump(cfg, f)
+    return str(p)
+
+
+def test_run_task_train_then_resume_then_validate(tmp_path):
+    import vlb200  # noqa: F401
+    from vlb200 import run_task
+
+    def small_train(run):
+        d = run["data"]["synthetic-train"]
+        d["num_items"] = 6
+        d["num_frames_per_clip"] = 2
+        run["train"]["batch_size"] = 2
+        run["train"]["epochs"] = 1
+    run_task.main(_cfg("config2_lrcn_train.yml", tmp_path, small_train))
+    folder = tmp_path / "run" / "checkpoints"
+    names = [l.strip() for l in open(folder / "checkpoint") if l.strip()]
+    assert len(names) == 1 and names[0].endswith("ep_1_btch_3_gs_3.graph-3")
+    assert os.path.exists(tmp_path / "run" / "config2_train_scratch_lr_decay_schedule.txt")
+
+    def small_val(run):
+        d = run["data"]["synthetic-val"]
+        d["num_items"] = 5
+        d["clips_per_video"] = [2, 1, 3, 1, 2]
+        d["num_frames_per_clip"] = 2
+        run["val"]["batch_size"] = 2
+        run["resume_file"] = "latest"
+        run["run_id"] = "config2"
+    acc = run_task.main(_cfg("config5_lrcn_val.yml", tmp_path, small_val))
+    assert 0.0 <= acc <= 1.0
+    files = os.listdir(tmp_path / "run")
+    assert any(f.startswith("validation_logits_config2_val_resume") and f.endswith(".total") for f in files)
+    assert "accuracy_config2_val_resume" in files
+    import pickle
+    tot = [f for f in files if f.endswith(".total")][0]
+    with open(tmp_path / "run" / tot, "rb") as f:
+        logits = pickle.load(f)
+    assert logits.shape == (5, 101) and logits.dtype == np.float32  # one fused row per video (val.py:124-137 format)

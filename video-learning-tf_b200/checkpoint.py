@@ -1,0 +1,89 @@
+"""Checkpoints: variables keyed by the reference's TF variable names + the `.snap` progress pickle.
+
+Reference: feeder.py:143-194 (resume_snap), :198-257 (init_saveload), :263-288 (save).  TensorFlow's V2 checkpoint
+format cannot be written without TensorFlow; variables go into `<prefix>-<global_step>.npz` (same keys), while the
+folder layout, the file-name pattern `<ddmmyy_HHMMSS>_ep_E_btch_B_gs_G.graph-G`, the `.snap` pickle
+`[batch_index, epoch_index, global_step]` and `resume_file: latest` keep the reference's semantics.
+"""
+import glob
+import os
+import pickle
+import time
+
+import numpy as np
+
+from .utils import error, info, warning
+
+
+def checkpoint_folder(run_folder):
+    return os.path.join(run_folder, "checkpoints")
+
+
+def save(engine, run_folder, progress_str, batch_index, epoch_index, max_to_keep=None):
+    folder = checkpoint_folder(run_folder)
+    os.makedirs(folder, exist_ok=True)
+    gs = engine.global_step
+    prefix = os.path.join(folder, "%s_%s.graph-%d" % (time.strftime("%d%m%y_%H%M%S"), progress_str, gs))
+    sd = engine.state_dict()
+    np.savez(prefix + ".npz", **{k.replace("/", "|"): v for k, v in sd.items()})
+    with open(prefix + ".snap", "wb") as f:
+        pickle.dump([batch_index, epoch_index, gs], f)
+    with open(os.path.join(folder, "checkpoint"), "a") as f:
+        f.write(os.path.basename(prefix) + "\n")
+    info("Saved checkpoint %s" % prefix)
+    if max_to_keep:
+        with open(os.path.join(folder, "checkpoint")) as f:
+            names = [l.strip() for l in f if l.strip()]
+        for old in names[:-max_to_keep]:
+            for ext in (".npz", ".snap"):
+                p = os.path.join(folder, old + ext)
+                if os.path.exists(p):
+                    os.remove(p)
+        with open(os.path.join(folder, "checkpoint"), "w") as f:
+            f.write("\n".join(names[-max_to_keep:]) + "\n")
+    return prefix
+
+
+def resolve(run_folder, resume_file):
+    folder = checkpoint_folder(run_folder)
+    if resume_file == "latest":
+        index = os.path.join(folder, "checkpoint")
+        if not os.path.exists(index):
+            error("No checkpoint index in %s to resume `latest` from" % folder)
+        with open(index) as f:
+            names = [l.strip() for l in f if l.strip()]
+        if not names:
+            error("Empty checkpoint index %s" % index)
+        return os.path.join(folder, names[-1])
+    cand = resume_file if os.path.isabs(resume_file) else os.path.join(folder, resume_file)
+    for ext in (".npz", ".snap"):
+        if cand.endswith(ext):
+            cand = cand[:-len(ext)]
+    if not os.path.exists(cand + ".npz"):
+        matches = sorted(glob.glob(cand + "*.npz"))
+        if not matches:
+            error("Checkpoint %s not found" % cand)
+        cand = matches[-1][:-4]
+    return cand
+
+
+def restore(engine, prefix, ignorable=("global_step",), is_validation=False):
+    """Load variables (name-diff check like feeder.py:229-249) and return (batch_index, epoch_index, global_step)."""
+    blob = np.load(prefix + ".npz")
+    sd = {k.replace("|", "/"): blob[k] for k in blob.files}
+    want = {name for name, _ in engine.var_shapes}
+    have = set(sd) - {"global_step"}
+    missing, extra = want - have, have - want
+    if missing:
+        error("Variables missing from checkpoint %s: %s" % (prefix, sorted(missing)))
+    if extra:
+        warning("Checkpoint variables not in the model (ignored): %s" % sorted(extra))
+    if is_validation:
+        sd.pop("global_step", None)  # ignorable in validation (feeder.py:226-227)
+    engine.load_state_dict(sd)
+    snap = [0, 0, int(sd.get("global_step", 0))]
+    if os.path.exists(prefix + ".snap"):
+        with open(prefix + ".snap", "rb") as f:
+            snap = pickle.load(f)
+    info("Restored %s: batch %d, epoch %d, global step %d" % (prefix, snap[0], snap[1], snap[2]))
+    return snap

@@ -15,6 +15,7 @@ import torch
 
 from . import _native as nv
 from . import kernels as K
+from . import parallel
 
 BF16, F32 = torch.bfloat16, torch.float32
 POOL = {"avg": 0, "last": 1, "max": 2}
@@ -602,14 +603,13 @@ class Engine(object):
             A["labels"][:b].copy_(torch.from_numpy(lab), non_blocking=True)
         feat = self._encoder_fwd(frames, is_u8, n, True)
         logits = self._head_fwd(feat, n, True)
-        nv.call("vl_softmax_ce", logits, A["labels"][:b], b, c, 1.0 / (b * self.world), A["row_loss"],
+        nv.call("vl_softmax_ce", logits, A["labels"][:b], b, c, parallel.local_grad_scale(b, self.world), A["row_loss"],
                 self.scalars[4:6], A["dlogits"][:b], A["dlogits_bf"][:b], self.c_pad)
         self.grads.zero_()
         dfeat = self._head_bwd(n)
         self._encoder_bwd(dfeat, n)
         if self.world > 1:
-            torch.distributed.all_reduce(self.grads, group=self.group)
-            torch.distributed.all_reduce(self.scalars[4:6], group=self.group)
+            parallel.allreduce_gradients(self.grads, self.scalars[4:6], self.group)
         nv.call("vl_grad_sqnorms", self.grads, self.arena_n, self.seg_offsets, len(self.var_shapes), self.sqnorms)
         clip = float(cfg.clip_norm) if cfg.clip_norm else 0.0
         nv.call("vl_clip_scalars", self.sqnorms, len(self.var_shapes), clip, 1.0, self.scalars)
