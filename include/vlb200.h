@@ -113,6 +113,15 @@ int vl_maxpool_fwd(const void* x, void* y, void* argmax, int32_t n, int32_t h, i
 int vl_maxpool_bwd(const void* dy, const void* argmax, void* dx, const void* relu_of, int32_t n, int32_t h,
                    int32_t w, int32_t c, vl_stream_t stream);
 
+/* Fused LRN -> max-pool forward (alexnet.py:85-98,126-139): y = max_pool(lrn(x)); lrn(x) is never written to HBM.
+ * Same result as vl_lrn_fwd followed by vl_maxpool_fwd (lrn(x) is rounded to bf16 before the max in both). */
+int vl_lrn_pool_fwd(const void* x, void* y, void* argmax, int32_t n, int32_t h, int32_t w, int32_t c,
+                    int32_t radius, float alpha, float beta, float bias, vl_stream_t stream);
+/* Fused MaxPoolGrad -> LRNGrad -> ReluGrad: dx = relu'(x) * lrn_grad(x, maxpool_grad(dy, argmax)); when dbias is
+ * not NULL it also accumulates the bias gradient sum_pixels dx (dbias must be zeroed). */
+int vl_pool_lrn_bwd(const void* x, const void* dy, const void* argmax, void* dx, float* dbias, int32_t n, int32_t h,
+                    int32_t w, int32_t c, int32_t radius, float alpha, float beta, float bias, vl_stream_t stream);
+
 /* bias gradient: out[c] += sum_rows dy[row][c]  (bf16 in, fp32 accumulate; `out` must be zeroed). */
 int vl_colsum(const void* dy, float* out, int64_t rows, int32_t c, int32_t ld, vl_stream_t stream);
 
@@ -139,6 +148,14 @@ int vl_lstm_fwd(const float* gx, const float* w_h, float* acts, float* cs, float
  * the pre-activation gates) which feeds the tensor-core data/filter gradient GEMMs.  w_h_t = w_h^T [4h][h]. */
 int vl_lstm_bwd(const float* dh_seq, const float* acts, const float* cs, const float* w_h_t, void* dg,
                 int32_t batch, int32_t t_len, int32_t hidden, vl_stream_t stream);
+/* Persistent variants for hidden == 256: a cluster of 8 CTAs keeps the recurrent weights (fp32, kernel[d:], NOT
+ * transposed for both directions) resident in shared memory for all timesteps of its 8 clips and exchanges h_t /
+ * dh_t through distributed shared memory.  Same results as vl_lstm_fwd / vl_lstm_bwd. */
+int vl_lstm_fwd_cluster(const float* gx, const float* w_h, float* acts, float* cs, float* h_seq, void* h_seq_bf16,
+                        void* h_prev_bf16, int32_t batch, int32_t t_len, int32_t hidden, float forget_bias,
+                        vl_stream_t stream);
+int vl_lstm_bwd_cluster(const float* dh_seq, const float* acts, const float* cs, const float* w_h, void* dg,
+                        int32_t batch, int32_t t_len, int32_t hidden, vl_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Pooling / loss head.

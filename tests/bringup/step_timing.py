@@ -45,3 +45,18 @@ print("train step: %.3f ms  %.1f clips/s  (%.1f%% of sustained tensor peak), lau
     ms, clips / ms * 1e3, clips / ms * 1e3 * 68.326e9 / 1371.0e12 * 100, (l1 - l0) // 7), flush=True)
 print("loss etc:", eng.train_step(frames, labels, 1e-3))
 print("max mem GB", torch.cuda.max_memory_allocated() / 1e9)
+
+if "--profile" in sys.argv:
+    from torch.profiler import profile, ProfilerActivity
+    import re
+    for what, fn in (("forward", lambda: eng.forward_device(frames)), ("train", lambda: eng.train_step(frames, labels, 1e-3))):
+        fn(); torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            fn(); torch.cuda.synchronize()
+        evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+        evs.sort(key=lambda e: e.time_range.start)
+        tot = sum(e.device_time for e in evs)
+        print("== %s: %d kernels, %.1f us device time ==" % (what, len(evs), tot))
+        for i, e in enumerate(evs):
+            name = re.sub(r"\(.*", "", e.name).replace("(anonymous namespace)::", "").replace("void ", "")[:48]
+            print("%3d %-48s %9.1f us" % (i, name, e.device_time))

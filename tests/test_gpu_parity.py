@@ -134,8 +134,10 @@ def test_maxpool_fwd_bwd_bit_exact(vl, h, c):
     assert rel(dx.float().cpu().numpy(), dx_ref) < 1e-2  # sums of <= 4 bf16 values, rounded to bf16
 
 
-@pytest.mark.parametrize("batch,t_len,d_in,hidden", [(3, 4, 64, 32), (5, 16, 128, 256)])
-def test_lstm_fwd_bwd_vs_oracle(vl, batch, t_len, d_in, hidden):
+@pytest.mark.parametrize("batch,t_len,d_in,hidden,cluster", [(3, 4, 64, 32, False), (5, 16, 128, 256, False),
+                                                             (5, 16, 128, 256, True), (13, 3, 64, 256, True),
+                                                             (64, 16, 64, 256, True)])
+def test_lstm_fwd_bwd_vs_oracle(vl, batch, t_len, d_in, hidden, cluster):
     nv = vl["nv"]
     rng = np.random.default_rng(14)
     kern = (rng.uniform(-1, 1, size=(d_in + hidden, 4 * hidden)) * 0.2).astype(np.float32)
@@ -151,17 +153,57 @@ def test_lstm_fwd_bwd_vs_oracle(vl, batch, t_len, d_in, hidden):
     cs = torch.empty(n, hidden, device="cuda")
     hseq = torch.empty(n, hidden, device="cuda")
     hprev = torch.empty(n, hidden, dtype=torch.bfloat16, device="cuda")
-    nv.call("vl_lstm_fwd", gx, wh, acts, cs, hseq, None, hprev, batch, t_len, hidden, 1.0)
+    nv.call("vl_lstm_fwd_cluster" if cluster else "vl_lstm_fwd", gx, wh, acts, cs, hseq, None, hprev, batch, t_len,
+            hidden, 1.0)
     assert rel(hseq.cpu().numpy().reshape(out_ref.shape), out_ref) < 1e-4  # fp32 kernel
     dg = torch.empty(n, 4 * hidden, dtype=torch.bfloat16, device="cuda")
-    wht = dev(np.ascontiguousarray(kern[d_in:].T))
-    nv.call("vl_lstm_bwd", dev(dout.reshape(n, hidden)), acts, cs, wht, dg, batch, t_len, hidden)
+    if cluster:
+        nv.call("vl_lstm_bwd_cluster", dev(dout.reshape(n, hidden)), acts, cs, wh, dg, batch, t_len, hidden)
+    else:
+        wht = dev(np.ascontiguousarray(kern[d_in:].T))
+        nv.call("vl_lstm_bwd", dev(dout.reshape(n, hidden)), acts, cs, wht, dg, batch, t_len, hidden)
     dgf = dg.float().cpu().numpy()
     # d(kernel) = [x, h_prev]^T dg ; compare against the oracle through the gate gradients
     xh = np.concatenate([x.reshape(n, d_in), hprev.float().cpu().numpy()], axis=1)
     assert rel(xh.T @ dgf, dks[0]) < BF16_TOL
     assert rel(dgf.sum(axis=0), dbs[0]) < BF16_TOL
     assert rel(dgf @ kern[:d_in].T, dx_ref.reshape(n, d_in)) < BF16_TOL
+
+
+@pytest.mark.parametrize("h,c", [(57, 96), (28, 256)])
+def test_fused_lrn_pool_matches_unfused_and_oracle(vl, h, c):
+    nv = vl["nv"]
+    rng = np.random.default_rng(18)
+    n = 2
+    x = bf16_round(np.maximum(rng.standard_normal((n, h, h, c)) * 30, 0))
+    p = (h - 3) // 2 + 1
+    dy = bf16_round(rng.standard_normal((n, p, p, c)))
+    xd, dyd = dev(x, torch.bfloat16), dev(dy, torch.bfloat16)
+    # forward: fused == lrn_fwd -> maxpool_fwd up to one bf16 rounding of lrn(x) (fp32 contraction differences)
+    nrm = torch.empty_like(xd)
+    nv.call("vl_lrn_fwd", xd, nrm, n * h * h, c, 2, 2e-05, 0.75, 1.0)
+    y0 = torch.empty(n, p, p, c, dtype=torch.bfloat16, device="cuda")
+    a0 = torch.empty(n, p, p, c, dtype=torch.uint8, device="cuda")
+    nv.call("vl_maxpool_fwd", nrm, y0, a0, n, h, h, c)
+    y1, a1 = torch.empty_like(y0), torch.empty_like(a0)
+    nv.call("vl_lrn_pool_fwd", xd, y1, a1, n, h, h, c, 2, 2e-05, 0.75, 1.0)
+    assert rel(y1.float().cpu().numpy(), y0.float().cpu().numpy()) < 1e-2
+    assert (a0 == a1).float().mean().item() > 0.995  # argmax may move only between (near-)tied window entries
+    y_ref, arg_ref = O.maxpool_3x3s2(O.bf16_round(O.lrn(x)))
+    assert rel(y1.float().cpu().numpy(), y_ref) < 1e-2
+    # backward: fused == maxpool_bwd -> lrn_bwd(+relu) within rounding, and matches the oracle; bias gradient too
+    dn = torch.empty_like(xd)
+    nv.call("vl_maxpool_bwd", dyd, a0, dn, None, n, h, h, c)
+    dx0 = torch.empty_like(xd)
+    nv.call("vl_lrn_bwd", xd, dn, dx0, n * h * h, c, 2, 2e-05, 0.75, 1.0, 1)
+    dx1 = torch.empty_like(xd)
+    db = torch.zeros(c, device="cuda")
+    nv.call("vl_pool_lrn_bwd", xd, dyd, a0, dx1, db, n, h, h, c, 2, 2e-05, 0.75, 1.0)
+    assert rel(dx1.float().cpu().numpy(), dx0.float().cpu().numpy()) < 1e-2
+    dn_ref = O.bf16_round(O.maxpool_3x3s2_backward(x.shape, a0.cpu().numpy().astype(np.int64), dy))
+    dx_ref = O.lrn_backward(x, dn_ref) * (x > 0)
+    assert rel(dx1.float().cpu().numpy(), dx_ref) < 1e-2
+    assert rel(db.cpu().numpy(), dx1.float().cpu().numpy().reshape(-1, c).sum(0)) < 1e-4
 
 
 def test_segment_pool_bit_exact_vs_numpy(vl):
@@ -390,7 +432,8 @@ def _oracle_backward_on_device_state(eng, cfg, params, frames, onehot, mask):
     def f(t):
         return t.float().cpu().numpy()
 
-    ac = {k: f(A[k][:n]) for k in ("a1", "n1", "p1", "a2", "n2", "p2", "a3", "a4", "a5", "p5", "f6", "f7")}
+    ac = {k: f(A[k][:n]) for k in ("a1", "p1", "a2", "p2", "a3", "a4", "a5", "p5", "f6", "f7")}
+    ac["n1"], ac["n2"] = q(O.lrn(ac["a1"])), q(O.lrn(ac["a2"]))  # never materialised on the device (fused LRN+pool)
     for k in ("arg1", "arg2", "arg5"):
         ac[k] = A[k][:n].cpu().numpy().astype(np.int64)
     ac["x0"] = q(frames)

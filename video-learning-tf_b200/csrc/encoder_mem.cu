@@ -37,53 +37,70 @@ __device__ __forceinline__ Bf16x8 pack8(const float (&f)[8]) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// conv1 patch matrix
+// conv1 patch matrix.  One CTA per (frame, output row): the kh input rows it needs are staged once in shared
+// memory as mean-subtracted bf16 with the SAME zero padding materialised, then every 16-byte chunk of the 57
+// patch rows is a gather of 8 shared-memory elements through a k -> (row, column) offset table.  Global reads
+// are row-contiguous, global writes are fully coalesced 16B vectors (the kernel is bound by the 2.5 GB it writes).
 // ------------------------------------------------------------------------------------------------
 template <bool U8>
-__global__ void conv1_patches_kernel(const void* __restrict__ frames_, const float* __restrict__ mean3,
-                                     bf16* __restrict__ col, int n, int h, int w, int kh, int kw, int stride,
-                                     int pad_top, int pad_left, int p, int q, int k_ld, long long total_chunks) {
-  const int chunks_per_row = k_ld >> 3;
-  const int kvalid = kh * kw * 3;
-  float m0 = 0.f, m1 = 0.f, m2 = 0.f;
+__global__ void __launch_bounds__(256)
+    conv1_patches_kernel(const void* __restrict__ frames_, const float* __restrict__ mean3, bf16* __restrict__ col,
+                         int h, int w, int kh, int kw, int stride, int pad_top, int pad_left, int p, int q, int k_ld,
+                         int pitch) {
+  extern __shared__ uint8_t smem_raw[];
+  bf16* rows = reinterpret_cast<bf16*>(smem_raw);                       // [kh][pitch]
+  uint16_t* koff = reinterpret_cast<uint16_t*>(rows + kh * pitch);     // [k_ld]
+  const int pp = blockIdx.x % p;
+  const int nn = blockIdx.x / p;
+  const int row_elems = kw * 3;
+  const int kvalid = kh * row_elems;
+  float m[3] = {0.f, 0.f, 0.f};
   if (U8 && mean3 != nullptr) {
-    m0 = mean3[0];
-    m1 = mean3[1];
-    m2 = mean3[2];
+    m[0] = mean3[0];
+    m[1] = mean3[1];
+    m[2] = mean3[2];
   }
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total_chunks;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const long long row = idx / chunks_per_row;
-    const int ch = (int)(idx - row * chunks_per_row);
-    const int qq = (int)(row % q);
-    const long long t = row / q;
-    const int pp = (int)(t % p);
-    const int nn = (int)(t / p);
-    const int y0 = pp * stride - pad_top;
-    const int x0 = qq * stride - pad_left;
-    float f[8];
+  for (int k = threadIdx.x; k < k_ld; k += blockDim.x) {
+    int off = 0xFFFF;  // sentinel: zero column of the K padding
+    if (k < kvalid) {
+      const int r = k / row_elems;
+      off = r * pitch + (k - r * row_elems);
+    }
+    koff[k] = (uint16_t)off;
+  }
+  const int y0 = pp * stride - pad_top;
+  const int lead = pad_left * 3;
+  for (int idx = threadIdx.x; idx < kh * pitch; idx += blockDim.x) {
+    const int r = idx / pitch;
+    const int e = idx - r * pitch;
+    const int y = y0 + r;
+    const int xe = e - lead;  // element index inside the image row (x*3 + c)
+    float v = 0.f;
+    if (y >= 0 && y < h && xe >= 0 && xe < w * 3) {
+      const long long off = ((long long)nn * h + y) * (w * 3) + xe;
+      if (U8) {
+        const int c = xe % 3;
+        v = (float)reinterpret_cast<const uint8_t*>(frames_)[off] - m[c];
+      } else {
+        v = reinterpret_cast<const float*>(frames_)[off];
+      }
+    }
+    rows[idx] = __float2bfloat16_rn(v);
+  }
+  __syncthreads();
+  const int cpr = k_ld >> 3;
+  const long long row0 = ((long long)nn * p + pp) * q;
+  for (int idx = threadIdx.x; idx < q * cpr; idx += blockDim.x) {
+    const int qq = idx / cpr;
+    const int ch = idx - qq * cpr;
+    const int base = qq * stride * 3;
+    alignas(16) bf16 v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int kk = ch * 8 + j;
-      float v = 0.f;
-      if (kk < kvalid) {
-        const int tap = kk / 3;
-        const int c = kk - tap * 3;
-        const int r = tap / kw;
-        const int s = tap - r * kw;
-        const int y = y0 + r, x = x0 + s;
-        if (y >= 0 && y < h && x >= 0 && x < w) {
-          const long long off = (((long long)nn * h + y) * w + x) * 3 + c;
-          if (U8) {
-            v = (float)reinterpret_cast<const uint8_t*>(frames_)[off] - (c == 0 ? m0 : (c == 1 ? m1 : m2));
-          } else {
-            v = reinterpret_cast<const float*>(frames_)[off];
-          }
-        }
-      }
-      f[j] = v;
+      const int o = koff[ch * 8 + j];
+      v[j] = (o == 0xFFFF) ? __float2bfloat16_rn(0.f) : rows[o + base];
     }
-    *reinterpret_cast<Bf16x8*>(col + row * k_ld + ch * 8) = pack8(f);
+    *reinterpret_cast<uint4*>(col + (row0 + qq) * k_ld + ch * 8) = *reinterpret_cast<const uint4*>(v);
   }
 }
 
@@ -293,6 +310,187 @@ __global__ void maxpool_bwd_kernel(const bf16* __restrict__ dy, const uint8_t* _
 }
 
 // ------------------------------------------------------------------------------------------------
+// Fused LRN + max-pool (forward) and max-pool-grad + LRN-grad + ReLU-grad (+ bias gradient) (backward).
+// The normalised tensor n = lrn(a) and its gradient dn are never written to HBM: the forward recomputes the LRN
+// inside each 3x3 window (radius 2, beta .75 fast path), the backward rebuilds dn for the 12 channels an 8-channel
+// chunk depends on from the pooled gradient and the saved argmax codes.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load_window16(const bf16* __restrict__ row, int c0, int c, float (&v)[16]) {
+  // channels [c0-4, c0+12) of one pixel, zero outside [0, c)
+  float t[8];
+  unpack8(*reinterpret_cast<const Bf16x8*>(row + c0), t);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[4 + j] = t[j];
+  if (c0 >= 8) {
+    const uint2 l = *reinterpret_cast<const uint2*>(row + c0 - 4);
+    const __nv_bfloat162* lp = reinterpret_cast<const __nv_bfloat162*>(&l);
+    float2 a = __bfloat1622float2(lp[0]), b = __bfloat1622float2(lp[1]);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+  } else {
+    v[0] = v[1] = v[2] = v[3] = 0.f;
+  }
+  if (c0 + 8 < c) {
+    const uint2 r = *reinterpret_cast<const uint2*>(row + c0 + 8);
+    const __nv_bfloat162* rp = reinterpret_cast<const __nv_bfloat162*>(&r);
+    float2 a = __bfloat1622float2(rp[0]), b = __bfloat1622float2(rp[1]);
+    v[12] = a.x; v[13] = a.y; v[14] = b.x; v[15] = b.y;
+  } else {
+    v[12] = v[13] = v[14] = v[15] = 0.f;
+  }
+}
+
+__global__ void lrn_pool_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, uint8_t* __restrict__ arg, int n,
+                                    int h, int w, int c, int p, int q, float alpha, float bias,
+                                    long long total_chunks) {
+  const int cpr = c >> 3;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total_chunks;
+       idx += (long long)gridDim.x * blockDim.x) {
+    long long pix = idx / cpr;
+    const int c0 = (int)(idx - pix * cpr) * 8;
+    const int qq = (int)(pix % q);
+    const long long t = pix / q;
+    const int pp = (int)(t % p);
+    const int nn = (int)(t / p);
+    float best[8];
+    int bi[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      best[j] = -INFINITY;
+      bi[j] = 0;
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const bf16* src = x + (((long long)nn * h + (pp * 2 + r)) * w + (qq * 2 + s)) * c;
+        float v[16];
+        load_window16(src, c0, c, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float acc = 0.f;
+#pragma unroll
+          for (int o = 2; o <= 6; ++o) acc = fmaf(v[j + o], v[j + o], acc);
+          const float sc = bias + alpha * acc;
+          const float rs = rsqrtf(sc);
+          // the unfused path stores lrn(a) in bf16 before pooling: round here too so both paths agree bit for bit
+          const float val = __bfloat162float(__float2bfloat16_rn(v[4 + j] * (rs * sqrtf(rs))));
+          if (val > best[j]) {
+            best[j] = val;
+            bi[j] = r * 3 + s;
+          }
+        }
+      }
+    }
+    *reinterpret_cast<Bf16x8*>(y + pix * c + c0) = pack8(best);
+    uint32_t lo = bi[0] | (bi[1] << 8) | (bi[2] << 16) | (bi[3] << 24);
+    uint32_t hi = bi[4] | (bi[5] << 8) | (bi[6] << 16) | (bi[7] << 24);
+    *reinterpret_cast<uint2*>(arg + pix * c + c0) = make_uint2(lo, hi);
+  }
+}
+
+__global__ void pool_lrn_bwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy,
+                                    const uint8_t* __restrict__ arg, bf16* __restrict__ dx, float* __restrict__ dbias,
+                                    int n, int h, int w, int c, int p, int q, float alpha, float beta, float bias,
+                                    long long total_chunks) {
+  extern __shared__ float bsum[];  // [c] per-block bias-gradient partials
+  if (dbias != nullptr) {
+    for (int i = threadIdx.x; i < c; i += blockDim.x) bsum[i] = 0.f;
+    __syncthreads();
+  }
+  const int cpr = c >> 3;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total_chunks;
+       idx += (long long)gridDim.x * blockDim.x) {
+    long long pix = idx / cpr;
+    const int c0 = (int)(idx - pix * cpr) * 8;
+    const int ww = (int)(pix % w);
+    const long long t = pix / w;
+    const int hh = (int)(t % h);
+    const int nn = (int)(t / h);
+    // dn for channels [c0-2, c0+10): pooled gradient routed through the saved argmax codes (bf16 rounded, as the
+    // unfused path stores it)
+    float gv[12];
+#pragma unroll
+    for (int j = 0; j < 12; ++j) gv[j] = 0.f;
+    const int p_lo = max(0, (hh - 1) >> 1), p_hi = min(p - 1, hh >> 1);
+    const int q_lo = max(0, (ww - 1) >> 1), q_hi = min(q - 1, ww >> 1);
+    for (int pp = p_lo; pp <= p_hi; ++pp) {
+      const int r = hh - 2 * pp;
+      if (r < 0 || r > 2) continue;
+      for (int qq = q_lo; qq <= q_hi; ++qq) {
+        const int s = ww - 2 * qq;
+        if (s < 0 || s > 2) continue;
+        const long long opix = ((long long)nn * p + pp) * q + qq;
+        const uint32_t code = r * 3 + s;
+        const uint8_t* ap = arg + opix * c;
+        const bf16* gp = dy + opix * c;
+        float g[8];
+        unpack8(*reinterpret_cast<const Bf16x8*>(gp + c0), g);
+        const uint2 a = *reinterpret_cast<const uint2*>(ap + c0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t aj = ((j < 4 ? a.x : a.y) >> (8 * (j & 3))) & 0xffu;
+          if (aj == code) gv[2 + j] += g[j];
+        }
+        if (c0 >= 8) {
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+            if (ap[c0 - 2 + j] == code) gv[j] += __bfloat162float(gp[c0 - 2 + j]);
+        }
+        if (c0 + 8 < c) {
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+            if (ap[c0 + 8 + j] == code) gv[10 + j] += __bfloat162float(gp[c0 + 8 + j]);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 12; ++j) gv[j] = __bfloat162float(__float2bfloat16_rn(gv[j]));
+    float xv[16];
+    load_window16(x + pix * c, c0, c, xv);
+    float tt[12];
+    float sp[8];
+#pragma unroll
+    for (int d = 0; d < 12; ++d) {
+      float acc = 0.f;
+#pragma unroll
+      for (int o = 0; o < 5; ++o) acc = fmaf(xv[d + o], xv[d + o], acc);
+      const float sc = bias + alpha * acc;
+      float pw, inv;
+      if (beta == 0.75f) {
+        const float rs = rsqrtf(sc);
+        pw = rs * sqrtf(rs);
+        inv = rs * rs;
+      } else {
+        pw = __powf(sc, -beta);
+        inv = 1.0f / sc;
+      }
+      tt[d] = gv[d] * xv[2 + d] * pw * inv;
+      if (d >= 2 && d < 10) sp[d - 2] = pw;
+    }
+    float out[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float sum = tt[j] + tt[j + 1] + tt[j + 2] + tt[j + 3] + tt[j + 4];
+      float g = gv[2 + j] * sp[j] - 2.0f * alpha * beta * xv[4 + j] * sum;
+      if (!(xv[4 + j] > 0.f)) g = 0.f;  // ReLU gradient of the producing conv
+      out[j] = g;
+    }
+    const Bf16x8 packed = pack8(out);
+    *reinterpret_cast<Bf16x8*>(dx + pix * c + c0) = packed;
+    if (dbias != nullptr) {
+      float rb[8];
+      unpack8(packed, rb);  // the bias gradient sums the bf16 values that are stored (as vl_colsum would)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(&bsum[c0 + j], rb[j]);
+    }
+  }
+  if (dbias != nullptr) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < c; i += blockDim.x) atomicAdd(dbias + i, bsum[i]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // column sums (bias gradients)
 // ------------------------------------------------------------------------------------------------
 constexpr int COLSUM_THREADS = 256;
@@ -403,14 +601,20 @@ extern "C" int vl_conv1_patches(const void* frames, int is_u8, const float* mean
                                 int32_t p, int32_t q, int32_t k_ld, vl_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   VL_REQUIRE(frames && col && k_ld % 8 == 0 && k_ld >= kh * kw * 3, "vl_conv1_patches: bad arguments");
-  const long long total = (long long)n * p * q * (k_ld / 8);
-  const int block = 256;
+  // widest element touched: ((q-1)*stride - pad_left + kw - 1) * 3 + 2, shifted by the left padding
+  int pitch = ((q - 1) * stride + kw) * 3;
+  if (pitch < (w + pad_left) * 3) pitch = (w + pad_left) * 3;
+  pitch = (pitch + 1) & ~1;
+  VL_REQUIRE(kh * pitch < 65535, "vl_conv1_patches: image row too wide for the 16-bit offset table");
+  const size_t smem = (size_t)kh * pitch * sizeof(bf16) + (size_t)k_ld * sizeof(uint16_t);
+  VL_REQUIRE(smem <= 48 * 1024, "vl_conv1_patches: %zu bytes of shared memory needed (> 48 KB)", smem);
+  const int grid = n * p;
   if (is_u8)
-    conv1_patches_kernel<true><<<sweep_grid(total, block), block, 0, stream>>>(
-        frames, mean3, reinterpret_cast<bf16*>(col), n, h, w, kh, kw, stride, pad_top, pad_left, p, q, k_ld, total);
+    conv1_patches_kernel<true><<<grid, 256, smem, stream>>>(frames, mean3, reinterpret_cast<bf16*>(col), h, w, kh, kw,
+                                                            stride, pad_top, pad_left, p, q, k_ld, pitch);
   else
-    conv1_patches_kernel<false><<<sweep_grid(total, block), block, 0, stream>>>(
-        frames, mean3, reinterpret_cast<bf16*>(col), n, h, w, kh, kw, stride, pad_top, pad_left, p, q, k_ld, total);
+    conv1_patches_kernel<false><<<grid, 256, smem, stream>>>(frames, mean3, reinterpret_cast<bf16*>(col), h, w, kh, kw,
+                                                             stride, pad_top, pad_left, p, q, k_ld, pitch);
   VL_LAUNCHED();
   return 0;
 }
@@ -513,6 +717,36 @@ extern "C" int vl_transpose_f32(const float* src, float* dst, int32_t rows, int3
   VL_REQUIRE(src && dst && rows > 0 && cols > 0, "vl_transpose_f32: bad arguments");
   dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
   transpose_f32_kernel<<<grid, block, 0, stream>>>(src, dst, rows, cols);
+  VL_LAUNCHED();
+  return 0;
+}
+
+extern "C" int vl_lrn_pool_fwd(const void* x, void* y, void* argmax, int32_t n, int32_t h, int32_t w, int32_t c,
+                               int32_t radius, float alpha, float beta, float bias, vl_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  VL_REQUIRE(x && y && argmax && c % 8 == 0 && h >= 3 && w >= 3, "vl_lrn_pool_fwd: bad arguments");
+  VL_REQUIRE(radius == 2 && beta == 0.75f, "vl_lrn_pool_fwd: fused path serves depth_radius 2, beta 0.75 (alexnet.py:80-89)");
+  const int p = (h - 3) / 2 + 1, q = (w - 3) / 2 + 1;
+  const long long total = (long long)n * p * q * (c / 8);
+  lrn_pool_fwd_kernel<<<sweep_grid(total, 256), 256, 0, stream>>>(reinterpret_cast<const bf16*>(x),
+                                                                  reinterpret_cast<bf16*>(y),
+                                                                  reinterpret_cast<uint8_t*>(argmax), n, h, w, c, p, q,
+                                                                  alpha, bias, total);
+  VL_LAUNCHED();
+  return 0;
+}
+
+extern "C" int vl_pool_lrn_bwd(const void* x, const void* dy, const void* argmax, void* dx, float* dbias, int32_t n,
+                               int32_t h, int32_t w, int32_t c, int32_t radius, float alpha, float beta, float bias,
+                               vl_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  VL_REQUIRE(x && dy && argmax && dx && c % 8 == 0, "vl_pool_lrn_bwd: bad arguments");
+  VL_REQUIRE(radius == 2, "vl_pool_lrn_bwd: only depth_radius 2 (alexnet.py:80,121) is implemented");
+  const int p = (h - 3) / 2 + 1, q = (w - 3) / 2 + 1;
+  const long long total = (long long)n * h * w * (c / 8);
+  pool_lrn_bwd_kernel<<<sweep_grid(total, 256), 256, dbias ? c * sizeof(float) : 0, stream>>>(
+      reinterpret_cast<const bf16*>(x), reinterpret_cast<const bf16*>(dy), reinterpret_cast<const uint8_t*>(argmax),
+      reinterpret_cast<bf16*>(dx), dbias, n, h, w, c, p, q, alpha, beta, bias, total);
   VL_LAUNCHED();
   return 0;
 }

@@ -32,7 +32,7 @@ constexpr int TMEM_COLS = 512;              // 2 accumulator stages x 256 fp32 c
 constexpr int ACC_STRIDE_COLS = 256;
 constexpr int MAX_STAGES = 8;
 constexpr int SMEM_LIMIT = 232448;          // 227 KB opt-in maximum per CTA
-constexpr int BAR_REGION = 1024;
+constexpr int BAR_REGION = 2048;            // mbarriers + TMEM slot (256 B) + bias slice (1 KB)
 
 struct KParams {
   int M, N;  // valid extents per group
@@ -89,6 +89,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
   uint64_t* tmem_full = empty_bar + MAX_STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* sbias = reinterpret_cast<float*>(smem + 256);  // [256] bias slice of the current tile
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -117,6 +118,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 
   if (warp == 0) {
     // ===================== TMA producer =====================
+    // One thread issues every load; its loop must stay free of integer divisions (a dependent chain of
+    // software divides per k-block was measured to cap the whole pipeline at ~900 cycles per k-block), so
+    // the (tap, channel-chunk) and pixel coordinates advance with adds and compares only.
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
@@ -124,67 +128,90 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
         const TileCoord t = decode_tile(p, tile);
         const int m0 = t.m_blk * BM;
         const int n0 = t.n_blk * p.BN;
+        const int a_c0 = t.g * p.a_goff;
+        const int b_c0 = t.g * p.b_goff;
+        // contraction walk state (per tile: one division pair, then incremental)
+        int tap = 0, cc = 0, tr = 0, ts = 0;
+        if (p.taps > 1 || p.a_mode == VL_A_IM2COL_K) {
+          tap = t.kb_begin / p.cchunks;
+          cc = t.kb_begin - tap * p.cchunks;
+          tr = tap / p.kw;
+          ts = tap - tr * p.kw;
+        } else {
+          cc = t.kb_begin;
+        }
+        // pixel of the first row of the tile (im2col K-major) / of the first k-block (transposed im2col)
         int pn = 0, pp = 0, pq = 0;
+        int wx = 0, wy = 0;  // TMA base-pixel coordinates
+        int mn_tap_r[2] = {0, 0}, mn_tap_s[2] = {0, 0}, mn_c[2] = {0, 0};
+        int a_valid = 2;
         if (p.a_mode == VL_A_IM2COL_K) {
           pn = m0 / p.PQ;
           int rem = m0 - pn * p.PQ;
           pp = rem / p.Q;
           pq = rem - pp * p.Q;
+          wx = pq * p.stride_w + p.lower_w;
+          wy = pp * p.stride_h + p.lower_h;
+        } else if (p.a_mode == VL_A_IM2COL_MN) {
+          const int pix = t.kb_begin * BK;
+          pn = pix / p.PQ;
+          int rem = pix - pn * p.PQ;
+          pp = rem / p.Q;
+          pq = rem - pp * p.Q;
+          const int chunks = p.taps * p.cchunks;
+          a_valid = min(2, chunks - t.m_blk * 2);
+          for (int j = 0; j < a_valid; ++j) {
+            const int mc = t.m_blk * 2 + j;
+            const int tp = mc / p.cchunks;
+            mn_c[j] = a_c0 + (mc - tp * p.cchunks) * BK;
+            mn_tap_r[j] = tp / p.kw;
+            mn_tap_s[j] = tp - mn_tap_r[j] * p.kw;
+          }
         }
+        const uint32_t bytes = p.b_stage_bytes + (p.a_mode == VL_A_IM2COL_MN ? 8192u * a_valid : (uint32_t)A_STAGE_BYTES);
         for (int kb = t.kb_begin; kb < t.kb_end; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           uint8_t* sA = tiles + stage * p.stage_bytes;
           uint8_t* sB = sA + A_STAGE_BYTES;
-          // ---- expected bytes ----
-          uint32_t bytes = p.b_stage_bytes;
-          int a_valid = 2;
-          if (p.a_mode == VL_A_IM2COL_MN) {
-            int chunks = p.taps * p.cchunks;
-            a_valid = min(2, chunks - t.m_blk * 2);
-            bytes += 8192u * a_valid;
-          } else {
-            bytes += A_STAGE_BYTES;
-          }
           mbar_expect_tx(&full_bar[stage], bytes);
           // ---- A ----
           if (p.a_mode == VL_A_TILED_K) {
-            tma_load_2d(sA, &tmA, &full_bar[stage], t.g * p.a_goff + kb * BK, m0);
+            tma_load_2d(sA, &tmA, &full_bar[stage], a_c0 + kb * BK, m0);
           } else if (p.a_mode == VL_A_TILED_MN) {
-            tma_load_2d(sA, &tmA, &full_bar[stage], t.g * p.a_goff + m0, kb * BK);
-            tma_load_2d(sA + 8192, &tmA, &full_bar[stage], t.g * p.a_goff + m0 + 64, kb * BK);
+            tma_load_2d(sA, &tmA, &full_bar[stage], a_c0 + m0, kb * BK);
+            tma_load_2d(sA + 8192, &tmA, &full_bar[stage], a_c0 + m0 + 64, kb * BK);
           } else if (p.a_mode == VL_A_IM2COL_K) {
-            int tap = kb / p.cchunks;
-            int cc = kb - tap * p.cchunks;
-            int r = tap / p.kw;
-            int s = tap - r * p.kw;
-            tma_load_im2col_4d(sA, &tmA, &full_bar[stage], t.g * p.a_goff + cc * BK, pq * p.stride_w + p.lower_w,
-                               pp * p.stride_h + p.lower_h, pn, (uint16_t)s, (uint16_t)r);
-          } else {  // VL_A_IM2COL_MN
-            int pix = kb * BK;
-            int n_ = pix / p.PQ;
-            int rem = pix - n_ * p.PQ;
-            int p_ = rem / p.Q;
-            int q_ = rem - p_ * p.Q;
-            for (int j = 0; j < a_valid; ++j) {
-              int mc = t.m_blk * 2 + j;
-              int tap = mc / p.cchunks;
-              int cc = mc - tap * p.cchunks;
-              int r = tap / p.kw;
-              int s = tap - r * p.kw;
-              tma_load_im2col_4d(sA + j * 8192, &tmA, &full_bar[stage], t.g * p.a_goff + cc * BK,
-                                 q_ * p.stride_w + p.lower_w, p_ * p.stride_h + p.lower_h, n_, (uint16_t)s,
-                                 (uint16_t)r);
+            tma_load_im2col_4d(sA, &tmA, &full_bar[stage], a_c0 + cc * BK, wx, wy, pn, (uint16_t)ts, (uint16_t)tr);
+          } else {  // VL_A_IM2COL_MN: this k-block's 64 pixels start at (pn, pp, pq)
+            const int bx = pq * p.stride_w + p.lower_w, by = pp * p.stride_h + p.lower_h;
+            for (int j = 0; j < a_valid; ++j)
+              tma_load_im2col_4d(sA + j * 8192, &tmA, &full_bar[stage], mn_c[j], bx, by, pn, (uint16_t)mn_tap_s[j],
+                                 (uint16_t)mn_tap_r[j]);
+            pq += BK;  // advance 64 pixels
+            while (pq >= p.Q) {
+              pq -= p.Q;
+              if (++pp == p.P) {
+                pp = 0;
+                ++pn;
+              }
             }
           }
           // ---- B ----
           if (p.b_mode == VL_B_TILED_K) {
-            int tap = kb / p.cchunks;
-            int cc = kb - tap * p.cchunks;
-            int tapb = p.flip ? (p.taps - 1 - tap) : tap;
-            tma_load_2d(sB, &tmB, &full_bar[stage], t.g * p.b_goff + cc * BK, n0 + tapb * p.b_tap_stride);
+            const int tapb = p.flip ? (p.taps - 1 - tap) : tap;
+            tma_load_2d(sB, &tmB, &full_bar[stage], b_c0 + cc * BK, n0 + tapb * p.b_tap_stride);
           } else {
             for (int j = 0; j < p.BN / 64; ++j)
-              tma_load_2d(sB + j * 8192, &tmB, &full_bar[stage], t.g * p.b_goff + n0 + j * 64, kb * BK);
+              tma_load_2d(sB + j * 8192, &tmB, &full_bar[stage], b_c0 + n0 + j * 64, kb * BK);
+          }
+          // ---- advance the contraction walk ----
+          if (++cc == p.cchunks && (p.taps > 1 || p.a_mode == VL_A_IM2COL_K)) {
+            cc = 0;
+            ++tap;
+            if (++ts == p.kw) {
+              ts = 0;
+              ++tr;
+            }
           }
           if (++stage == p.num_stages) {
             stage = 0;
@@ -231,6 +258,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
   } else {
     // ===================== epilogue warps (TMEM -> registers -> HBM) =====================
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    const int epi_tid = threadIdx.x - 64;
     int local = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++local) {
       const TileCoord t = decode_tile(p, tile);
@@ -253,25 +281,34 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
         row_ok = grow < p.M;
       }
       const int gcol0 = t.g * p.c_goff + n0;  // global column of tile column 0
+      // stage this tile's bias slice in shared memory once (instead of one global load per element)
+      if (p.bias != nullptr) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // previous tile's readers are done
+        for (int j = epi_tid; j < p.BN; j += 128) sbias[j] = (n0 + j < p.N) ? __ldg(p.bias + gcol0 + j) : 0.f;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + acc * ACC_STRIDE_COLS;
       const bool vec_ok = (p.c_ld % 8 == 0) && (gcol0 % 8 == 0) && !p.c_atomic &&
                           (p.mask == nullptr || p.mask_ld % 8 == 0);
-      for (int c0 = 0; c0 < p.BN; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld_x16(taddr + c0, v);
-        tmem_ld_wait();
-        if (!row_ok) continue;
+
+      auto process = [&](const uint32_t (&v)[16], int c0) {
+        if (!row_ok) return;
         const int ncols = min(16, p.N - (n0 + c0));
-        if (ncols <= 0) continue;
+        if (ncols <= 0) return;
         float f[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
         if (p.bias != nullptr) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (j < ncols) f[j] += __ldg(p.bias + gcol0 + c0 + j);
+          for (int j = 0; j < 4; ++j) {
+            const float4 bv = *reinterpret_cast<const float4*>(sbias + c0 + 4 * j);
+            f[4 * j] += bv.x;
+            f[4 * j + 1] += bv.y;
+            f[4 * j + 2] += bv.z;
+            f[4 * j + 3] += bv.w;
+          }
         }
         if (p.relu) {
 #pragma unroll
@@ -327,6 +364,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
             for (int j = 0; j < 16; ++j)
               if (j < ncols) out[j] = f[j];
           }
+        }
+      };
+
+      // software pipelined TMEM drain: the load of chunk i+1 is in flight while chunk i is processed
+      uint32_t va[16], vb[16];
+      tmem_ld_x16(taddr, va);
+      for (int c0 = 0; c0 < p.BN; c0 += 32) {
+        tmem_ld_wait();
+        const bool has_b = c0 + 16 < p.BN;
+        if (has_b) tmem_ld_x16(taddr + c0 + 16, vb);
+        process(va, c0);
+        if (has_b) {
+          tmem_ld_wait();
+          if (c0 + 32 < p.BN) tmem_ld_x16(taddr + c0 + 32, va);
+          process(vb, c0 + 16);
         }
       }
       tc_fence_before();

@@ -185,3 +185,264 @@ extern "C" int vl_lstm_bwd(const float* dh_seq, const float* acts, const float* 
   VL_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
+
+// =================================================================================================
+// Persistent cluster kernels (hidden == 256): the recurrent weights stay resident in shared memory.
+//
+// A cluster of 8 CTAs owns CB = 8 clips for the whole sequence.  CTA r holds the fp32 slice of kernel[D:] for its
+// 32 hidden units (4 gates x 32 = 128 columns, 256 x 129 floats = 132 KB, pitch 129 against bank conflicts) for all
+// timesteps.  Per step each CTA forms its 128 gate columns for the 8 clips (K split over two thread halves),
+// applies the cell update for its 32 units and publishes h_t to every CTA of the cluster through distributed
+// shared memory; one cluster barrier per step replaces the per-timestep launches of a while_loop.
+// The backward kernel walks time in reverse with the same residency: gate gradients stay fp32 on chip for the
+// dh_{t-1} = dg * W_h^T recursion (partial sums exchanged all-to-all over DSMEM), bf16 copies go to HBM for the
+// tensor-core filter/data-gradient GEMMs.
+// =================================================================================================
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
+
+namespace {
+
+constexpr int CL = 8;          // CTAs per cluster
+constexpr int CH = 256;        // hidden size served by the cluster kernels
+constexpr int CU = CH / CL;    // hidden units per CTA (32)
+constexpr int CN = 4 * CU;     // gate columns per CTA (128)
+constexpr int CCB = 8;         // clips per cluster
+constexpr int WP = CN + 1;     // padded pitch of the weight slice
+constexpr int LSTM_CL_THREADS = 256;
+
+struct ClusterSmem {
+  float w[CH * WP];            // w[k][g*CU+u] = kernel[D+k][g*CH + rank*CU + u]
+  float h[2][CH][CCB];         // h_{t-1} of the 8 clips, k-major, double buffered (fwd) / recv partials (bwd)
+  float part[2][CN][CCB];      // K-half partial sums (fwd) / dg of this step [n][cb] in part[0] (bwd)
+};
+
+__device__ __forceinline__ void load_w_slice(float* w, const float* __restrict__ w_h, int rank) {
+  for (int idx = threadIdx.x; idx < CH * CN; idx += LSTM_CL_THREADS) {
+    const int k = idx / CN, col = idx - k * CN;
+    const int g = col / CU, u = col - g * CU;
+    w[k * WP + col] = w_h[(long long)k * (4 * CH) + g * CH + rank * CU + u];
+  }
+}
+
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(LSTM_CL_THREADS, 1)
+    lstm_fwd_cluster_kernel(const float* __restrict__ gx, const float* __restrict__ w_h, float* __restrict__ acts,
+                            float* __restrict__ cs, float* __restrict__ h_seq, bf16* __restrict__ h_seq_bf16,
+                            bf16* __restrict__ h_prev_bf16, int batch, int t_len, float forget_bias) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  ClusterSmem& S = *reinterpret_cast<ClusterSmem*>(smem_raw);
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int b0 = (blockIdx.x / CL) * CCB;
+  const int tid = threadIdx.x;
+  load_w_slice(S.w, w_h, rank);
+  for (int idx = tid; idx < CH * CCB; idx += LSTM_CL_THREADS) (&S.h[0][0][0])[idx] = 0.f;
+  // matmul role: column `col`, K half `kh`
+  const int col = tid & (CN - 1);
+  const int khalf = tid >> 7;
+  // cell role: unit u, clip cb
+  const int u = tid & (CU - 1);
+  const int cb = tid >> 5;
+  const int b = b0 + cb;
+  const bool live = b < batch;
+  const int junit = rank * CU + u;
+  float c = 0.f;
+  float gxr[4] = {0.f, 0.f, 0.f, 0.f};
+  if (live) {
+    const float* g = gx + ((long long)b * t_len) * (4 * CH) + junit;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) gxr[q] = g[q * CH];
+  }
+  cluster.sync();
+  for (int t = 0; t < t_len; ++t) {
+    const int cur = t & 1;
+    float pre[4] = {gxr[0], gxr[1], gxr[2], gxr[3]};
+    if (live && t + 1 < t_len) {  // prefetch the next step's input projection
+      const float* g = gx + ((long long)b * t_len + t + 1) * (4 * CH) + junit;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) gxr[q] = g[q * CH];
+    }
+    if (t > 0) {
+      float acc[CCB];
+#pragma unroll
+      for (int i = 0; i < CCB; ++i) acc[i] = 0.f;
+      const float* hk = &S.h[cur][khalf * (CH / 2)][0];
+      const float* wk = S.w + khalf * (CH / 2) * WP + col;
+#pragma unroll 4
+      for (int k = 0; k < CH / 2; ++k) {
+        const float wv = wk[k * WP];
+        const float4 h0 = *reinterpret_cast<const float4*>(hk + k * CCB);
+        const float4 h1 = *reinterpret_cast<const float4*>(hk + k * CCB + 4);
+        acc[0] = fmaf(h0.x, wv, acc[0]);
+        acc[1] = fmaf(h0.y, wv, acc[1]);
+        acc[2] = fmaf(h0.z, wv, acc[2]);
+        acc[3] = fmaf(h0.w, wv, acc[3]);
+        acc[4] = fmaf(h1.x, wv, acc[4]);
+        acc[5] = fmaf(h1.y, wv, acc[5]);
+        acc[6] = fmaf(h1.z, wv, acc[6]);
+        acc[7] = fmaf(h1.w, wv, acc[7]);
+      }
+      float4* dst = reinterpret_cast<float4*>(&S.part[khalf][col][0]);
+      dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+      __syncthreads();
+#pragma unroll
+      for (int q = 0; q < 4; ++q) pre[q] += S.part[0][q * CU + u][cb] + S.part[1][q * CU + u][cb];
+    }
+    const float hprev = S.h[cur][junit][cb];
+    const float si = sigmoidf_(pre[0]);
+    const float tj = tanhf(pre[1]);
+    const float sf = sigmoidf_(pre[2] + forget_bias);
+    const float so = sigmoidf_(pre[3]);
+    c = c * sf + si * tj;
+    const float h = tanhf(c) * so;
+    // publish h_t[junit][cb] to every CTA of the cluster (next step's operand)
+#pragma unroll
+    for (int r = 0; r < CL; ++r) {
+      float* remote = cluster.map_shared_rank(&S.h[cur ^ 1][0][0], r);
+      remote[junit * CCB + cb] = h;
+    }
+    if (live) {
+      const long long row = (long long)b * t_len + t;
+      if (acts != nullptr) {
+        float* a = acts + row * (4 * CH) + junit;
+        a[0] = si;
+        a[CH] = tj;
+        a[2 * CH] = sf;
+        a[3 * CH] = so;
+      }
+      if (cs != nullptr) cs[row * CH + junit] = c;
+      if (h_seq != nullptr) h_seq[row * CH + junit] = h;
+      if (h_seq_bf16 != nullptr) h_seq_bf16[row * CH + junit] = __float2bfloat16_rn(h);
+      if (h_prev_bf16 != nullptr) h_prev_bf16[row * CH + junit] = __float2bfloat16_rn(hprev);
+    }
+    cluster.sync();  // h_t visible cluster-wide; also orders the reuse of S.part and S.h[cur]
+  }
+}
+
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(LSTM_CL_THREADS, 1)
+    lstm_bwd_cluster_kernel(const float* __restrict__ dh_seq, const float* __restrict__ acts,
+                            const float* __restrict__ cs, const float* __restrict__ w_h, bf16* __restrict__ dg,
+                            int batch, int t_len) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  ClusterSmem& S = *reinterpret_cast<ClusterSmem*>(smem_raw);
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int b0 = (blockIdx.x / CL) * CCB;
+  const int tid = threadIdx.x;
+  load_w_slice(S.w, w_h, rank);
+  // recv[parity][src][u][cb] aliases S.h[parity] (CL * CU * CCB = CH * CCB floats)
+  for (int idx = tid; idx < 2 * CH * CCB; idx += LSTM_CL_THREADS) (&S.h[0][0][0])[idx] = 0.f;
+  const int u = tid & (CU - 1);
+  const int cb = tid >> 5;
+  const int b = b0 + cb;
+  const bool live = b < batch;
+  const int junit = rank * CU + u;
+  float dc_next = 0.f;
+  cluster.sync();
+  for (int t = t_len - 1; t >= 0; --t) {
+    const int par = t & 1;
+    // dh_next = sum over source CTAs of the partials they sent for my units (zero at t = T-1)
+    float dh = 0.f;
+    {
+      const float* recv = &S.h[par ^ 1][0][0];
+#pragma unroll
+      for (int src = 0; src < CL; ++src) dh += recv[(src * CU + u) * CCB + cb];
+    }
+    float d_i = 0.f, d_j = 0.f, d_f = 0.f, d_o = 0.f;
+    if (live) {
+      const long long row = (long long)b * t_len + t;
+      const float* a = acts + row * (4 * CH) + junit;
+      const float si = a[0], tj = a[CH], sf = a[2 * CH], so = a[3 * CH];
+      const float ct = cs[row * CH + junit];
+      const float cprev = t > 0 ? cs[(row - 1) * CH + junit] : 0.f;
+      const float tc = tanhf(ct);
+      dh += dh_seq[row * CH + junit];
+      d_o = dh * tc * so * (1.f - so);
+      const float dc = dh * so * (1.f - tc * tc) + dc_next;
+      d_i = dc * tj * si * (1.f - si);
+      d_j = dc * si * (1.f - tj * tj);
+      d_f = dc * cprev * sf * (1.f - sf);
+      dc_next = dc * sf;
+      bf16* out = dg + row * (4 * CH) + junit;
+      out[0] = __float2bfloat16_rn(d_i);
+      out[CH] = __float2bfloat16_rn(d_j);
+      out[2 * CH] = __float2bfloat16_rn(d_f);
+      out[3 * CH] = __float2bfloat16_rn(d_o);
+    }
+    S.part[0][u][cb] = d_i;
+    S.part[0][CU + u][cb] = d_j;
+    S.part[0][2 * CU + u][cb] = d_f;
+    S.part[0][3 * CU + u][cb] = d_o;
+    __syncthreads();
+    if (t > 0) {
+      // partial dh_{t-1}[k][cb] over my 128 gate columns, thread = k
+      const int k = tid;
+      float acc[CCB];
+#pragma unroll
+      for (int i = 0; i < CCB; ++i) acc[i] = 0.f;
+      const float* wr = S.w + k * WP;
+#pragma unroll 4
+      for (int n = 0; n < CN; ++n) {
+        const float wv = wr[n];
+        const float4 g0 = *reinterpret_cast<const float4*>(&S.part[0][n][0]);
+        const float4 g1 = *reinterpret_cast<const float4*>(&S.part[0][n][4]);
+        acc[0] = fmaf(g0.x, wv, acc[0]);
+        acc[1] = fmaf(g0.y, wv, acc[1]);
+        acc[2] = fmaf(g0.z, wv, acc[2]);
+        acc[3] = fmaf(g0.w, wv, acc[3]);
+        acc[4] = fmaf(g1.x, wv, acc[4]);
+        acc[5] = fmaf(g1.y, wv, acc[5]);
+        acc[6] = fmaf(g1.z, wv, acc[6]);
+        acc[7] = fmaf(g1.w, wv, acc[7]);
+      }
+      // send to the CTA that owns unit k: recv[par][my rank][k % CU][cb]
+      float* remote = cluster.map_shared_rank(&S.h[par][0][0], k / CU) + (rank * CU + (k % CU)) * CCB;
+      reinterpret_cast<float4*>(remote)[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      reinterpret_cast<float4*>(remote)[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    }
+    cluster.sync();
+  }
+}
+
+}  // namespace
+
+extern "C" int vl_lstm_fwd_cluster(const float* gx, const float* w_h, float* acts, float* cs, float* h_seq,
+                                   void* h_seq_bf16, void* h_prev_bf16, int32_t batch, int32_t t_len, int32_t hidden,
+                                   float forget_bias, vl_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  VL_REQUIRE(gx && w_h && batch > 0 && t_len > 0, "vl_lstm_fwd_cluster: bad arguments");
+  VL_REQUIRE(hidden == CH, "vl_lstm_fwd_cluster: the resident-weight kernel serves hidden == %d", CH);
+  static bool attr = false;
+  if (!attr) {
+    VL_CHECK_CUDA(cudaFuncSetAttribute(lstm_fwd_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)sizeof(ClusterSmem)));
+    attr = true;
+  }
+  const int clusters = (batch + CCB - 1) / CCB;
+  lstm_fwd_cluster_kernel<<<clusters * CL, LSTM_CL_THREADS, sizeof(ClusterSmem), stream>>>(
+      gx, w_h, acts, cs, h_seq, reinterpret_cast<bf16*>(h_seq_bf16), reinterpret_cast<bf16*>(h_prev_bf16), batch, t_len,
+      forget_bias);
+  vl::g_launches.fetch_add(1);
+  VL_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int vl_lstm_bwd_cluster(const float* dh_seq, const float* acts, const float* cs, const float* w_h, void* dg,
+                                   int32_t batch, int32_t t_len, int32_t hidden, vl_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  VL_REQUIRE(dh_seq && acts && cs && w_h && dg && batch > 0 && t_len > 0, "vl_lstm_bwd_cluster: bad arguments");
+  VL_REQUIRE(hidden == CH, "vl_lstm_bwd_cluster: the resident-weight kernel serves hidden == %d", CH);
+  static bool attr = false;
+  if (!attr) {
+    VL_CHECK_CUDA(cudaFuncSetAttribute(lstm_bwd_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)sizeof(ClusterSmem)));
+    attr = true;
+  }
+  const int clusters = (batch + CCB - 1) / CCB;
+  lstm_bwd_cluster_kernel<<<clusters * CL, LSTM_CL_THREADS, sizeof(ClusterSmem), stream>>>(
+      dh_seq, acts, cs, w_h, reinterpret_cast<bf16*>(dg), batch, t_len);
+  vl::g_launches.fetch_add(1);
+  VL_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -282,11 +282,9 @@ class Engine(object):
         A["frames_f32"] = None  # allocated lazily: only the reference-compatible fp32 feed needs it
         A["col1"] = act(n * s1.p * s1.q, self.k1_ld)
         A["a1"] = act(n, s1.p, s1.q, 96)
-        A["n1"] = act(n, s1.p, s1.q, 96)
         A["p1"] = act(n, p1h, p1w, 96)
         A["arg1"] = act(n, p1h, p1w, 96, dtype=torch.uint8)
         A["a2"] = act(n, s2.p, s2.q, 256)
-        A["n2"] = act(n, s2.p, s2.q, 256)
         A["p2"] = act(n, p2h, p2w, 256)
         A["arg2"] = act(n, p2h, p2w, 256, dtype=torch.uint8)
         A["a3"] = act(n, s3.p, s3.q, 384)
@@ -344,10 +342,8 @@ class Engine(object):
         G["da4"] = act(n, s3.p, s3.q, 384)
         G["da3"] = act(n, s3.p, s3.q, 384)
         G["dp2"] = act(n, p2h, p2w, 256)
-        G["dn2"] = act(n, s2.p, s2.q, 256)
         G["da2"] = act(n, s2.p, s2.q, 256)
         G["dp1"] = act(n, p1h, p1w, 96)
-        G["dn1"] = act(n, s1.p, s1.q, 96)
         G["da1"] = act(n, s1.p, s1.q, 96)
         self.G = G
 
@@ -403,13 +399,12 @@ class Engine(object):
                 self.cfg.width, s1.kh, s1.kw, s1.stride, s1.pad_top, s1.pad_left, s1.p, s1.q, self.k1_ld)
         a1 = A["a1"][:n]
         K.linear_fwd(col, sh["conv1"], self.var("dcnn/conv1b"), a1.view(m1, 96), relu=True)
-        nv.call("vl_lrn_fwd", a1, A["n1"][:n], m1, 96, LRN["radius"], LRN["alpha"], LRN["beta"], LRN["bias"])
-        nv.call("vl_maxpool_fwd", A["n1"][:n], A["p1"][:n], A["arg1"][:n], n, s1.p, s1.q, 96)
+        nv.call("vl_lrn_pool_fwd", a1, A["p1"][:n], A["arg1"][:n], n, s1.p, s1.q, 96, LRN["radius"], LRN["alpha"],
+                LRN["beta"], LRN["bias"])
         s2 = sp["conv2"]
         K.conv_fwd(s2, A["p1"][:n], sh["conv2_packed"], self.var("dcnn/conv2b"), A["a2"][:n], relu=True)
-        m2 = n * s2.p * s2.q
-        nv.call("vl_lrn_fwd", A["a2"][:n], A["n2"][:n], m2, 256, LRN["radius"], LRN["alpha"], LRN["beta"], LRN["bias"])
-        nv.call("vl_maxpool_fwd", A["n2"][:n], A["p2"][:n], A["arg2"][:n], n, s2.p, s2.q, 256)
+        nv.call("vl_lrn_pool_fwd", A["a2"][:n], A["p2"][:n], A["arg2"][:n], n, s2.p, s2.q, 256, LRN["radius"],
+                LRN["alpha"], LRN["beta"], LRN["bias"])
         K.conv_fwd(sp["conv3"], A["p2"][:n], sh["conv3"], self.var("dcnn/conv3b"), A["a3"][:n], relu=True)
         K.conv_fwd(sp["conv4"], A["a3"][:n], sh["conv4"], self.var("dcnn/conv4b"), A["a4"][:n], relu=True)
         K.conv_fwd(sp["conv5"], A["a4"][:n], sh["conv5"], self.var("dcnn/conv5b"), A["a5"][:n], relu=True)
@@ -441,9 +436,9 @@ class Engine(object):
             d_in = kern.shape[0] - hd
             gx = A["gx%d" % layer][:n]
             K.linear_fwd(x, sh["lstm%d" % layer][:d_in], bias, gx, relu=False)
-            nv.call("vl_lstm_fwd", gx, kern[d_in:], A["acts%d" % layer][:n], A["cs%d" % layer][:n],
-                    A["hseq%d" % layer][:n], A["hseq_bf%d" % layer][:n], A["hprev_bf%d" % layer][:n], b, t_len, hd,
-                    1.0)
+            nv.call("vl_lstm_fwd_cluster" if hd == 256 else "vl_lstm_fwd", gx, kern[d_in:], A["acts%d" % layer][:n],
+                    A["cs%d" % layer][:n], A["hseq%d" % layer][:n], A["hseq_bf%d" % layer][:n],
+                    A["hprev_bf%d" % layer][:n], b, t_len, hd, 1.0)
             x = A["hseq_bf%d" % layer][:n]
         hseq = A["hseq%d" % (cfg.lstm_layers - 1)][:n]
         nv.call("vl_segment_pool_fwd", hseq, None, t_len, b, hd, POOL[cfg.fusion], A["fused"][:b], A["fused_bf"][:b])
@@ -494,12 +489,13 @@ class Engine(object):
         K.linear_wgrad(x, dy, dw, split_k=self._split_k(dw.shape[0], n_cols, x.shape[0]), n=n_cols)
         nv.call("vl_colsum", dy, self.var(bname, self.grads), dy.shape[0], n_cols, dy.stride(0))
 
-    def _conv_bwd(self, name, x, dy, dx, relu_mask):
+    def _conv_bwd(self, name, x, dy, dx, relu_mask, bias_done=False):
         s = self.sp[name]
         n = x.shape[0]
         dw = self.var2d("dcnn/%sW" % name, self.grads)
         K.conv_wgrad(s, x, dy, dw, split_k=self._split_k(s.taps * s.cchunks * 64, s.cout_g, n * s.p * s.q, s.groups))
-        nv.call("vl_colsum", dy, self.var("dcnn/%sb" % name, self.grads), n * s.p * s.q, s.cout, s.cout)
+        if not bias_done:
+            nv.call("vl_colsum", dy, self.var("dcnn/%sb" % name, self.grads), n * s.p * s.q, s.cout, s.cout)
         if dx is not None:
             K.conv_dgrad(s, dy, self.sh[name], dx, relu_mask=relu_mask)
 
@@ -537,8 +533,13 @@ class Engine(object):
             kern_g = self.var(kn, self.grads)
             d_in = kern_g.shape[0] - hd
             dg = A["dg"][:n]
-            nv.call("vl_lstm_bwd", A["dhseq%d" % layer][:n], A["acts%d" % layer][:n], A["cs%d" % layer][:n],
-                    sh["lstm%d_wht" % layer], dg, b, t_len, hd)
+            if hd == 256:
+                kern = self.var(kn)
+                nv.call("vl_lstm_bwd_cluster", A["dhseq%d" % layer][:n], A["acts%d" % layer][:n],
+                        A["cs%d" % layer][:n], kern[d_in:], dg, b, t_len, hd)
+            else:
+                nv.call("vl_lstm_bwd", A["dhseq%d" % layer][:n], A["acts%d" % layer][:n], A["cs%d" % layer][:n],
+                        sh["lstm%d_wht" % layer], dg, b, t_len, hd)
             x = feat if layer == 0 else A["hseq_bf%d" % (layer - 1)][:n]
             K.linear_wgrad(x, dg, kern_g[:d_in], split_k=self._split_k(d_in, 4 * hd, n))
             K.linear_wgrad(A["hprev_bf%d" % layer][:n], dg, kern_g[d_in:], split_k=self._split_k(hd, 4 * hd, n))
@@ -563,18 +564,17 @@ class Engine(object):
         self._conv_bwd("conv5", A["a4"][:n], G["da5"][:n], G["da4"][:n], A["a4"][:n])
         self._conv_bwd("conv4", A["a3"][:n], G["da4"][:n], G["da3"][:n], A["a3"][:n])
         self._conv_bwd("conv3", A["p2"][:n], G["da3"][:n], G["dp2"][:n], None)
-        nv.call("vl_maxpool_bwd", G["dp2"][:n], A["arg2"][:n], G["dn2"][:n], None, n, s2.p, s2.q, 256)
-        nv.call("vl_lrn_bwd", A["a2"][:n], G["dn2"][:n], G["da2"][:n], n * s2.p * s2.q, 256, LRN["radius"],
-                LRN["alpha"], LRN["beta"], LRN["bias"], 1)
-        self._conv_bwd("conv2", A["p1"][:n], G["da2"][:n], G["dp1"][:n], None)
-        nv.call("vl_maxpool_bwd", G["dp1"][:n], A["arg1"][:n], G["dn1"][:n], None, n, s1.p, s1.q, 96)
+        nv.call("vl_pool_lrn_bwd", A["a2"][:n], G["dp2"][:n], A["arg2"][:n], G["da2"][:n],
+                self.var("dcnn/conv2b", self.grads), n, s2.p, s2.q, 256, LRN["radius"], LRN["alpha"], LRN["beta"],
+                LRN["bias"])
+        self._conv_bwd("conv2", A["p1"][:n], G["da2"][:n], G["dp1"][:n], None, bias_done=True)
+        nv.call("vl_pool_lrn_bwd", A["a1"][:n], G["dp1"][:n], A["arg1"][:n], G["da1"][:n],
+                self.var("dcnn/conv1b", self.grads), n, s1.p, s1.q, 96, LRN["radius"], LRN["alpha"], LRN["beta"],
+                LRN["bias"])
         m1 = n * s1.p * s1.q
-        nv.call("vl_lrn_bwd", A["a1"][:n], G["dn1"][:n], G["da1"][:n], m1, 96, LRN["radius"], LRN["alpha"],
-                LRN["beta"], LRN["bias"], 1)
         da1 = G["da1"][:n].view(m1, 96)
         dw1 = self.var2d("dcnn/conv1W", self.grads)
         K.linear_wgrad(A["col1"][:m1], da1, dw1, split_k=self._split_k(self.k1, 96, m1), n=96)
-        nv.call("vl_colsum", da1, self.var("dcnn/conv1b", self.grads), m1, 96, 96)
 
     # ------------------------------------------------------------------------------------------
     # training step
