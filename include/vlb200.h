@@ -96,6 +96,19 @@ int vl_conv1_patches(const void* frames, int is_u8, const float* mean3, void* co
                      int32_t w, int32_t kh, int32_t kw, int32_t stride, int32_t pad_top, int32_t pad_left,
                      int32_t p, int32_t q, int32_t k_ld, vl_stream_t stream);
 
+/* Space-to-depth staging of the conv1 input (alexnet.py:60-77, dataset_.py:521-530): frames [n][h][w][3] (uint8,
+ * mean subtracted here, or fp32 as fed by feeder.py:97-100) -> bf16 out[n][hb][wb][s*s*3] with
+ * out[n][by][bx][(dy*s+dx)*3+c] = frame[n][s*by-pad_top+dy][s*bx-pad_left+dx][c] (0 outside the image), so that the
+ * kh x kw stride-s SAME convolution equals a ceil(kh/s) x ceil(kw/s) stride-1 VALID convolution over s*s*3 channels. */
+int vl_frames_s2d(const void* frames, int32_t is_u8, const float* mean3, void* out, int32_t n, int32_t h, int32_t w,
+                  int32_t s, int32_t pad_top, int32_t pad_left, int32_t hb, int32_t wb, vl_stream_t stream);
+/* Filter of that convolution: HWIO fp32 [kh][kw][cin][cout] -> bf16 [taps][chunk][cout] (chunk >= s*s*cin rows per
+ * tap, zero padded), and the inverse scatter of its filter gradient dws[taps*s*s*cin][cout] -> HWIO dw. */
+int vl_s2d_pack_filter(const float* src, void* dst, int32_t kh, int32_t kw, int32_t cin, int32_t cout, int32_t s,
+                       int32_t chunk, vl_stream_t stream);
+int vl_s2d_unpack_grad(const float* dws, float* dw, int32_t kh, int32_t kw, int32_t cin, int32_t cout, int32_t s,
+                       vl_stream_t stream);
+
 /* tf.nn.local_response_normalization(depth_radius=2, alpha=2e-5, beta=.75, bias=1) (alexnet.py:85,126) over
  * the channel axis of x[rows][c] (bf16). */
 int vl_lrn_fwd(const void* x, void* y, int64_t rows, int32_t c, int32_t radius, float alpha, float beta,
@@ -121,6 +134,13 @@ int vl_lrn_pool_fwd(const void* x, void* y, void* argmax, int32_t n, int32_t h, 
  * not NULL it also accumulates the bias gradient sum_pixels dx (dbias must be zeroed). */
 int vl_pool_lrn_bwd(const void* x, const void* dy, const void* argmax, void* dx, float* dbias, int32_t n, int32_t h,
                     int32_t w, int32_t c, int32_t radius, float alpha, float beta, float bias, vl_stream_t stream);
+/* Any-channel-count versions of the two fused kernels (one thread per 16-byte chunk, halo re-loaded from global
+ * memory); vl_lrn_pool_fwd / vl_pool_lrn_bwd dispatch to them when c > 256. */
+int vl_lrn_pool_fwd_generic(const void* x, void* y, void* argmax, int32_t n, int32_t h, int32_t w, int32_t c,
+                            int32_t radius, float alpha, float beta, float bias, vl_stream_t stream);
+int vl_pool_lrn_bwd_generic(const void* x, const void* dy, const void* argmax, void* dx, float* dbias, int32_t n,
+                            int32_t h, int32_t w, int32_t c, int32_t radius, float alpha, float beta, float bias,
+                            vl_stream_t stream);
 
 /* bias gradient: out[c] += sum_rows dy[row][c]  (bf16 in, fp32 accumulate; `out` must be zeroed). */
 int vl_colsum(const void* dy, float* out, int64_t rows, int32_t c, int32_t ld, vl_stream_t stream);

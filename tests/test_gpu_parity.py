@@ -97,6 +97,46 @@ def test_conv1_patches_and_gemm_vs_oracle(vl):
     assert torch.equal(col, col2)
 
 
+def test_conv1_space_to_depth_path_vs_oracle(vl):
+    """conv1 (11x11 stride 4 SAME, alexnet.py:60-77) as space-to-depth + 3x3 VALID im2col-TMA convolution."""
+    nv, K, E = vl["nv"], vl["K"], vl["E"]
+    rng = np.random.default_rng(12)
+    n = 2
+    frames_u8 = rng.integers(0, 256, size=(n, 227, 227, 3), dtype=np.uint8)
+    mean = np.array([99.197148, 105.293620, 109.503945], np.float32)
+    x = frames_u8.astype(np.float32) - mean
+    w = bf16_round(rng.standard_normal((11, 11, 3, 96)) * 0.05)
+    b = np.full(96, 0.1, np.float32)
+    sp = E.encoder_specs(227, 227)
+    s1s = sp["conv1_s2d"]
+    assert (s1s.h, s1s.w, s1s.cin, s1s.p, s1s.q, s1s.taps) == (59, 59, 48, 57, 57, 9)
+    # staging kernel: bit-exact against a numpy restatement (integer indexing + one bf16 rounding)
+    xs = torch.empty(n, 59, 59, 48, dtype=torch.bfloat16, device="cuda")
+    nv.call("vl_frames_s2d", dev(frames_u8), 1, dev(mean), xs, n, 227, 227, 4, 4, 4, 59, 59)
+    pad = np.zeros((n, 236, 236, 3), np.float32)
+    pad[:, 4:231, 4:231] = x
+    ref = pad.reshape(n, 59, 4, 59, 4, 3).transpose(0, 1, 3, 2, 4, 5).reshape(n, 59, 59, 48)
+    assert np.array_equal(xs.float().cpu().numpy(), bf16_round(ref))
+    xs2 = torch.empty_like(xs)
+    nv.call("vl_frames_s2d", dev(x), 0, None, xs2, n, 227, 227, 4, 4, 4, 59, 59)
+    assert torch.equal(xs, xs2)  # fp32 feed (feeder.py:97-100) == uint8 + mean feed
+    # filter packing + forward
+    wp = torch.empty(s1s.k_packed, 96, dtype=torch.bfloat16, device="cuda")
+    nv.call("vl_s2d_pack_filter", dev(w), wp, 11, 11, 3, 96, 4, 64)
+    out = torch.empty(n, 57, 57, 96, dtype=torch.bfloat16, device="cuda")
+    K.conv_fwd(s1s, xs, wp, dev(b), out, relu=True)
+    y_ref = O.relu(O.conv2d_same(bf16_round(x), w, b, 4, 1))
+    assert rel(out.float().cpu().numpy(), y_ref) < BF16_TOL
+    # filter gradient through the space-to-depth form, scattered back to HWIO
+    dy = bf16_round(rng.standard_normal((n, 57, 57, 96)))
+    _, dw_ref, _ = O.conv2d_same_backward(bf16_round(x), w, dy, 4, 1, need_dx=False)
+    dws = torch.zeros(9 * 48, 96, device="cuda")
+    K.conv_wgrad(s1s, xs, dev(dy, torch.bfloat16), dws, split_k=4)
+    dw = torch.empty(11, 11, 3, 96, device="cuda")
+    nv.call("vl_s2d_unpack_grad", dws, dw, 11, 11, 3, 96, 4)
+    assert rel(dw.cpu().numpy(), dw_ref) < 1e-3
+
+
 @pytest.mark.parametrize("c", [96, 256])
 def test_lrn_fwd_bwd_vs_oracle(vl, c):
     nv = vl["nv"]

@@ -1,0 +1,506 @@
+// Second-generation HBM-bound kernels of the AlexNet encoder (sm_100a).
+//
+//   vl_frames_s2d          frames (uint8 / fp32) -> mean-subtracted bf16 space-to-depth tensor: the 11x11 stride-4
+//                          SAME conv1 (alexnet.py:60-77) becomes a 3x3 stride-1 VALID convolution over 48 channels
+//                          that the im2col-TMA contraction kernel consumes directly (no 2.5 GB patch matrix).
+//   vl_s2d_pack_filter     conv1 HWIO fp32 filter -> bf16 [9 taps x 64, cout] operand of that convolution
+//   vl_s2d_unpack_grad     filter gradient of the 3x3x48 convolution -> HWIO gradient of the 11x11x3 filter
+//   vl_lrn_pool_fwd        LRN + 3x3/2 max-pool (alexnet.py:80-98,121-139): LRN evaluated once per input pixel into
+//                          shared memory (bf16, as the unfused path stores it), pooled from shared memory
+//   vl_pool_lrn_bwd        MaxPoolGrad -> LRNGrad -> ReluGrad (+ bias gradient), one 16-byte chunk per thread, channel
+//                          halos exchanged with warp shuffles (every expensive term is evaluated exactly once)
+//
+// All global accesses are 16-byte vectors over the channel axis of NHWC tensors; these kernels are judged on
+// achieved HBM GB/s (DESIGN.md lists the algorithmic bytes of each).
+#include "common.cuh"
+#include "../../include/vlb200.h"
+
+#include <atomic>
+
+namespace vl {
+extern std::atomic<long long> g_launches;
+}
+
+namespace {
+
+typedef __nv_bfloat16 bf16;
+
+struct alignas(16) Bf16x8 {
+  __nv_bfloat162 v[4];
+};
+
+__device__ __forceinline__ void unpack8(const Bf16x8& in, float (&f)[8]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __bfloat1622float2(in.v[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ Bf16x8 pack8(const float (&f)[8]) {
+  Bf16x8 o;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) o.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return o;
+}
+__device__ __forceinline__ float sqrt_approx(float x) {
+  float y;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float bf16_round_f(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+// Channel halo of an 8-channel chunk inside a group of LPP lanes that together hold one pixel: lane l owns channels
+// [8l, 8l+8); returns the two values left of the chunk (from lane l-1) and right of it (from lane l+1), zero outside.
+template <int LPP>
+__device__ __forceinline__ void halo2(const float (&v)[8], int l, int cpr, float (&left)[2], float (&right)[2]) {
+  left[0] = __shfl_up_sync(0xffffffffu, v[6], 1, LPP);
+  left[1] = __shfl_up_sync(0xffffffffu, v[7], 1, LPP);
+  right[0] = __shfl_down_sync(0xffffffffu, v[0], 1, LPP);
+  right[1] = __shfl_down_sync(0xffffffffu, v[1], 1, LPP);
+  if (l == 0) left[0] = left[1] = 0.f;
+  if (l >= cpr - 1) right[0] = right[1] = 0.f;
+}
+
+// s_j = bias + alpha * sum_{|o|<=2} x_{j+o}^2 for the 8 own channels (tf.nn.lrn, depth_radius 2)
+template <int LPP>
+__device__ __forceinline__ void lrn_scale8(const float (&x)[8], int l, int cpr, float alpha, float bias, float (&s)[8]) {
+  float sq[12];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sq[2 + j] = x[j] * x[j];
+  float own[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) own[j] = sq[2 + j];
+  float lf[2], rt[2];
+  halo2<LPP>(own, l, cpr, lf, rt);
+  sq[0] = lf[0];
+  sq[1] = lf[1];
+  sq[10] = rt[0];
+  sq[11] = rt[1];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = fmaf(alpha, ((sq[j] + sq[j + 1]) + sq[j + 2]) + (sq[j + 3] + sq[j + 4]), bias);
+}
+
+// ------------------------------------------------------------------------------------------------
+// frames -> space-to-depth bf16.  One CTA per (frame, block row): `s` image rows are staged in shared memory
+// (mean-subtracted bf16, SAME zero padding materialised), then out[bx][(dy*s+dx)*3+c] = rows[dy][(s*bx+dx)*3+c].
+// ------------------------------------------------------------------------------------------------
+template <bool U8>
+__global__ void __launch_bounds__(128)
+    frames_s2d_kernel(const void* __restrict__ frames_, const float* __restrict__ mean3, bf16* __restrict__ out, int h,
+                      int w, int s, int pad_top, int pad_left, int hb, int wb) {
+  extern __shared__ uint8_t smem_raw[];
+  bf16* rows = reinterpret_cast<bf16*>(smem_raw);  // [s][wb*s*3]
+  const int by = blockIdx.x % hb;
+  const int nn = blockIdx.x / hb;
+  const int rw = wb * s * 3;  // staged row width in elements
+  float m[3] = {0.f, 0.f, 0.f};
+  if (U8 && mean3 != nullptr) {
+    m[0] = mean3[0];
+    m[1] = mean3[1];
+    m[2] = mean3[2];
+  }
+  const int lead = pad_left * 3;
+  for (int idx = threadIdx.x; idx < s * rw; idx += blockDim.x) {
+    const int dy = idx / rw;
+    const int e = idx - dy * rw;
+    const int y = by * s - pad_top + dy;
+    const int xe = e - lead;  // x*3 + c inside the image row
+    float v = 0.f;
+    if (y >= 0 && y < h && xe >= 0 && xe < w * 3) {
+      const long long off = ((long long)nn * h + y) * (w * 3) + xe;
+      if (U8) {
+        v = (float)reinterpret_cast<const uint8_t*>(frames_)[off] - m[xe % 3];
+      } else {
+        v = reinterpret_cast<const float*>(frames_)[off];
+      }
+    }
+    rows[idx] = __float2bfloat16_rn(v);
+  }
+  __syncthreads();
+  const int cblk = s * s * 3;  // channels of the space-to-depth tensor (48)
+  const int seg = s * 3;       // contiguous source elements per (bx, dy)
+  const int chunks = wb * cblk / 8;
+  bf16* orow = out + ((long long)nn * hb + by) * wb * cblk;
+  for (int ch = threadIdx.x; ch < chunks; ch += blockDim.x) {
+    alignas(16) bf16 v[8];
+    int e = ch * 8;
+    int bx = e / cblk;
+    int j = e - bx * cblk;
+    int dy = j / seg;
+    int r = j - dy * seg;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      v[k] = rows[dy * rw + bx * seg + r];
+      if (++r == seg) {
+        r = 0;
+        if (++dy == s) {
+          dy = 0;
+          ++bx;
+        }
+      }
+    }
+    *reinterpret_cast<uint4*>(orow + ch * 8) = *reinterpret_cast<const uint4*>(v);
+  }
+}
+
+// dst[(tr*kb+ts)*chunk + (dy*s+dx)*cin + c][o] = src[s*tr+dy][s*ts+dx][c][o] (0 when outside the kh x kw filter or
+// in the chunk padding).  kb = ceil(kh/s) taps per axis of the space-to-depth convolution.
+__global__ void s2d_pack_filter_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int kh, int kw, int cin,
+                                       int cout, int s, int kb_h, int kb_w, int chunk, long long total) {
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int o = (int)(idx % cout);
+    const int row = (int)(idx / cout);
+    const int tap = row / chunk;
+    const int j = row - tap * chunk;
+    const int tr = tap / kb_w, ts = tap - tr * kb_w;
+    float v = 0.f;
+    if (j < s * s * cin) {
+      const int c = j % cin;
+      const int dd = j / cin;
+      const int dy = dd / s, dx = dd - dy * s;
+      const int r = s * tr + dy, q = s * ts + dx;
+      if (r < kh && q < kw) v = src[(((long long)r * kw + q) * cin + c) * cout + o];
+    }
+    dst[idx] = __float2bfloat16_rn(v);
+  }
+}
+
+// dw[r][q][c][o] = dws[(tr*kb_w+ts)*(s*s*cin) + (dy*s+dx)*cin + c][o]  with r = s*tr+dy, q = s*ts+dx
+__global__ void s2d_unpack_grad_kernel(const float* __restrict__ dws, float* __restrict__ dw, int kh, int kw, int cin,
+                                       int cout, int s, int kb_w, long long total) {
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int o = (int)(idx % cout);
+    long long t = idx / cout;
+    const int c = (int)(t % cin);
+    t /= cin;
+    const int q = (int)(t % kw);
+    const int r = (int)(t / kw);
+    const int tr = r / s, dy = r - tr * s, ts = q / s, dx = q - ts * s;
+    const long long row = (long long)(tr * kb_w + ts) * (s * s * cin) + (dy * s + dx) * cin + c;
+    dw[idx] = dws[row * cout + o];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LRN + max-pool forward.  CTA = (frame, strip of `rows_out` pooled rows).  Phase 1 evaluates lrn(x) once for every
+// input pixel of the strip (LPP lanes per pixel, 16 B per lane) into shared memory as bf16; phase 2 pools 3x3/2
+// windows out of shared memory.  beta = 0.75 fast path: s^-0.75 = rsqrt(s) * sqrt(rsqrt(s)).
+// ------------------------------------------------------------------------------------------------
+template <int LPP>
+__global__ void __launch_bounds__(256)
+    lrn_pool_fwd_kernel2(const bf16* __restrict__ x, bf16* __restrict__ y, uint8_t* __restrict__ arg, int h, int w, int c,
+                         int p, int q, int rows_out, int strips, float alpha, float bias) {
+  extern __shared__ uint8_t smem_raw[];
+  bf16* tile = reinterpret_cast<bf16*>(smem_raw);  // [(2*rows_out+1)][w][c]
+  const int strip = blockIdx.x % strips;
+  const int nn = blockIdx.x / strips;
+  const int p0 = strip * rows_out;
+  const int np = min(rows_out, p - p0);  // pooled rows of this strip
+  const int in_rows = 2 * np + 1;
+  const int cpr = c >> 3;
+  const int l = threadIdx.x % LPP;
+  const int grp = threadIdx.x / LPP;
+  const int ngrp = blockDim.x / LPP;
+  const bf16* xin = x + ((long long)nn * h + 2 * p0) * w * c;
+  const int npix = in_rows * w;
+  // phase 1 (all lanes of a group take part in the shuffles, also for the padded chunk slots l >= cpr)
+  for (int pix0 = 0; pix0 < npix; pix0 += ngrp) {
+    const int pix = pix0 + grp;
+    const bool live = pix < npix && l < cpr;
+    float v[8];
+    if (live) {
+      unpack8(*reinterpret_cast<const Bf16x8*>(xin + (long long)pix * c + l * 8), v);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = 0.f;
+    }
+    float s[8];
+    lrn_scale8<LPP>(v, l, cpr, alpha, bias, s);
+    if (live) {
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float rs = rsqrtf(s[j]);
+        o[j] = v[j] * (rs * sqrt_approx(rs));
+      }
+      *reinterpret_cast<Bf16x8*>(tile + (long long)pix * c + l * 8) = pack8(o);
+    }
+  }
+  __syncthreads();
+  // phase 2
+  const int nout = np * q * cpr;
+  for (int idx = threadIdx.x; idx < nout; idx += blockDim.x) {
+    const int ch = idx % cpr;
+    const int t = idx / cpr;
+    const int qq = t % q;
+    const int pl = t / q;
+    float best[8];
+    int bi[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      best[j] = -INFINITY;
+      bi[j] = 0;
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+#pragma unroll
+      for (int s2 = 0; s2 < 3; ++s2) {
+        float v[8];
+        unpack8(*reinterpret_cast<const Bf16x8*>(tile + ((2 * pl + r) * w + (2 * qq + s2)) * c + ch * 8), v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (v[j] > best[j]) {  // strict: the first maximum in (h, w) scan order wins, like TF
+            best[j] = v[j];
+            bi[j] = r * 3 + s2;
+          }
+        }
+      }
+    }
+    const long long opix = ((long long)nn * p + (p0 + pl)) * q + qq;
+    *reinterpret_cast<Bf16x8*>(y + opix * c + ch * 8) = pack8(best);
+    uint32_t lo = bi[0] | (bi[1] << 8) | (bi[2] << 16) | (bi[3] << 24);
+    uint32_t hi = bi[4] | (bi[5] << 8) | (bi[6] << 16) | (bi[7] << 24);
+    *reinterpret_cast<uint2*>(arg + opix * c + ch * 8) = make_uint2(lo, hi);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// MaxPoolGrad -> LRNGrad -> ReluGrad (+ bias gradient).
+//   dn_i = sum over pooling windows whose argmax is pixel i of dy          (bf16 rounded, as the unfused path stores it)
+//   dx_i = relu'(x_i) * ( dn_i * s_i^-b  -  2ab x_i * sum_{|d-i|<=2} dn_d x_d s_d^(-b-1) )
+// ------------------------------------------------------------------------------------------------
+template <int LPP>
+__global__ void __launch_bounds__(256)
+    pool_lrn_bwd_kernel2(const bf16* __restrict__ x, const bf16* __restrict__ dy, const uint8_t* __restrict__ arg,
+                         bf16* __restrict__ dx, float* __restrict__ dbias, int h, int w, int c, int p, int q, float alpha,
+                         float beta, float bias, long long total_pix) {
+  __shared__ float bsum[256];
+  const int cpr = c >> 3;
+  const int l = threadIdx.x % LPP;
+  const int grp = threadIdx.x / LPP;
+  const int ngrp = blockDim.x / LPP;
+  if (dbias != nullptr) {
+    for (int i = threadIdx.x; i < c; i += blockDim.x) bsum[i] = 0.f;
+    __syncthreads();
+  }
+  float bacc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) bacc[j] = 0.f;
+  const float k2ab = 2.0f * alpha * beta;
+  const long long stride = (long long)gridDim.x * ngrp;
+  const long long iters = (total_pix + stride - 1) / stride;
+  long long pix = (long long)blockIdx.x * ngrp + grp;
+  for (long long it = 0; it < iters; ++it, pix += stride) {
+    const bool live = pix < total_pix && l < cpr;
+    float xv[8], gv[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) xv[j] = gv[j] = 0.f;
+    if (live) {
+      const int c0 = l * 8;
+      const int ww = (int)(pix % w);
+      const long long t = pix / w;
+      const int hh = (int)(t % h);
+      const int nn = (int)(t / h);
+      unpack8(*reinterpret_cast<const Bf16x8*>(x + pix * c + c0), xv);
+      const int p_lo = max(0, (hh - 1) >> 1), p_hi = min(p - 1, hh >> 1);
+      const int q_lo = max(0, (ww - 1) >> 1), q_hi = min(q - 1, ww >> 1);
+      for (int pp = p_lo; pp <= p_hi; ++pp) {
+        const int r = hh - 2 * pp;
+        if (r > 2) continue;
+        for (int qq = q_lo; qq <= q_hi; ++qq) {
+          const int s2 = ww - 2 * qq;
+          if (s2 > 2) continue;
+          const long long opix = ((long long)nn * p + pp) * q + qq;
+          const uint32_t code = r * 3 + s2;
+          float g[8];
+          unpack8(*reinterpret_cast<const Bf16x8*>(dy + opix * c + c0), g);
+          const uint2 a = *reinterpret_cast<const uint2*>(arg + opix * c + c0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t aj = ((j < 4 ? a.x : a.y) >> (8 * (j & 3))) & 0xffu;
+            if (aj == code) gv[j] += g[j];
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) gv[j] = bf16_round_f(gv[j]);
+    }
+    float s[8];
+    lrn_scale8<LPP>(xv, l, cpr, alpha, bias, s);
+    float pw[8], tt[12];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float inv;
+      if (beta == 0.75f) {
+        const float rs = rsqrtf(s[j]);
+        pw[j] = rs * sqrt_approx(rs);
+        inv = rs * rs;
+      } else {
+        pw[j] = __powf(s[j], -beta);
+        inv = __fdividef(1.0f, s[j]);
+      }
+      tt[2 + j] = gv[j] * xv[j] * pw[j] * inv;
+    }
+    {
+      float own[8], lf[2], rt[2];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) own[j] = tt[2 + j];
+      halo2<LPP>(own, l, cpr, lf, rt);
+      tt[0] = lf[0];
+      tt[1] = lf[1];
+      tt[10] = rt[0];
+      tt[11] = rt[1];
+    }
+    if (live) {
+      float out[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float sum = ((tt[j] + tt[j + 1]) + tt[j + 2]) + (tt[j + 3] + tt[j + 4]);
+        float g = gv[j] * pw[j] - k2ab * xv[j] * sum;
+        if (!(xv[j] > 0.f)) g = 0.f;  // ReLU gradient of the producing conv
+        out[j] = g;
+      }
+      const Bf16x8 packed = pack8(out);
+      *reinterpret_cast<Bf16x8*>(dx + pix * c + l * 8) = packed;
+      if (dbias != nullptr) {
+        float rb[8];
+        unpack8(packed, rb);  // the bias gradient sums the bf16 values that are stored (as vl_colsum would)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) bacc[j] += rb[j];
+      }
+    }
+  }
+  if (dbias != nullptr) {
+    if (l < cpr) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(&bsum[l * 8 + j], bacc[j]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < c; i += blockDim.x) atomicAdd(dbias + i, bsum[i]);
+  }
+}
+
+}  // namespace
+
+#define VL_LAUNCHED()                  \
+  do {                                 \
+    vl::g_launches.fetch_add(1);       \
+    VL_CHECK_CUDA(cudaGetLastError()); \
+  } while (0)
+
+extern "C" int vl_frames_s2d(const void* frames, int32_t is_u8, const float* mean3, void* out, int32_t n, int32_t h,
+                             int32_t w, int32_t s, int32_t pad_top, int32_t pad_left, int32_t hb, int32_t wb,
+                             vl_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  VL_REQUIRE(frames && out && s >= 1 && hb > 0 && wb > 0, "vl_frames_s2d: bad arguments");
+  VL_REQUIRE((wb * s * s * 3) % 8 == 0, "vl_frames_s2d: wb*s*s*3 must be a multiple of 8");
+  const size_t smem = (size_t)s * wb * s * 3 * sizeof(bf16);
+  VL_REQUIRE(smem <= 48 * 1024, "vl_frames_s2d: image row too wide (%zu bytes of shared memory)", smem);
+  const int grid = n * hb;
+  if (is_u8)
+    frames_s2d_kernel<true><<<grid, 128, smem, stream>>>(frames, mean3, reinterpret_cast<bf16*>(out), h, w, s, pad_top,
+                                                         pad_left, hb, wb);
+  else
+    frames_s2d_kernel<false><<<grid, 128, smem, stream>>>(frames, mean3, reinterpret_cast<bf16*>(out), h, w, s, pad_top,
+                                                          pad_left, hb, wb);
+  VL_LAUNCHED();
+  return 0;
+}
+
+extern "C" int vl_s2d_pack_filter(const float* src, void* dst, int32_t kh, int32_t kw, int32_t cin, int32_t cout,
+                                  int32_t s, int32_t chunk, vl_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  VL_REQUIRE(src && dst && s >= 1 && chunk >= s * s * cin, "vl_s2d_pack_filter: bad arguments");
+  const int kb_h = (kh + s - 1) / s, kb_w = (kw + s - 1) / s;
+  const long long total = (long long)kb_h * kb_w * chunk * cout;
+  s2d_pack_filter_kernel<<<(int)((total + 255) / 256), 256, 0, stream>>>(src, reinterpret_cast<bf16*>(dst), kh, kw, cin,
+                                                                         cout, s, kb_h, kb_w, chunk, total);
+  VL_LAUNCHED();
+  return 0;
+}
+
+extern "C" int vl_s2d_unpack_grad(const float* dws, float* dw, int32_t kh, int32_t kw, int32_t cin, int32_t cout,
+                                  int32_t s, vl_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  VL_REQUIRE(dws && dw && s >= 1, "vl_s2d_unpack_grad: bad arguments");
+  const int kb_w = (kw + s - 1) / s;
+  const long long total = (long long)kh * kw * cin * cout;
+  s2d_unpack_grad_kernel<<<(int)((total + 255) / 256), 256, 0, stream>>>(dws, dw, kh, kw, cin, cout, s, kb_w, total);
+  VL_LAUNCHED();
+  return 0;
+}
+
+// Generic (any c % 8 == 0, radius <= 4) versions live in encoder_mem.cu.
+extern "C" int vl_lrn_pool_fwd_generic(const void* x, void* y, void* argmax, int32_t n, int32_t h, int32_t w, int32_t c,
+                                       int32_t radius, float alpha, float beta, float bias, vl_stream_t stream_);
+extern "C" int vl_pool_lrn_bwd_generic(const void* x, const void* dy, const void* argmax, void* dx, float* dbias,
+                                       int32_t n, int32_t h, int32_t w, int32_t c, int32_t radius, float alpha,
+                                       float beta, float bias, vl_stream_t stream_);
+
+extern "C" int vl_lrn_pool_fwd(const void* x, void* y, void* argmax, int32_t n, int32_t h, int32_t w, int32_t c,
+                               int32_t radius, float alpha, float beta, float bias, vl_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  VL_REQUIRE(x && y && argmax && c % 8 == 0 && h >= 3 && w >= 3, "vl_lrn_pool_fwd: bad arguments");
+  VL_REQUIRE(radius == 2 && beta == 0.75f, "vl_lrn_pool_fwd: fused path serves depth_radius 2, beta 0.75 (alexnet.py:80-89)");
+  const int p = (h - 3) / 2 + 1, q = (w - 3) / 2 + 1;
+  const size_t row_bytes = (size_t)w * c * sizeof(bf16);
+  int rows_out = 0;
+  for (int r = 1; r <= p; ++r)
+    if ((size_t)(2 * r + 1) * row_bytes <= 100 * 1024) rows_out = r;
+  if (c > 256 || rows_out == 0)
+    return vl_lrn_pool_fwd_generic(x, y, argmax, n, h, w, c, radius, alpha, beta, bias, stream_);
+  const int strips = (p + rows_out - 1) / rows_out;
+  rows_out = (p + strips - 1) / strips;  // balance the strips
+  const size_t smem = (size_t)(2 * rows_out + 1) * row_bytes;
+  const int grid = n * strips;
+  if (c <= 128) {
+    static bool attr = false;
+    if (!attr) {
+      VL_CHECK_CUDA(cudaFuncSetAttribute(lrn_pool_fwd_kernel2<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+      attr = true;
+    }
+    lrn_pool_fwd_kernel2<16><<<grid, 256, smem, stream>>>(reinterpret_cast<const bf16*>(x), reinterpret_cast<bf16*>(y),
+                                                          reinterpret_cast<uint8_t*>(argmax), h, w, c, p, q, rows_out,
+                                                          strips, alpha, bias);
+  } else {
+    static bool attr = false;
+    if (!attr) {
+      VL_CHECK_CUDA(cudaFuncSetAttribute(lrn_pool_fwd_kernel2<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+      attr = true;
+    }
+    lrn_pool_fwd_kernel2<32><<<grid, 256, smem, stream>>>(reinterpret_cast<const bf16*>(x), reinterpret_cast<bf16*>(y),
+                                                          reinterpret_cast<uint8_t*>(argmax), h, w, c, p, q, rows_out,
+                                                          strips, alpha, bias);
+  }
+  VL_LAUNCHED();
+  return 0;
+}
+
+extern "C" int vl_pool_lrn_bwd(const void* x, const void* dy, const void* argmax, void* dx, float* dbias, int32_t n,
+                               int32_t h, int32_t w, int32_t c, int32_t radius, float alpha, float beta, float bias,
+                               vl_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  VL_REQUIRE(x && dy && argmax && dx && c % 8 == 0, "vl_pool_lrn_bwd: bad arguments");
+  VL_REQUIRE(radius == 2, "vl_pool_lrn_bwd: only depth_radius 2 (alexnet.py:80,121) is implemented");
+  if (c > 256) return vl_pool_lrn_bwd_generic(x, dy, argmax, dx, dbias, n, h, w, c, radius, alpha, beta, bias, stream_);
+  const int p = (h - 3) / 2 + 1, q = (w - 3) / 2 + 1;
+  const long long total_pix = (long long)n * h * w;
+  const int lpp = c <= 128 ? 16 : 32;
+  const int ngrp = 256 / lpp;
+  long long blocks = (total_pix + ngrp - 1) / ngrp;
+  const long long cap = (long long)vl::num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  if (lpp == 16)
+    pool_lrn_bwd_kernel2<16><<<(int)blocks, 256, 0, stream>>>(
+        reinterpret_cast<const bf16*>(x), reinterpret_cast<const bf16*>(dy), reinterpret_cast<const uint8_t*>(argmax),
+        reinterpret_cast<bf16*>(dx), dbias, h, w, c, p, q, alpha, beta, bias, total_pix);
+  else
+    pool_lrn_bwd_kernel2<32><<<(int)blocks, 256, 0, stream>>>(
+        reinterpret_cast<const bf16*>(x), reinterpret_cast<const bf16*>(dy), reinterpret_cast<const uint8_t*>(argmax),
+        reinterpret_cast<bf16*>(dx), dbias, h, w, c, p, q, alpha, beta, bias, total_pix);
+  VL_LAUNCHED();
+  return 0;
+}

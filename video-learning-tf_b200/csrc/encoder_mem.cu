@@ -721,11 +721,11 @@ extern "C" int vl_transpose_f32(const float* src, float* dst, int32_t rows, int3
   return 0;
 }
 
-extern "C" int vl_lrn_pool_fwd(const void* x, void* y, void* argmax, int32_t n, int32_t h, int32_t w, int32_t c,
+extern "C" int vl_lrn_pool_fwd_generic(const void* x, void* y, void* argmax, int32_t n, int32_t h, int32_t w, int32_t c,
                                int32_t radius, float alpha, float beta, float bias, vl_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   VL_REQUIRE(x && y && argmax && c % 8 == 0 && h >= 3 && w >= 3, "vl_lrn_pool_fwd: bad arguments");
-  VL_REQUIRE(radius == 2 && beta == 0.75f, "vl_lrn_pool_fwd: fused path serves depth_radius 2, beta 0.75 (alexnet.py:80-89)");
+  VL_REQUIRE(radius == 2 && beta == 0.75f, "vl_lrn_pool_fwd_generic: fused path serves depth_radius 2, beta 0.75 (alexnet.py:80-89)");
   const int p = (h - 3) / 2 + 1, q = (w - 3) / 2 + 1;
   const long long total = (long long)n * p * q * (c / 8);
   lrn_pool_fwd_kernel<<<sweep_grid(total, 256), 256, 0, stream>>>(reinterpret_cast<const bf16*>(x),
@@ -736,7 +736,7 @@ extern "C" int vl_lrn_pool_fwd(const void* x, void* y, void* argmax, int32_t n, 
   return 0;
 }
 
-extern "C" int vl_pool_lrn_bwd(const void* x, const void* dy, const void* argmax, void* dx, float* dbias, int32_t n,
+extern "C" int vl_pool_lrn_bwd_generic(const void* x, const void* dy, const void* argmax, void* dx, float* dbias, int32_t n,
                                int32_t h, int32_t w, int32_t c, int32_t radius, float alpha, float beta, float bias,
                                vl_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);

@@ -14,6 +14,7 @@
 #include "../../include/vlb200.h"
 
 #include <atomic>
+#include <cstdlib>
 
 namespace vl {
 extern std::atomic<long long> g_launches;
@@ -53,6 +54,10 @@ struct KParams {
   uint32_t a_desc_hi, b_desc_hi;      // upper 32 bits of the smem descriptors (SBO, version, swizzle)
   uint32_t a_lbo_enc, b_lbo_enc;      // encoded leading byte offset (bits 16..29 of the low word)
   uint32_t a_kstep_enc, b_kstep_enc;  // encoded start-address advance per UMMA_K (=16 elements)
+  int mma_cchunks;  // k-blocks per tap as seen by the MMA issuer (tail detection)
+  int ksteps_tail;  // UMMA K-steps (of 16) that carry data in the last channel chunk of a tap / last dense k-block
+  int mn_step_rows, mn_step_rem;  // transposed im2col: 64 pixels = mn_step_rows image rows + mn_step_rem pixels
+  int dbg;  // development probes (VL_GEMM_DBG): 1 = no MMA, 2 = no A loads, 4 = no B loads, 8 = no stores
 };
 
 struct TileCoord {
@@ -77,6 +82,12 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_e
   return (static_cast<uint64_t>(hi) << 32) | lo;
 }
 
+// The producer and the MMA issuer are WARP-UNIFORM loops: all 32 lanes run the loop control on values derived
+// from blockIdx / kernel parameters (so the compiler keeps them in uniform registers) and one elected lane issues
+// the TMA / tcgen05 instructions.  A single-lane (`lane == 0`) formulation was measured at ~450 cycles of issue
+// overhead per k-block (R2UR round trips and per-instruction ELECT loops), which capped every shape at <45 % of
+// the tensor pipe; see profiles/r01_gemm_probe_v1.txt.
+template <int AM, int BMODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
     umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ KParams p) {
@@ -91,7 +102,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   float* sbias = reinterpret_cast<float*>(smem + 256);  // [256] bias slice of the current tile
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform role index
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
@@ -115,145 +126,189 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
+  const uint32_t tiles_u32 = smem_u32(tiles);
+  const uint32_t full_u32 = smem_u32(full_bar);
+  const uint32_t empty_u32 = smem_u32(empty_bar);
+  const int num_stages = p.num_stages;
+  const int stage_bytes = p.stage_bytes;
+  const int total_tiles = p.total_tiles;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    // One thread issues every load; its loop must stay free of integer divisions (a dependent chain of
-    // software divides per k-block was measured to cap the whole pipeline at ~900 cycles per k-block), so
-    // the (tap, channel-chunk) and pixel coordinates advance with adds and compares only.
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const TileCoord t = decode_tile(p, tile);
-        const int m0 = t.m_blk * BM;
-        const int n0 = t.n_blk * p.BN;
-        const int a_c0 = t.g * p.a_goff;
-        const int b_c0 = t.g * p.b_goff;
-        // contraction walk state (per tile: one division pair, then incremental)
-        int tap = 0, cc = 0, tr = 0, ts = 0;
-        if (p.taps > 1 || p.a_mode == VL_A_IM2COL_K) {
-          tap = t.kb_begin / p.cchunks;
-          cc = t.kb_begin - tap * p.cchunks;
-          tr = tap / p.kw;
-          ts = tap - tr * p.kw;
-        } else {
-          cc = t.kb_begin;
+    // The loop stays free of integer divisions: the (tap, channel-chunk) and pixel coordinates advance with adds
+    // and compares only.
+    const int BN = p.BN, cchunks = p.cchunks, kw = p.kw, taps = p.taps;
+    const bool walk_taps = (AM == VL_A_IM2COL_K) || taps > 1;
+    const bool ld_a = !(p.dbg & 2), ld_b = !(p.dbg & 4);
+    const int mn_step_rows = p.mn_step_rows, mn_step_rem = p.mn_step_rem;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(p, tile);
+      const int m0 = t.m_blk * BM;
+      const int n0 = t.n_blk * BN;
+      const int a_c0 = t.g * p.a_goff;
+      const int b_c0 = t.g * p.b_goff;
+      // contraction walk state (per tile: one division pair, then incremental)
+      int tap = 0, cc = 0, tr = 0, ts = 0;
+      if (walk_taps) {
+        tap = t.kb_begin / cchunks;
+        cc = t.kb_begin - tap * cchunks;
+        tr = tap / kw;
+        ts = tap - tr * kw;
+      } else {
+        cc = t.kb_begin;
+      }
+      // pixel of the first row of the tile (im2col K-major) / of the first k-block (transposed im2col)
+      int pn = 0, pp = 0, pq = 0;
+      int wx = 0, wy = 0;  // TMA base-pixel coordinates
+      int mn_tap_r0 = 0, mn_tap_s0 = 0, mn_c0 = 0, mn_tap_r1 = 0, mn_tap_s1 = 0, mn_c1 = 0;
+      int a_valid = 2;
+      if (AM == VL_A_IM2COL_K) {
+        pn = m0 / p.PQ;
+        int rem = m0 - pn * p.PQ;
+        pp = rem / p.Q;
+        pq = rem - pp * p.Q;
+        wx = pq * p.stride_w + p.lower_w;
+        wy = pp * p.stride_h + p.lower_h;
+      } else if (AM == VL_A_IM2COL_MN) {
+        const int pix = t.kb_begin * BK;
+        pn = pix / p.PQ;
+        int rem = pix - pn * p.PQ;
+        pp = rem / p.Q;
+        pq = rem - pp * p.Q;
+        const int chunks = taps * cchunks;
+        a_valid = min(2, chunks - t.m_blk * 2);
+        {
+          const int mc = t.m_blk * 2;
+          const int tp = mc / cchunks;
+          mn_c0 = a_c0 + (mc - tp * cchunks) * BK;
+          mn_tap_r0 = tp / kw;
+          mn_tap_s0 = tp - mn_tap_r0 * kw;
         }
-        // pixel of the first row of the tile (im2col K-major) / of the first k-block (transposed im2col)
-        int pn = 0, pp = 0, pq = 0;
-        int wx = 0, wy = 0;  // TMA base-pixel coordinates
-        int mn_tap_r[2] = {0, 0}, mn_tap_s[2] = {0, 0}, mn_c[2] = {0, 0};
-        int a_valid = 2;
-        if (p.a_mode == VL_A_IM2COL_K) {
-          pn = m0 / p.PQ;
-          int rem = m0 - pn * p.PQ;
-          pp = rem / p.Q;
-          pq = rem - pp * p.Q;
-          wx = pq * p.stride_w + p.lower_w;
-          wy = pp * p.stride_h + p.lower_h;
-        } else if (p.a_mode == VL_A_IM2COL_MN) {
-          const int pix = t.kb_begin * BK;
-          pn = pix / p.PQ;
-          int rem = pix - pn * p.PQ;
-          pp = rem / p.Q;
-          pq = rem - pp * p.Q;
-          const int chunks = p.taps * p.cchunks;
-          a_valid = min(2, chunks - t.m_blk * 2);
-          for (int j = 0; j < a_valid; ++j) {
-            const int mc = t.m_blk * 2 + j;
-            const int tp = mc / p.cchunks;
-            mn_c[j] = a_c0 + (mc - tp * p.cchunks) * BK;
-            mn_tap_r[j] = tp / p.kw;
-            mn_tap_s[j] = tp - mn_tap_r[j] * p.kw;
-          }
+        if (a_valid > 1) {
+          const int mc = t.m_blk * 2 + 1;
+          const int tp = mc / cchunks;
+          mn_c1 = a_c0 + (mc - tp * cchunks) * BK;
+          mn_tap_r1 = tp / kw;
+          mn_tap_s1 = tp - mn_tap_r1 * kw;
         }
-        const uint32_t bytes = p.b_stage_bytes + (p.a_mode == VL_A_IM2COL_MN ? 8192u * a_valid : (uint32_t)A_STAGE_BYTES);
-        for (int kb = t.kb_begin; kb < t.kb_end; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1u);
-          uint8_t* sA = tiles + stage * p.stage_bytes;
-          uint8_t* sB = sA + A_STAGE_BYTES;
-          mbar_expect_tx(&full_bar[stage], bytes);
+      }
+      const uint32_t a_bytes = !ld_a ? 0u : (AM == VL_A_IM2COL_MN ? 8192u * a_valid : (uint32_t)A_STAGE_BYTES);
+      const uint32_t bytes = (ld_b ? (uint32_t)p.b_stage_bytes : 0u) + a_bytes;
+      for (int kb = t.kb_begin; kb < t.kb_end; ++kb) {
+        mbar_wait_u32(empty_u32 + stage * 8, phase ^ 1u);
+        const uint32_t sA = tiles_u32 + stage * stage_bytes;
+        const uint32_t sB = sA + A_STAGE_BYTES;
+        const uint32_t fb = full_u32 + stage * 8;
+        if (elect_one()) {
+          mbar_expect_tx_u32(fb, bytes);
           // ---- A ----
-          if (p.a_mode == VL_A_TILED_K) {
-            tma_load_2d(sA, &tmA, &full_bar[stage], a_c0 + kb * BK, m0);
-          } else if (p.a_mode == VL_A_TILED_MN) {
-            tma_load_2d(sA, &tmA, &full_bar[stage], a_c0 + m0, kb * BK);
-            tma_load_2d(sA + 8192, &tmA, &full_bar[stage], a_c0 + m0 + 64, kb * BK);
-          } else if (p.a_mode == VL_A_IM2COL_K) {
-            tma_load_im2col_4d(sA, &tmA, &full_bar[stage], a_c0 + cc * BK, wx, wy, pn, (uint16_t)ts, (uint16_t)tr);
-          } else {  // VL_A_IM2COL_MN: this k-block's 64 pixels start at (pn, pp, pq)
-            const int bx = pq * p.stride_w + p.lower_w, by = pp * p.stride_h + p.lower_h;
-            for (int j = 0; j < a_valid; ++j)
-              tma_load_im2col_4d(sA + j * 8192, &tmA, &full_bar[stage], mn_c[j], bx, by, pn, (uint16_t)mn_tap_s[j],
-                                 (uint16_t)mn_tap_r[j]);
-            pq += BK;  // advance 64 pixels
-            while (pq >= p.Q) {
-              pq -= p.Q;
-              if (++pp == p.P) {
-                pp = 0;
-                ++pn;
-              }
+          if (ld_a) {
+            if (AM == VL_A_TILED_K) {
+              tma_load_2d_u32(sA, &tmA, fb, a_c0 + kb * BK, m0);
+            } else if (AM == VL_A_TILED_MN) {
+              tma_load_2d_u32(sA, &tmA, fb, a_c0 + m0, kb * BK);
+              tma_load_2d_u32(sA + 8192, &tmA, fb, a_c0 + m0 + 64, kb * BK);
+            } else if (AM == VL_A_IM2COL_K) {
+              tma_load_im2col_4d_u32(sA, &tmA, fb, a_c0 + cc * BK, wx, wy, pn, (uint16_t)ts, (uint16_t)tr);
+            } else {  // VL_A_IM2COL_MN: this k-block's 64 pixels start at (pn, pp, pq)
+              const int bx = pq * p.stride_w + p.lower_w, by = pp * p.stride_h + p.lower_h;
+              tma_load_im2col_4d_u32(sA, &tmA, fb, mn_c0, bx, by, pn, (uint16_t)mn_tap_s0, (uint16_t)mn_tap_r0);
+              if (a_valid > 1)
+                tma_load_im2col_4d_u32(sA + 8192, &tmA, fb, mn_c1, bx, by, pn, (uint16_t)mn_tap_s1,
+                                       (uint16_t)mn_tap_r1);
             }
           }
           // ---- B ----
-          if (p.b_mode == VL_B_TILED_K) {
-            const int tapb = p.flip ? (p.taps - 1 - tap) : tap;
-            tma_load_2d(sB, &tmB, &full_bar[stage], b_c0 + cc * BK, n0 + tapb * p.b_tap_stride);
-          } else {
-            for (int j = 0; j < p.BN / 64; ++j)
-              tma_load_2d(sB + j * 8192, &tmB, &full_bar[stage], b_c0 + n0 + j * 64, kb * BK);
-          }
-          // ---- advance the contraction walk ----
-          if (++cc == p.cchunks && (p.taps > 1 || p.a_mode == VL_A_IM2COL_K)) {
-            cc = 0;
-            ++tap;
-            if (++ts == p.kw) {
-              ts = 0;
-              ++tr;
+          if (ld_b) {
+            if (BMODE == VL_B_TILED_K) {
+              const int tapb = p.flip ? (taps - 1 - tap) : tap;
+              tma_load_2d_u32(sB, &tmB, fb, b_c0 + cc * BK, n0 + tapb * p.b_tap_stride);
+            } else {
+              for (int j = 0; j < BN; j += 64) tma_load_2d_u32(sB + j * 128, &tmB, fb, b_c0 + n0 + j, kb * BK);
             }
           }
-          if (++stage == p.num_stages) {
-            stage = 0;
-            phase ^= 1u;
+        }
+        __syncwarp();
+        // ---- advance the contraction walk ----
+        if (AM == VL_A_IM2COL_MN) {
+          pq += mn_step_rem;  // advance 64 pixels = mn_step_rows rows + mn_step_rem pixels
+          pp += mn_step_rows;
+          if (pq >= p.Q) {
+            pq -= p.Q;
+            ++pp;
           }
+          while (pp >= p.P) {
+            pp -= p.P;
+            ++pn;
+          }
+        }
+        if (++cc == cchunks && walk_taps) {
+          cc = 0;
+          ++tap;
+          if (++ts == kw) {
+            ts = 0;
+            ++tr;
+          }
+        }
+        if (++stage == num_stages) {
+          stage = 0;
+          phase ^= 1u;
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (single thread) =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      int local = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++local) {
-        const TileCoord t = decode_tile(p, tile);
-        const int acc = local & 1;
-        const uint32_t acc_phase = (local >> 1) & 1;
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
+    // ===================== MMA issuer (one elected lane; warp-uniform control) =====================
+    const uint32_t idesc = p.idesc;
+    const uint64_t a_hi = (static_cast<uint64_t>(p.a_desc_hi) << 32) | (static_cast<uint64_t>(p.a_lbo_enc) << 16);
+    const uint64_t b_hi = (static_cast<uint64_t>(p.b_desc_hi) << 32) | (static_cast<uint64_t>(p.b_lbo_enc) << 16);
+    const uint32_t a_kstep = p.a_kstep_enc, b_kstep = p.b_kstep_enc;
+    const bool do_mma = !(p.dbg & 1);
+    const int cchunks_mma = p.mma_cchunks, ksteps_tail = p.ksteps_tail;
+    int stage = 0;
+    uint32_t phase = 0;
+    int local = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+      const TileCoord t = decode_tile(p, tile);
+      const int acc = local & 1;
+      const uint32_t acc_phase = (local >> 1) & 1;
+      mbar_wait_u32(smem_u32(&tmem_empty[acc]), acc_phase ^ 1u);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * ACC_STRIDE_COLS;
+      uint32_t accumulate = 0;
+      int cc = t.kb_begin % cchunks_mma;
+      for (int kb = t.kb_begin; kb < t.kb_end; ++kb) {
+        const bool tail = (++cc == cchunks_mma);
+        if (tail) cc = 0;
+        mbar_wait_u32(full_u32 + stage * 8, phase);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + acc * ACC_STRIDE_COLS;
-        for (int kb = t.kb_begin; kb < t.kb_end; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t sA = smem_u32(tiles + stage * p.stage_bytes);
-          const uint32_t sB = sA + A_STAGE_BYTES;
-          uint64_t adesc = make_desc(sA, p.a_lbo_enc, p.a_desc_hi);
-          uint64_t bdesc = make_desc(sB, p.b_lbo_enc, p.b_desc_hi);
+        const uint32_t sA = tiles_u32 + stage * stage_bytes;
+        const uint64_t adesc = a_hi | ((sA >> 4) & 0x3FFFu);
+        const uint64_t bdesc = b_hi | (((sA + A_STAGE_BYTES) >> 4) & 0x3FFFu);
+        if (elect_one()) {
+          if (do_mma) {
+            if (!tail || ksteps_tail == BK / 16) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            umma_bf16(tmem_d, adesc, bdesc, p.idesc, (kb > t.kb_begin || k > 0) ? 1u : 0u);
-            adesc += p.a_kstep_enc;
-            bdesc += p.b_kstep_enc;
+              for (int k = 0; k < BK / 16; ++k)
+                umma_bf16(tmem_d, adesc + k * a_kstep, bdesc + k * b_kstep, idesc, accumulate | (uint32_t)k);
+            } else {
+              // zero-padded K-steps of the last channel chunk (cin_g = 48 -> 3 of 4) are not issued at all
+              for (int k = 0; k < ksteps_tail; ++k)
+                umma_bf16(tmem_d, adesc + k * a_kstep, bdesc + k * b_kstep, idesc, accumulate | (uint32_t)k);
+            }
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot once the MMAs have read it
-          if (++stage == p.num_stages) {
-            stage = 0;
-            phase ^= 1u;
-          }
+          umma_commit_u32(empty_u32 + stage * 8);  // frees the smem slot once the MMAs have read it
         }
-        umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+        __syncwarp();
+        accumulate = 1;
+        if (++stage == num_stages) {
+          stage = 0;
+          phase ^= 1u;
+        }
       }
+      if (elect_one()) umma_commit_u32(smem_u32(&tmem_full[acc]));  // accumulator complete -> epilogue
+      __syncwarp();
     }
   } else {
     // ===================== epilogue warps (TMEM -> registers -> HBM) =====================
@@ -269,7 +324,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
       const int row_in_tile = quad * 32 + lane;
       long long grow;
       bool row_ok;
-      if (p.a_mode == VL_A_IM2COL_MN) {
+      if (AM == VL_A_IM2COL_MN) {
         int mc = t.m_blk * 2 + (row_in_tile >> 6);
         int tap = mc / p.cchunks;
         int cc = mc - tap * p.cchunks;
@@ -294,7 +349,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
                           (p.mask == nullptr || p.mask_ld % 8 == 0);
 
       auto process = [&](const uint32_t (&v)[16], int c0) {
-        if (!row_ok) return;
+        if (!row_ok || (p.dbg & 8)) return;
         const int ncols = min(16, p.N - (n0 + c0));
         if (ncols <= 0) return;
         float f[16];
@@ -541,6 +596,17 @@ extern "C" int vl_gemm(const vl_gemm_desc* d, const void* a, const void* b, void
     }
   }
   if (!a_im2col) p.cchunks = p.kb_total;  // dense k-block walk: tap = 0, cc = kb
+  p.ksteps_tail = BK / 16;
+  p.mma_cchunks = p.cchunks;
+  if (d->a_mode == VL_A_IM2COL_K)
+    p.ksteps_tail = ceil_div(cg.cin_g - (p.cchunks - 1) * 64, 16);
+  else if (!a_im2col)
+    p.ksteps_tail = ceil_div(d->k - (p.kb_total - 1) * BK, 16);
+  if (d->a_mode == VL_A_IM2COL_MN) {
+    p.mma_cchunks = 1 << 30;  // the contraction runs over pixels: no per-tap tail
+    p.mn_step_rows = BK / cg.q;
+    p.mn_step_rem = BK % cg.q;
+  }
   // B_TILED_K decodes (tap, cc) from kb with p.cchunks; for transposed-im2col A the B operand is always N-major.
   VL_REQUIRE(!(d->a_mode == VL_A_IM2COL_MN && d->b_mode == VL_B_TILED_K),
              "vl_gemm: transposed im2col A requires an N-major B");
@@ -552,6 +618,10 @@ extern "C" int vl_gemm(const vl_gemm_desc* d, const void* a, const void* b, void
   VL_REQUIRE(p.split_k == 1 || (d->c_atomic && d->c_dtype == VL_DT_F32), "vl_gemm: split_k needs fp32 atomic output");
   p.total_tiles = p.num_m_blk * p.num_n_blk * p.groups * p.split_k;
 
+  {
+    const char* e = getenv("VL_GEMM_DBG");
+    p.dbg = e ? atoi(e) : 0;
+  }
   // ---- epilogue ----
   p.C = c;
   p.c_ld = d->c_ld;
@@ -614,13 +684,29 @@ extern "C" int vl_gemm(const vl_gemm_desc* d, const void* a, const void* b, void
     if (make_tiled_map(&tmB, b, inner, outer, d->b_ld, 64, 64) != 0) return -1;
   }
 
-  static bool attr_set = false;
-  if (!attr_set) {
-    VL_CHECK_CUDA(cudaFuncSetAttribute(umma_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-    attr_set = true;
+  const int grid = p.total_tiles < vl::num_sms() ? p.total_tiles : vl::num_sms();
+#define VL_LAUNCH_GEMM(AMODE, BMODE_)                                                                            \
+  do {                                                                                                          \
+    static bool attr_set = false;                                                                               \
+    if (!attr_set) {                                                                                            \
+      VL_CHECK_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<AMODE, BMODE_>,                                       \
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));             \
+      attr_set = true;                                                                                          \
+    }                                                                                                           \
+    umma_gemm_kernel<AMODE, BMODE_><<<grid, NUM_THREADS, smem_bytes, stream>>>(tmA, tmB, p);                    \
+  } while (0)
+  const int combo = d->a_mode * 2 + d->b_mode;
+  switch (combo) {
+    case VL_A_TILED_K * 2 + VL_B_TILED_K: VL_LAUNCH_GEMM(VL_A_TILED_K, VL_B_TILED_K); break;
+    case VL_A_TILED_K * 2 + VL_B_TILED_MN: VL_LAUNCH_GEMM(VL_A_TILED_K, VL_B_TILED_MN); break;
+    case VL_A_TILED_MN * 2 + VL_B_TILED_K: VL_LAUNCH_GEMM(VL_A_TILED_MN, VL_B_TILED_K); break;
+    case VL_A_TILED_MN * 2 + VL_B_TILED_MN: VL_LAUNCH_GEMM(VL_A_TILED_MN, VL_B_TILED_MN); break;
+    case VL_A_IM2COL_K * 2 + VL_B_TILED_K: VL_LAUNCH_GEMM(VL_A_IM2COL_K, VL_B_TILED_K); break;
+    case VL_A_IM2COL_K * 2 + VL_B_TILED_MN: VL_LAUNCH_GEMM(VL_A_IM2COL_K, VL_B_TILED_MN); break;
+    case VL_A_IM2COL_MN * 2 + VL_B_TILED_MN: VL_LAUNCH_GEMM(VL_A_IM2COL_MN, VL_B_TILED_MN); break;
+    default: VL_REQUIRE(false, "vl_gemm: unsupported operand mode combination a=%d b=%d", d->a_mode, d->b_mode);
   }
-  int grid = p.total_tiles < vl::num_sms() ? p.total_tiles : vl::num_sms();
-  umma_gemm_kernel<<<grid, NUM_THREADS, smem_bytes, stream>>>(tmA, tmB, p);
+#undef VL_LAUNCH_GEMM
   vl::g_launches.fetch_add(1);
   VL_CHECK_CUDA(cudaGetLastError());
   return 0;

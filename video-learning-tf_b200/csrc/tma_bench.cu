@@ -103,3 +103,90 @@ extern "C" int vl_debug_tma_bench(const void* base, int32_t im2col, int32_t n_im
   VL_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Development probe 2: cost per iteration of the producer/consumer mbarrier handshake of the contraction kernel,
+// without any data movement.  variant bits: 1 = consumer releases slots with tcgen05.commit (else mbarrier.arrive),
+// 2 = tcgen05.fence::after_thread_sync after each full-wait, 4 = consumer issues 4 UMMAs (128 x bn x 16) per iteration.
+// ------------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(64, 1)
+    sync_bench_kernel(int variant, int stages, int iters, int bn, long long* out_cycles) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* empty_bar = full_bar + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 256);
+  const uint32_t tiles = smem_u32(smem + 1024);
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t full_u32 = smem_u32(full_bar), empty_u32 = smem_u32(empty_bar);
+  if (warp == 0) {
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int i = 0; i < iters; ++i) {
+      mbar_wait_u32(empty_u32 + stage * 8, phase ^ 1u);
+      if (elect_one()) mbar_expect_tx_u32(full_u32 + stage * 8, 0);
+      __syncwarp();
+      if (++stage == stages) { stage = 0; phase ^= 1u; }
+    }
+  } else {
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((128u >> 4) << 24);
+    const uint64_t hi = (static_cast<uint64_t>((1024u >> 4) | (1u << 14) | (2u << 29)) << 32) | (1ull << 16);
+    int stage = 0;
+    uint32_t phase = 0;
+    long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) {
+      mbar_wait_u32(full_u32 + stage * 8, phase);
+      if (variant & 2) tc_fence_after();
+      const uint64_t adesc = hi | (((tiles + stage * 49152) >> 4) & 0x3FFFu);
+      const uint64_t bdesc = hi | (((tiles + stage * 49152 + 16384) >> 4) & 0x3FFFu);
+      if (elect_one()) {
+        if (variant & 4) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(tmem_base, adesc + k * 2, bdesc + k * 2, idesc, (uint32_t)(i | k));
+        }
+        if (variant & 1) umma_commit_u32(empty_u32 + stage * 8);
+        else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty_u32 + stage * 8) : "memory");
+      }
+      __syncwarp();
+      if (++stage == stages) { stage = 0; phase ^= 1u; }
+    }
+    // drain: wait until the last commit has landed (producer side of the last used slot)
+    long long t1 = clock64();
+    if (threadIdx.x == 32) out_cycles[blockIdx.x] = t1 - t0;
+  }
+  __syncthreads();
+  // let outstanding MMAs / commits finish before TMEM is released
+  if (warp == 1) {
+    __nanosleep(20000);
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+}  // namespace
+
+extern "C" int vl_debug_sync_bench(int32_t variant, int32_t stages, int32_t iters, int32_t bn, int32_t grid,
+                                   long long* out_cycles, vl_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  VL_REQUIRE(stages >= 1 && stages <= 4, "stages 1..4");
+  const int smem = 2048 + stages * 49152;
+  VL_CHECK_CUDA(cudaFuncSetAttribute(sync_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+  sync_bench_kernel<<<grid, 64, smem, stream>>>(variant, stages, iters, bn, out_cycles);
+  VL_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

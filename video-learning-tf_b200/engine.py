@@ -88,6 +88,11 @@ def encoder_specs(h, w):
     """Layer geometry of dcnn.create (alexnet.py:60-211) for an h x w input."""
     sp = {}
     sp["conv1"] = K.ConvSpec(h, w, 3, 96, 11, 11, 4, 1)
+    # conv1 runs as a 3x3 stride-1 VALID convolution over the space-to-depth input (4x4x3 = 48 channels)
+    c1 = sp["conv1"]
+    st = c1.stride
+    hb, wb = c1.p - 1 + -(-c1.kh // st), c1.q - 1 + -(-c1.kw // st)
+    sp["conv1_s2d"] = K.ConvSpec(hb, wb, st * st * 3, 96, -(-c1.kh // st), -(-c1.kw // st), 1, 1, padding="VALID")
     p1h, p1w = K.valid_out(sp["conv1"].p, 3, 2), K.valid_out(sp["conv1"].q, 3, 2)
     sp["conv2"] = K.ConvSpec(p1h, p1w, 96, 256, 5, 5, 1, 2)
     p2h, p2w = K.valid_out(sp["conv2"].p, 3, 2), K.valid_out(sp["conv2"].q, 3, 2)
@@ -156,7 +161,12 @@ class Engine(object):
             offsets.append(off)
         self.arena_n = off
         self.params = torch.zeros(off, dtype=F32, device=self.dev)
-        self.grads = torch.zeros(off, dtype=F32, device=self.dev)
+        # gradient arena + scratch for the filter gradient of the space-to-depth conv1 (zeroed together every step)
+        s1s = self.sp["conv1_s2d"]
+        self._dws_n = _align(s1s.taps * s1s.cin_g * s1s.cout)
+        self.grads_ext = torch.zeros(off + self._dws_n, dtype=F32, device=self.dev)
+        self.grads = self.grads_ext[:off]
+        self.dws1 = self.grads_ext[off:off + s1s.taps * s1s.cin_g * s1s.cout].view(s1s.taps * s1s.cin_g, s1s.cout)
         self.seg_offsets = torch.tensor(offsets, dtype=torch.int64, device=self.dev)
         self.sqnorms = torch.zeros(len(self.var_shapes), dtype=F32, device=self.dev)
         self.scalars = torch.zeros(8, dtype=F32, device=self.dev)  # [0..2] clip scalars, [4] loss, [5] correct
@@ -210,10 +220,8 @@ class Engine(object):
     def _alloc_shadows(self):
         cfg, sp, dev = self.cfg, self.sp, self.dev
         sh = {}
-        s1 = sp["conv1"]
-        self.k1 = s1.taps * 3
-        self.k1_ld = _align(self.k1, 64)
-        sh["conv1"] = torch.zeros(self.k1_ld, 96, dtype=BF16, device=dev)
+        s1s = sp["conv1_s2d"]
+        sh["conv1"] = torch.zeros(s1s.k_packed, 96, dtype=BF16, device=dev)
         for name in ("conv2", "conv3", "conv4", "conv5"):
             s = sp[name]
             sh[name] = torch.zeros(s.taps * s.cin_g, s.cout, dtype=BF16, device=dev)  # HWIO as 2D
@@ -238,8 +246,9 @@ class Engine(object):
     def refresh_shadows(self):
         """fp32 master -> bf16 tensor-core operands (after load and after every optimiser step)."""
         sh, sp = self.sh, self.sp
-        w1 = self.var2d("dcnn/conv1W")
-        nv.call("vl_pack_bf16", w1, self.k1, 96, sh["conv1"], self.k1_ld, 96, self.k1, self.k1_ld)
+        s1 = sp["conv1"]
+        nv.call("vl_s2d_pack_filter", self.var("dcnn/conv1W"), sh["conv1"], s1.kh, s1.kw, 3, 96, s1.stride,
+                sp["conv1_s2d"].cchunks * 64)
         for name in ("conv2", "conv3", "conv4", "conv5"):
             s = sp[name]
             w = self.var2d("dcnn/%sW" % name)
@@ -280,7 +289,8 @@ class Engine(object):
         A = {}
         A["frames_u8"] = act(n, cfg.height, cfg.width, 3, dtype=torch.uint8)
         A["frames_f32"] = None  # allocated lazily: only the reference-compatible fp32 feed needs it
-        A["col1"] = act(n * s1.p * s1.q, self.k1_ld)
+        s1s = sp["conv1_s2d"]
+        A["x_s2d"] = act(n, s1s.h, s1s.w, s1s.cin)
         A["a1"] = act(n, s1.p, s1.q, 96)
         A["p1"] = act(n, p1h, p1w, 96)
         A["arg1"] = act(n, p1h, p1w, 96, dtype=torch.uint8)
@@ -393,12 +403,12 @@ class Engine(object):
         A, sp, sh = self.A, self.sp, self.sh
         s1 = sp["conv1"]
         (p1h, p1w), (p2h, p2w), (p5h, p5w) = sp["pool1"], sp["pool2"], sp["pool5"]
-        m1 = n * s1.p * s1.q
-        col = A["col1"][:m1]
-        nv.call("vl_conv1_patches", frames, 1 if is_u8 else 0, self._mean_dev(), col, n, self.cfg.height,
-                self.cfg.width, s1.kh, s1.kw, s1.stride, s1.pad_top, s1.pad_left, s1.p, s1.q, self.k1_ld)
+        s1s = sp["conv1_s2d"]
+        xs = A["x_s2d"][:n]
+        nv.call("vl_frames_s2d", frames, 1 if is_u8 else 0, self._mean_dev(), xs, n, self.cfg.height, self.cfg.width,
+                s1.stride, s1.pad_top, s1.pad_left, s1s.h, s1s.w)
         a1 = A["a1"][:n]
-        K.linear_fwd(col, sh["conv1"], self.var("dcnn/conv1b"), a1.view(m1, 96), relu=True)
+        K.conv_fwd(s1s, xs, sh["conv1"], self.var("dcnn/conv1b"), a1, relu=True)
         nv.call("vl_lrn_pool_fwd", a1, A["p1"][:n], A["arg1"][:n], n, s1.p, s1.q, 96, LRN["radius"], LRN["alpha"],
                 LRN["beta"], LRN["bias"])
         s2 = sp["conv2"]
@@ -571,10 +581,10 @@ class Engine(object):
         nv.call("vl_pool_lrn_bwd", A["a1"][:n], G["dp1"][:n], A["arg1"][:n], G["da1"][:n],
                 self.var("dcnn/conv1b", self.grads), n, s1.p, s1.q, 96, LRN["radius"], LRN["alpha"], LRN["beta"],
                 LRN["bias"])
-        m1 = n * s1.p * s1.q
-        da1 = G["da1"][:n].view(m1, 96)
-        dw1 = self.var2d("dcnn/conv1W", self.grads)
-        K.linear_wgrad(A["col1"][:m1], da1, dw1, split_k=self._split_k(self.k1, 96, m1), n=96)
+        s1s = sp["conv1_s2d"]
+        K.conv_wgrad(s1s, A["x_s2d"][:n], G["da1"][:n], self.dws1,
+                     split_k=self._split_k(s1s.taps * s1s.cchunks * 64, s1s.cout_g, n * s1s.p * s1s.q, 1))
+        nv.call("vl_s2d_unpack_grad", self.dws1, self.var("dcnn/conv1W", self.grads), s1.kh, s1.kw, 3, 96, s1.stride)
 
     # ------------------------------------------------------------------------------------------
     # training step
@@ -605,7 +615,7 @@ class Engine(object):
         logits = self._head_fwd(feat, n, True)
         nv.call("vl_softmax_ce", logits, A["labels"][:b], b, c, parallel.local_grad_scale(b, self.world), A["row_loss"],
                 self.scalars[4:6], A["dlogits"][:b], A["dlogits_bf"][:b], self.c_pad)
-        self.grads.zero_()
+        self.grads_ext.zero_()
         dfeat = self._head_bwd(n)
         self._encoder_bwd(dfeat, n)
         if self.world > 1:

@@ -30,13 +30,17 @@ def valid_out(in_size, k, stride):
 
 
 class ConvSpec(object):
-    """Static description of one (possibly grouped) SAME convolution of the AlexNet encoder."""
+    """Static description of one (possibly grouped) convolution of the AlexNet encoder."""
 
-    def __init__(self, h, w, cin, cout, kh, kw, stride, groups):
+    def __init__(self, h, w, cin, cout, kh, kw, stride, groups, padding="SAME"):
         self.h, self.w, self.cin, self.cout = h, w, cin, cout
         self.kh, self.kw, self.stride, self.groups = kh, kw, stride, groups
-        self.p, self.pad_top, self.pad_bottom = same_padding(h, kh, stride)
-        self.q, self.pad_left, self.pad_right = same_padding(w, kw, stride)
+        if padding == "SAME":
+            self.p, self.pad_top, self.pad_bottom = same_padding(h, kh, stride)
+            self.q, self.pad_left, self.pad_right = same_padding(w, kw, stride)
+        else:  # VALID: the space-to-depth form of conv1 (vl_frames_s2d materialises the SAME padding)
+            self.p, self.pad_top, self.pad_bottom = valid_out(h, kh, stride), 0, 0
+            self.q, self.pad_left, self.pad_right = valid_out(w, kw, stride), 0, 0
         self.cin_g = cin // groups
         self.cout_g = cout // groups
         self.taps = kh * kw
