@@ -68,11 +68,15 @@ typedef struct vl_gemm_desc {
   int32_t a_ld, b_ld;    /* row pitch in elements of tiled operands (ignored for im2col A)           */
   int32_t a_goff, b_goff, c_goff; /* per-group offset: A channel / inner coordinate, B inner coordinate, C column */
   int32_t b_tap_stride;  /* VL_B_TILED_K with conv: rows of B per filter tap (cin_g); 0 for dense   */
+  int32_t b_row_goff;    /* VL_B_TILED_K: per-group ROW offset of B (K-major forward filters [cout][K])   */
+  int32_t b_tap_inner;   /* VL_B_TILED_K with conv: inner (contraction) advance of B per filter tap; 0 when
+                            the taps are addressed through rows (b_tap_stride, data gradients)            */
   int32_t c_ld;          /* row pitch of C in elements                                              */
   int32_t c_dtype;       /* VL_DT_BF16 / VL_DT_F32                                                  */
   int32_t c_atomic;      /* 1: red.add into C (split-K filter gradients; C must be zeroed)          */
   int32_t relu;          /* 1: max(x,0) after bias                                                  */
-  int32_t split_k;       /* >=1                                                                     */
+  int32_t split_k;       /* >=1; 0 = choose (atomic epilogue only)                                  */
+  int32_t msub;          /* 128-row sub-tiles per CTA tile: 0 = choose, 1, or 2 (needs 2*block_n <= 256)   */
   int32_t block_n;       /* 0 = choose; else multiple of 16 in [16,256]                             */
   int32_t mask_ld;       /* row pitch of relu_mask                                                  */
   vl_conv_geom conv;     /* used when a_mode is an im2col mode                                      */
@@ -105,7 +109,7 @@ int vl_frames_s2d(const void* frames, int32_t is_u8, const float* mean3, void* o
 /* Filter of that convolution: HWIO fp32 [kh][kw][cin][cout] -> bf16 [taps][chunk][cout] (chunk >= s*s*cin rows per
  * tap, zero padded), and the inverse scatter of its filter gradient dws[taps*s*s*cin][cout] -> HWIO dw. */
 int vl_s2d_pack_filter(const float* src, void* dst, int32_t kh, int32_t kw, int32_t cin, int32_t cout, int32_t s,
-                       int32_t chunk, vl_stream_t stream);
+                       int32_t chunk, int32_t transpose /* 1: dst is K-major [cout][taps*chunk] */, vl_stream_t stream);
 int vl_s2d_unpack_grad(const float* dws, float* dw, int32_t kh, int32_t kw, int32_t cin, int32_t cout, int32_t s,
                        vl_stream_t stream);
 
@@ -150,6 +154,10 @@ int vl_colsum(const void* dy, float* out, int64_t rows, int32_t c, int32_t ld, v
  * for padding the class dimension of fc8/output_fc to a multiple of 8. */
 int vl_pack_bf16(const float* src, int32_t rows, int32_t cols, void* dst, int32_t dst_rows, int32_t dst_ld,
                  int32_t src_grp, int32_t dst_grp, vl_stream_t stream);
+/* K-major (transposed) form of the same packing: dst[col][(r/src_grp)*dst_grp + r%src_grp] = src[r][col], dst row
+ * pitch dst_ld; the operand layout of the forward convolutions (one TMA box per k-block). */
+int vl_pack_bf16_t(const float* src, int32_t rows, int32_t cols, void* dst, int32_t dst_ld, int32_t src_grp,
+                   int32_t dst_grp, vl_stream_t stream);
 int vl_cast_f32_to_bf16(const float* src, void* dst, int64_t n, vl_stream_t stream);
 /* dst[cols][rows] = src[rows][cols]^T (fp32): recurrent weights for the BPTT kernel. */
 int vl_transpose_f32(const float* src, float* dst, int32_t rows, int32_t cols, vl_stream_t stream);

@@ -28,7 +28,7 @@ def timed(fn, iters=3):
 
 
 cases = []
-specs = {"conv2": K.ConvSpec(28, 28, 96, 256, 5, 5, 1, 2), "conv3": K.ConvSpec(13, 13, 256, 384, 3, 3, 1, 1),
+specs = {"conv1": K.ConvSpec(59, 59, 48, 96, 3, 3, 1, 1, padding="VALID"), "conv2": K.ConvSpec(28, 28, 96, 256, 5, 5, 1, 2), "conv3": K.ConvSpec(13, 13, 256, 384, 3, 3, 1, 1),
          "conv4": K.ConvSpec(13, 13, 384, 384, 3, 3, 1, 2), "conv5": K.ConvSpec(13, 13, 384, 256, 3, 3, 1, 2)}
 for name, s in specs.items():
     x = torch.randn(n, s.h, s.w, s.cin, device=dev).to(bf)
@@ -38,12 +38,13 @@ for name, s in specs.items():
     b = torch.full((s.cout,), 0.1, device=dev)
     y = torch.empty(n, s.p, s.q, s.cout, device=dev, dtype=bf)
     dy = torch.randn(n, s.p, s.q, s.cout, device=dev).to(bf)
-    dx = torch.empty(n, s.h, s.w, s.cin, device=dev, dtype=bf)
+    dx = torch.empty(n, s.h, s.w, s.cin, device=dev, dtype=bf) if name != "conv1" else None
     dw = torch.zeros(s.taps * s.cin_g, s.cout, device=dev)
     flops = 2.0 * n * s.p * s.q * s.taps * s.cin_g * s.cout
     cases.append((name + " fwd", flops, lambda s=s, x=x, wp=wp, b=b, y=y: K.conv_fwd(s, x, wp, b, y, relu=True)))
-    cases.append((name + " dgrad", flops, lambda s=s, dy=dy, wd=wd, dx=dx: K.conv_dgrad(s, dy, wd, dx)))
-    cases.append((name + " wgrad", flops, lambda s=s, x=x, dy=dy, dw=dw: K.conv_wgrad(s, x, dy, dw, split_k=8)))
+    if dx is not None:
+        cases.append((name + " dgrad", flops, lambda s=s, dy=dy, wd=wd, dx=dx: K.conv_dgrad(s, dy, wd, dx)))
+    cases.append((name + " wgrad", flops, lambda s=s, x=x, dy=dy, dw=dw: K.conv_wgrad(s, x, dy, dw)))
 # dense layers
 for name, m, kk, nn in (("fc6", n, 9216, 4096), ("fc7", n, 4096, 4096)):
     x = torch.randn(m, kk, device=dev).to(bf)
@@ -54,6 +55,8 @@ for name, m, kk, nn in (("fc6", n, 9216, 4096), ("fc7", n, 4096, 4096)):
 
 modes = [(0, "full"), (1, "noMMA"), (1 | 4, "A only"), (1 | 2, "B only"), (1 | 2 | 4, "no loads"), (8, "no store"),
          (2 | 4, "MMA+epi only")]
+if "--quick" in sys.argv:
+    modes = [(0, "full"), (1, "noMMA"), (2 | 4, "MMA+epi only")]
 print("%-14s" % "case" + "".join("%14s" % m[1] for m in modes) + "   TF/s(full)")
 for name, flops, fn in cases:
     row = []

@@ -59,6 +59,10 @@ def test_conv_fwd_dgrad_wgrad_vs_oracle(vl, name, n, h, cin, cout, k, groups):
     spec = K.ConvSpec(h, h, cin, cout, k, k, 1, groups)
     xd, dyd = dev(x, torch.bfloat16), dev(dy, torch.bfloat16)
     packed = K.pack_conv_weight_host(spec, dev(w))
+    dev_packed = torch.empty_like(packed)  # the device packing kernel must agree with the torch restatement
+    vl["nv"].call("vl_pack_bf16_t", dev(w.reshape(-1, cout)), k * k * (cin // groups), cout, dev_packed, spec.k_packed,
+                  cin // groups, spec.cchunks * 64)
+    assert torch.equal(packed, dev_packed)
     out = torch.empty(n, h, h, cout, dtype=torch.bfloat16, device="cuda")
     K.conv_fwd(spec, xd, packed, dev(b), out, relu=True)
     assert rel(out.float().cpu().numpy(), y_ref) < BF16_TOL
@@ -121,8 +125,8 @@ def test_conv1_space_to_depth_path_vs_oracle(vl):
     nv.call("vl_frames_s2d", dev(x), 0, None, xs2, n, 227, 227, 4, 4, 4, 59, 59)
     assert torch.equal(xs, xs2)  # fp32 feed (feeder.py:97-100) == uint8 + mean feed
     # filter packing + forward
-    wp = torch.empty(s1s.k_packed, 96, dtype=torch.bfloat16, device="cuda")
-    nv.call("vl_s2d_pack_filter", dev(w), wp, 11, 11, 3, 96, 4, 64)
+    wp = torch.empty(96, s1s.k_packed, dtype=torch.bfloat16, device="cuda")  # K-major
+    nv.call("vl_s2d_pack_filter", dev(w), wp, 11, 11, 3, 96, 4, 64, 1)
     out = torch.empty(n, 57, 57, 96, dtype=torch.bfloat16, device="cuda")
     K.conv_fwd(s1s, xs, wp, dev(b), out, relu=True)
     y_ref = O.relu(O.conv2d_same(bf16_round(x), w, b, 4, 1))

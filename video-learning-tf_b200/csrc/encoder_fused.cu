@@ -48,6 +48,11 @@ __device__ __forceinline__ float sqrt_approx(float x) {
   asm("sqrt.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+__device__ __forceinline__ float rsqrt_approx(float x) {
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float bf16_round_f(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
 // Channel halo of an 8-channel chunk inside a group of LPP lanes that together hold one pixel: lane l owns channels
@@ -82,72 +87,82 @@ __device__ __forceinline__ void lrn_scale8(const float (&x)[8], int l, int cpr, 
 }
 
 // ------------------------------------------------------------------------------------------------
-// frames -> space-to-depth bf16.  One CTA per (frame, block row): `s` image rows are staged in shared memory
-// (mean-subtracted bf16, SAME zero padding materialised), then out[bx][(dy*s+dx)*3+c] = rows[dy][(s*bx+dx)*3+c].
+// frames -> space-to-depth bf16.  One CTA per (frame, block row).  The S image rows are read with aligned 32-bit
+// loads (uint8 input: 4 pixels-channels per load), mean-subtracted, rounded to bf16 and written straight to their
+// permuted position of the output row in shared memory: out[bx][(dy*S+dx)*3+c] = frame[S*by-pt+dy][S*bx-pl+dx][c];
+// the finished row (wb * S*S*3 bf16, contiguous in HBM) is then copied out with 16-byte stores.
 // ------------------------------------------------------------------------------------------------
-template <bool U8>
+template <bool U8, int S>
 __global__ void __launch_bounds__(128)
     frames_s2d_kernel(const void* __restrict__ frames_, const float* __restrict__ mean3, bf16* __restrict__ out, int h,
-                      int w, int s, int pad_top, int pad_left, int hb, int wb) {
+                      int w, int pad_top, int pad_left, int hb, int wb, long long total_elems) {
   extern __shared__ uint8_t smem_raw[];
-  bf16* rows = reinterpret_cast<bf16*>(smem_raw);  // [s][wb*s*3]
+  bf16* orow_s = reinterpret_cast<bf16*>(smem_raw);  // [wb][S*S*3]
+  constexpr int SEG = S * 3;                          // contiguous source elements per (bx, dy)
+  constexpr int CBLK = S * S * 3;
   const int by = blockIdx.x % hb;
   const int nn = blockIdx.x / hb;
-  const int rw = wb * s * 3;  // staged row width in elements
   float m[3] = {0.f, 0.f, 0.f};
   if (U8 && mean3 != nullptr) {
     m[0] = mean3[0];
     m[1] = mean3[1];
     m[2] = mean3[2];
   }
+  const int row_elems = w * 3;
   const int lead = pad_left * 3;
-  for (int idx = threadIdx.x; idx < s * rw; idx += blockDim.x) {
-    const int dy = idx / rw;
-    const int e = idx - dy * rw;
-    const int y = by * s - pad_top + dy;
-    const int xe = e - lead;  // x*3 + c inside the image row
-    float v = 0.f;
-    if (y >= 0 && y < h && xe >= 0 && xe < w * 3) {
-      const long long off = ((long long)nn * h + y) * (w * 3) + xe;
-      if (U8) {
-        v = (float)reinterpret_cast<const uint8_t*>(frames_)[off] - m[xe % 3];
-      } else {
-        v = reinterpret_cast<const float*>(frames_)[off];
-      }
-    }
-    rows[idx] = __float2bfloat16_rn(v);
-  }
+  // zero fill (SAME padding and rows outside the image)
+  for (int i = threadIdx.x; i < wb * CBLK / 8; i += blockDim.x) reinterpret_cast<uint4*>(orow_s)[i] = make_uint4(0, 0, 0, 0);
   __syncthreads();
-  const int cblk = s * s * 3;  // channels of the space-to-depth tensor (48)
-  const int seg = s * 3;       // contiguous source elements per (bx, dy)
-  const int chunks = wb * cblk / 8;
-  bf16* orow = out + ((long long)nn * hb + by) * wb * cblk;
-  for (int ch = threadIdx.x; ch < chunks; ch += blockDim.x) {
-    alignas(16) bf16 v[8];
-    int e = ch * 8;
-    int bx = e / cblk;
-    int j = e - bx * cblk;
-    int dy = j / seg;
-    int r = j - dy * seg;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      v[k] = rows[dy * rw + bx * seg + r];
-      if (++r == seg) {
-        r = 0;
-        if (++dy == s) {
-          dy = 0;
-          ++bx;
+  for (int dy = 0; dy < S; ++dy) {
+    const int y = by * S - pad_top + dy;
+    if (y < 0 || y >= h) continue;
+    const long long row_off = ((long long)nn * h + y) * row_elems;  // element offset of the image row
+    if (U8) {
+      const uint8_t* base = reinterpret_cast<const uint8_t*>(frames_);
+      const int mis = (int)((reinterpret_cast<uintptr_t>(base) + row_off) & 3);  // bytes before the row in word 0
+      const uint32_t* words = reinterpret_cast<const uint32_t*>(base + row_off - mis);
+      const int nwords = (mis + row_elems + 3) >> 2;
+      for (int wi = threadIdx.x; wi < nwords; wi += blockDim.x) {
+        uint32_t word;
+        if (row_off - mis + 4LL * (wi + 1) <= total_elems) {
+          word = __ldg(words + wi);
+        } else {  // the last word of the buffer: never read past the caller's allocation
+          word = 0;
+          for (int k = 0; k < 4; ++k) {
+            const long long o = row_off - mis + 4LL * wi + k;
+            if (o < total_elems) word |= (uint32_t)base[o] << (8 * k);
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int xe = wi * 4 + k - mis;  // x*3 + c inside the image row
+          if (xe >= 0 && xe < row_elems) {
+            const int e = xe + lead;
+            const int bx = e / SEG, r = e - bx * SEG;
+            const float v = (float)((word >> (8 * k)) & 0xffu) - m[xe % 3];
+            orow_s[bx * CBLK + dy * SEG + r] = __float2bfloat16_rn(v);
+          }
         }
       }
+    } else {
+      const float* src = reinterpret_cast<const float*>(frames_) + row_off;
+      for (int xe = threadIdx.x; xe < row_elems; xe += blockDim.x) {
+        const int e = xe + lead;
+        const int bx = e / SEG, r = e - bx * SEG;
+        orow_s[bx * CBLK + dy * SEG + r] = __float2bfloat16_rn(__ldg(src + xe));
+      }
     }
-    *reinterpret_cast<uint4*>(orow + ch * 8) = *reinterpret_cast<const uint4*>(v);
   }
+  __syncthreads();
+  uint4* dst = reinterpret_cast<uint4*>(out + ((long long)nn * hb + by) * wb * CBLK);
+  for (int i = threadIdx.x; i < wb * CBLK / 8; i += blockDim.x) dst[i] = reinterpret_cast<const uint4*>(orow_s)[i];
 }
 
 // dst[(tr*kb+ts)*chunk + (dy*s+dx)*cin + c][o] = src[s*tr+dy][s*ts+dx][c][o] (0 when outside the kh x kw filter or
 // in the chunk padding).  kb = ceil(kh/s) taps per axis of the space-to-depth convolution.
 __global__ void s2d_pack_filter_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int kh, int kw, int cin,
-                                       int cout, int s, int kb_h, int kb_w, int chunk, long long total) {
+                                       int cout, int s, int kb_h, int kb_w, int chunk, int transpose, long long total) {
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
     const int o = (int)(idx % cout);
@@ -163,7 +178,10 @@ __global__ void s2d_pack_filter_kernel(const float* __restrict__ src, bf16* __re
       const int r = s * tr + dy, q = s * ts + dx;
       if (r < kh && q < kw) v = src[(((long long)r * kw + q) * cin + c) * cout + o];
     }
-    dst[idx] = __float2bfloat16_rn(v);
+    if (transpose)
+      dst[(long long)o * (kb_h * kb_w * chunk) + row] = __float2bfloat16_rn(v);
+    else
+      dst[idx] = __float2bfloat16_rn(v);
   }
 }
 
@@ -190,7 +208,7 @@ __global__ void s2d_unpack_grad_kernel(const float* __restrict__ dws, float* __r
 // windows out of shared memory.  beta = 0.75 fast path: s^-0.75 = rsqrt(s) * sqrt(rsqrt(s)).
 // ------------------------------------------------------------------------------------------------
 template <int LPP>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
     lrn_pool_fwd_kernel2(const bf16* __restrict__ x, bf16* __restrict__ y, uint8_t* __restrict__ arg, int h, int w, int c,
                          int p, int q, int rows_out, int strips, float alpha, float bias) {
   extern __shared__ uint8_t smem_raw[];
@@ -206,63 +224,77 @@ __global__ void __launch_bounds__(256)
   const int ngrp = blockDim.x / LPP;
   const bf16* xin = x + ((long long)nn * h + 2 * p0) * w * c;
   const int npix = in_rows * w;
-  // phase 1 (all lanes of a group take part in the shuffles, also for the padded chunk slots l >= cpr)
-  for (int pix0 = 0; pix0 < npix; pix0 += ngrp) {
-    const int pix = pix0 + grp;
-    const bool live = pix < npix && l < cpr;
-    float v[8];
-    if (live) {
-      unpack8(*reinterpret_cast<const Bf16x8*>(xin + (long long)pix * c + l * 8), v);
-    } else {
+  // phase 1: two pixels per lane group and iteration (both loads are in flight before the first use); all lanes of a
+  // group take part in the shuffles, also the padded chunk slots l >= cpr
+  for (int pix0 = 0; pix0 < npix; pix0 += 2 * ngrp) {
+    int pix[2];
+    bool live[2];
+    float v[2][8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = 0.f;
-    }
-    float s[8];
-    lrn_scale8<LPP>(v, l, cpr, alpha, bias, s);
-    if (live) {
-      float o[8];
+    for (int u = 0; u < 2; ++u) {
+      pix[u] = pix0 + u * ngrp + grp;
+      live[u] = pix[u] < npix && l < cpr;
+      if (live[u]) {
+        unpack8(*reinterpret_cast<const Bf16x8*>(xin + (long long)pix[u] * c + l * 8), v[u]);
+      } else {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float rs = rsqrtf(s[j]);
-        o[j] = v[j] * (rs * sqrt_approx(rs));
+        for (int j = 0; j < 8; ++j) v[u][j] = 0.f;
       }
-      *reinterpret_cast<Bf16x8*>(tile + (long long)pix * c + l * 8) = pack8(o);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      float s[8];
+      lrn_scale8<LPP>(v[u], l, cpr, alpha, bias, s);
+      if (live[u]) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float rs = rsqrt_approx(s[j]);
+          o[j] = v[u][j] * (rs * sqrt_approx(rs));
+        }
+        *reinterpret_cast<Bf16x8*>(tile + pix[u] * c + l * 8) = pack8(o);
+      }
     }
   }
   __syncthreads();
-  // phase 2
+  // phase 2: 3x3/2 windows out of shared memory, two channels per instruction (bf16x2 compare / max / select)
   const int nout = np * q * cpr;
   for (int idx = threadIdx.x; idx < nout; idx += blockDim.x) {
     const int ch = idx % cpr;
     const int t = idx / cpr;
     const int qq = t % q;
     const int pl = t / q;
-    float best[8];
-    int bi[8];
+    __nv_bfloat162 best[4];
+    uint32_t bidx[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      best[j] = -INFINITY;
-      bi[j] = 0;
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t ninf = 0xFF80FF80u;  // (-inf, -inf)
+      best[i] = *reinterpret_cast<const __nv_bfloat162*>(&ninf);
+      bidx[i] = 0;
     }
+    const bf16* wbase = tile + ((2 * pl) * w + 2 * qq) * c + ch * 8;
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
 #pragma unroll
       for (int s2 = 0; s2 < 3; ++s2) {
-        float v[8];
-        unpack8(*reinterpret_cast<const Bf16x8*>(tile + ((2 * pl + r) * w + (2 * qq + s2)) * c + ch * 8), v);
+        const Bf16x8 v = *reinterpret_cast<const Bf16x8*>(wbase + (r * w + s2) * c);
+        const uint32_t code2 = (uint32_t)(r * 3 + s2) * 0x00010001u;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if (v[j] > best[j]) {  // strict: the first maximum in (h, w) scan order wins, like TF
-            best[j] = v[j];
-            bi[j] = r * 3 + s2;
-          }
+        for (int i = 0; i < 4; ++i) {
+          // strict >: the first maximum in (h, w) scan order wins, like TF
+          const uint32_t m = __hgt2_mask(v.v[i], best[i]);
+          best[i] = __hmax2(best[i], v.v[i]);
+          bidx[i] = (bidx[i] & ~m) | (code2 & m);
         }
       }
     }
     const long long opix = ((long long)nn * p + (p0 + pl)) * q + qq;
-    *reinterpret_cast<Bf16x8*>(y + opix * c + ch * 8) = pack8(best);
-    uint32_t lo = bi[0] | (bi[1] << 8) | (bi[2] << 16) | (bi[3] << 24);
-    uint32_t hi = bi[4] | (bi[5] << 8) | (bi[6] << 16) | (bi[7] << 24);
+    Bf16x8 o;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o.v[i] = best[i];
+    *reinterpret_cast<Bf16x8*>(y + opix * c + ch * 8) = o;
+    const uint32_t lo = __byte_perm(bidx[0], bidx[1], 0x6420);
+    const uint32_t hi = __byte_perm(bidx[2], bidx[3], 0x6420);
     *reinterpret_cast<uint2*>(arg + opix * c + ch * 8) = make_uint2(lo, hi);
   }
 }
@@ -271,17 +303,22 @@ __global__ void __launch_bounds__(256)
 // MaxPoolGrad -> LRNGrad -> ReluGrad (+ bias gradient).
 //   dn_i = sum over pooling windows whose argmax is pixel i of dy          (bf16 rounded, as the unfused path stores it)
 //   dx_i = relu'(x_i) * ( dn_i * s_i^-b  -  2ab x_i * sum_{|d-i|<=2} dn_d x_d s_d^(-b-1) )
+// CTAs walk image rows (no per-thread 64-bit index arithmetic); LPP lanes hold one pixel, 16 bytes per lane.
 // ------------------------------------------------------------------------------------------------
-template <int LPP>
-__global__ void __launch_bounds__(256)
+// C_, H_, W_ > 0 fix the geometry at compile time (the two AlexNet instances); 0 = runtime values.
+template <int LPP, int C_, int H_, int W_>
+__global__ void __launch_bounds__(256, 3)
     pool_lrn_bwd_kernel2(const bf16* __restrict__ x, const bf16* __restrict__ dy, const uint8_t* __restrict__ arg,
-                         bf16* __restrict__ dx, float* __restrict__ dbias, int h, int w, int c, int p, int q, float alpha,
-                         float beta, float bias, long long total_pix) {
+                         bf16* __restrict__ dx, float* __restrict__ dbias, int n, int h_rt, int w_rt, int c_rt,
+                         float alpha, float beta, float bias) {
   __shared__ float bsum[256];
+  const int c = C_ ? C_ : c_rt, h = H_ ? H_ : h_rt, w = W_ ? W_ : w_rt;
+  const int p = (h - 3) / 2 + 1, q = (w - 3) / 2 + 1;
   const int cpr = c >> 3;
   const int l = threadIdx.x % LPP;
   const int grp = threadIdx.x / LPP;
-  const int ngrp = blockDim.x / LPP;
+  constexpr int ngrp = 256 / LPP;
+  const int c0 = l * 8;
   if (dbias != nullptr) {
     for (int i = threadIdx.x; i < c; i += blockDim.x) bsum[i] = 0.f;
     __syncthreads();
@@ -290,93 +327,100 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
   for (int j = 0; j < 8; ++j) bacc[j] = 0.f;
   const float k2ab = 2.0f * alpha * beta;
-  const long long stride = (long long)gridDim.x * ngrp;
-  const long long iters = (total_pix + stride - 1) / stride;
-  long long pix = (long long)blockIdx.x * ngrp + grp;
-  for (long long it = 0; it < iters; ++it, pix += stride) {
-    const bool live = pix < total_pix && l < cpr;
-    float xv[8], gv[8];
+  const int rows_total = n * h;
+  for (int row = blockIdx.x; row < rows_total; row += gridDim.x) {
+    const int nn = row / h;
+    const int hh = row - nn * h;
+    const int p_lo = max(0, (hh - 1) >> 1), p_hi = min(p - 1, hh >> 1);
+    const bf16* xrow = x + (long long)row * (w * c);
+    bf16* dxrow = dx + (long long)row * (w * c);
+    const bf16* dyimg = dy + (long long)nn * (p * q * c);      // pooled tensors of this frame (32-bit offsets inside)
+    const uint8_t* argimg = arg + (long long)nn * (p * q * c);
+    for (int ww0 = 0; ww0 < w; ww0 += ngrp) {
+      const int ww = ww0 + grp;
+      const bool live = ww < w && l < cpr;
+      float xv[8], gv[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) xv[j] = gv[j] = 0.f;
-    if (live) {
-      const int c0 = l * 8;
-      const int ww = (int)(pix % w);
-      const long long t = pix / w;
-      const int hh = (int)(t % h);
-      const int nn = (int)(t / h);
-      unpack8(*reinterpret_cast<const Bf16x8*>(x + pix * c + c0), xv);
-      const int p_lo = max(0, (hh - 1) >> 1), p_hi = min(p - 1, hh >> 1);
-      const int q_lo = max(0, (ww - 1) >> 1), q_hi = min(q - 1, ww >> 1);
-      for (int pp = p_lo; pp <= p_hi; ++pp) {
-        const int r = hh - 2 * pp;
-        if (r > 2) continue;
-        for (int qq = q_lo; qq <= q_hi; ++qq) {
-          const int s2 = ww - 2 * qq;
-          if (s2 > 2) continue;
-          const long long opix = ((long long)nn * p + pp) * q + qq;
-          const uint32_t code = r * 3 + s2;
-          float g[8];
-          unpack8(*reinterpret_cast<const Bf16x8*>(dy + opix * c + c0), g);
-          const uint2 a = *reinterpret_cast<const uint2*>(arg + opix * c + c0);
+      for (int j = 0; j < 8; ++j) xv[j] = gv[j] = 0.f;
+      if (live) {
+        const Bf16x8 xin = *reinterpret_cast<const Bf16x8*>(xrow + ww * c + c0);
+        // dn: pooled gradient routed through the argmax codes, accumulated two channels per instruction in bf16
+        // (exact for up to two contributions; the unfused path rounds the fp32 sum to bf16 once)
+        __nv_bfloat162 g2[4];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const uint32_t aj = ((j < 4 ? a.x : a.y) >> (8 * (j & 3))) & 0xffu;
-            if (aj == code) gv[j] += g[j];
+        for (int i = 0; i < 4; ++i) g2[i] = __floats2bfloat162_rn(0.f, 0.f);
+        const int q_lo = max(0, (ww - 1) >> 1), q_hi = min(q - 1, ww >> 1);
+        for (int pp = p_lo; pp <= p_hi; ++pp) {
+          const int r3 = (hh - 2 * pp) * 3;  // window row 0..2 by construction of [p_lo, p_hi]
+          for (int qq = q_lo; qq <= q_hi; ++qq) {
+            const int o = (pp * q + qq) * c + c0;
+            const uint32_t code4 = (uint32_t)(r3 + ww - 2 * qq) * 0x01010101u;
+            const uint4 g = *reinterpret_cast<const uint4*>(dyimg + o);
+            const uint2 a = *reinterpret_cast<const uint2*>(argimg + o);
+            const uint32_t mlo = __vcmpeq4(a.x, code4), mhi = __vcmpeq4(a.y, code4);  // 0xff per matching channel
+            const uint32_t gw[4] = {g.x & __byte_perm(mlo, 0, 0x1100), g.y & __byte_perm(mlo, 0, 0x3322),
+                                    g.z & __byte_perm(mhi, 0, 0x1100), g.w & __byte_perm(mhi, 0, 0x3322)};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) g2[i] = __hadd2(g2[i], *reinterpret_cast<const __nv_bfloat162*>(&gw[i]));
           }
         }
+        unpack8(xin, xv);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 t = __bfloat1622float2(g2[i]);
+          gv[2 * i] = t.x;
+          gv[2 * i + 1] = t.y;
+        }
       }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) gv[j] = bf16_round_f(gv[j]);
-    }
-    float s[8];
-    lrn_scale8<LPP>(xv, l, cpr, alpha, bias, s);
-    float pw[8], tt[12];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float inv;
-      if (beta == 0.75f) {
-        const float rs = rsqrtf(s[j]);
-        pw[j] = rs * sqrt_approx(rs);
-        inv = rs * rs;
-      } else {
-        pw[j] = __powf(s[j], -beta);
-        inv = __fdividef(1.0f, s[j]);
-      }
-      tt[2 + j] = gv[j] * xv[j] * pw[j] * inv;
-    }
-    {
-      float own[8], lf[2], rt[2];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) own[j] = tt[2 + j];
-      halo2<LPP>(own, l, cpr, lf, rt);
-      tt[0] = lf[0];
-      tt[1] = lf[1];
-      tt[10] = rt[0];
-      tt[11] = rt[1];
-    }
-    if (live) {
-      float out[8];
+      float s[8];
+      lrn_scale8<LPP>(xv, l, cpr, alpha, bias, s);
+      float pw[8], tt[12];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float sum = ((tt[j] + tt[j + 1]) + tt[j + 2]) + (tt[j + 3] + tt[j + 4]);
-        float g = gv[j] * pw[j] - k2ab * xv[j] * sum;
-        if (!(xv[j] > 0.f)) g = 0.f;  // ReLU gradient of the producing conv
-        out[j] = g;
+        float inv;
+        if (beta == 0.75f) {
+          const float rs = rsqrt_approx(s[j]);
+          pw[j] = rs * sqrt_approx(rs);
+          inv = rs * rs;
+        } else {
+          pw[j] = __powf(s[j], -beta);
+          inv = __fdividef(1.0f, s[j]);
+        }
+        tt[2 + j] = (gv[j] * xv[j]) * (pw[j] * inv);
       }
-      const Bf16x8 packed = pack8(out);
-      *reinterpret_cast<Bf16x8*>(dx + pix * c + l * 8) = packed;
-      if (dbias != nullptr) {
-        float rb[8];
-        unpack8(packed, rb);  // the bias gradient sums the bf16 values that are stored (as vl_colsum would)
+      {
+        float own[8], lf[2], rt[2];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) bacc[j] += rb[j];
+        for (int j = 0; j < 8; ++j) own[j] = tt[2 + j];
+        halo2<LPP>(own, l, cpr, lf, rt);
+        tt[0] = lf[0];
+        tt[1] = lf[1];
+        tt[10] = rt[0];
+        tt[11] = rt[1];
+      }
+      if (live) {
+        float out[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float sum = ((tt[j] + tt[j + 1]) + tt[j + 2]) + (tt[j + 3] + tt[j + 4]);
+          const float g = fmaf(gv[j], pw[j], -(k2ab * xv[j]) * sum);
+          out[j] = xv[j] > 0.f ? g : 0.f;  // ReLU gradient of the producing conv
+        }
+        const Bf16x8 packed = pack8(out);
+        *reinterpret_cast<Bf16x8*>(dxrow + ww * c + c0) = packed;
+        if (dbias != nullptr) {
+          float rb[8];
+          unpack8(packed, rb);  // the bias gradient sums the bf16 values that are stored (as vl_colsum would)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) bacc[j] += rb[j];
+        }
       }
     }
   }
   if (dbias != nullptr) {
     if (l < cpr) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) atomicAdd(&bsum[l * 8 + j], bacc[j]);
+      for (int j = 0; j < 8; ++j) atomicAdd(&bsum[c0 + j], bacc[j]);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < c; i += blockDim.x) atomicAdd(dbias + i, bsum[i]);
@@ -395,29 +439,31 @@ extern "C" int vl_frames_s2d(const void* frames, int32_t is_u8, const float* mea
                              int32_t w, int32_t s, int32_t pad_top, int32_t pad_left, int32_t hb, int32_t wb,
                              vl_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  VL_REQUIRE(frames && out && s >= 1 && hb > 0 && wb > 0, "vl_frames_s2d: bad arguments");
+  VL_REQUIRE(frames && out && hb > 0 && wb > 0, "vl_frames_s2d: bad arguments");
+  VL_REQUIRE(s == 4, "vl_frames_s2d: only stride 4 (conv1, alexnet.py:76) is instantiated");
   VL_REQUIRE((wb * s * s * 3) % 8 == 0, "vl_frames_s2d: wb*s*s*3 must be a multiple of 8");
-  const size_t smem = (size_t)s * wb * s * 3 * sizeof(bf16);
+  VL_REQUIRE((w + pad_left) * 3 <= wb * s * 3, "vl_frames_s2d: image row does not fit the block row");
+  const size_t smem = (size_t)wb * s * s * 3 * sizeof(bf16);
   VL_REQUIRE(smem <= 48 * 1024, "vl_frames_s2d: image row too wide (%zu bytes of shared memory)", smem);
   const int grid = n * hb;
   if (is_u8)
-    frames_s2d_kernel<true><<<grid, 128, smem, stream>>>(frames, mean3, reinterpret_cast<bf16*>(out), h, w, s, pad_top,
-                                                         pad_left, hb, wb);
+    frames_s2d_kernel<true, 4><<<grid, 128, smem, stream>>>(frames, mean3, reinterpret_cast<bf16*>(out), h, w, pad_top,
+                                                            pad_left, hb, wb, (long long)n * h * w * 3);
   else
-    frames_s2d_kernel<false><<<grid, 128, smem, stream>>>(frames, mean3, reinterpret_cast<bf16*>(out), h, w, s, pad_top,
-                                                          pad_left, hb, wb);
+    frames_s2d_kernel<false, 4><<<grid, 128, smem, stream>>>(frames, mean3, reinterpret_cast<bf16*>(out), h, w, pad_top,
+                                                             pad_left, hb, wb, (long long)n * h * w * 3);
   VL_LAUNCHED();
   return 0;
 }
 
 extern "C" int vl_s2d_pack_filter(const float* src, void* dst, int32_t kh, int32_t kw, int32_t cin, int32_t cout,
-                                  int32_t s, int32_t chunk, vl_stream_t stream_) {
+                                  int32_t s, int32_t chunk, int32_t transpose, vl_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   VL_REQUIRE(src && dst && s >= 1 && chunk >= s * s * cin, "vl_s2d_pack_filter: bad arguments");
   const int kb_h = (kh + s - 1) / s, kb_w = (kw + s - 1) / s;
   const long long total = (long long)kb_h * kb_w * chunk * cout;
   s2d_pack_filter_kernel<<<(int)((total + 255) / 256), 256, 0, stream>>>(src, reinterpret_cast<bf16*>(dst), kh, kw, cin,
-                                                                         cout, s, kb_h, kb_w, chunk, total);
+                                                                         cout, s, kb_h, kb_w, chunk, transpose, total);
   VL_LAUNCHED();
   return 0;
 }
@@ -462,7 +508,7 @@ extern "C" int vl_lrn_pool_fwd(const void* x, void* y, void* argmax, int32_t n, 
       VL_CHECK_CUDA(cudaFuncSetAttribute(lrn_pool_fwd_kernel2<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
       attr = true;
     }
-    lrn_pool_fwd_kernel2<16><<<grid, 256, smem, stream>>>(reinterpret_cast<const bf16*>(x), reinterpret_cast<bf16*>(y),
+    lrn_pool_fwd_kernel2<16><<<grid, 512, smem, stream>>>(reinterpret_cast<const bf16*>(x), reinterpret_cast<bf16*>(y),
                                                           reinterpret_cast<uint8_t*>(argmax), h, w, c, p, q, rows_out,
                                                           strips, alpha, bias);
   } else {
@@ -471,7 +517,7 @@ extern "C" int vl_lrn_pool_fwd(const void* x, void* y, void* argmax, int32_t n, 
       VL_CHECK_CUDA(cudaFuncSetAttribute(lrn_pool_fwd_kernel2<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
       attr = true;
     }
-    lrn_pool_fwd_kernel2<32><<<grid, 256, smem, stream>>>(reinterpret_cast<const bf16*>(x), reinterpret_cast<bf16*>(y),
+    lrn_pool_fwd_kernel2<32><<<grid, 512, smem, stream>>>(reinterpret_cast<const bf16*>(x), reinterpret_cast<bf16*>(y),
                                                           reinterpret_cast<uint8_t*>(argmax), h, w, c, p, q, rows_out,
                                                           strips, alpha, bias);
   }
@@ -487,20 +533,24 @@ extern "C" int vl_pool_lrn_bwd(const void* x, const void* dy, const void* argmax
   VL_REQUIRE(radius == 2, "vl_pool_lrn_bwd: only depth_radius 2 (alexnet.py:80,121) is implemented");
   if (c > 256) return vl_pool_lrn_bwd_generic(x, dy, argmax, dx, dbias, n, h, w, c, radius, alpha, beta, bias, stream_);
   const int p = (h - 3) / 2 + 1, q = (w - 3) / 2 + 1;
-  const long long total_pix = (long long)n * h * w;
   const int lpp = c <= 128 ? 16 : 32;
-  const int ngrp = 256 / lpp;
-  long long blocks = (total_pix + ngrp - 1) / ngrp;
-  const long long cap = (long long)vl::num_sms() * 8;
+  long long blocks = (long long)n * h;
+  const long long cap = (long long)vl::num_sms() * 6;
   if (blocks > cap) blocks = cap;
-  if (lpp == 16)
-    pool_lrn_bwd_kernel2<16><<<(int)blocks, 256, 0, stream>>>(
-        reinterpret_cast<const bf16*>(x), reinterpret_cast<const bf16*>(dy), reinterpret_cast<const uint8_t*>(argmax),
-        reinterpret_cast<bf16*>(dx), dbias, h, w, c, p, q, alpha, beta, bias, total_pix);
+#define VL_BWD_ARGS                                                                                                   \
+  reinterpret_cast<const bf16*>(x), reinterpret_cast<const bf16*>(dy), reinterpret_cast<const uint8_t*>(argmax),    \
+      reinterpret_cast<bf16*>(dx), dbias, n, h, w, c, alpha, beta, bias
+  (void)p;
+  (void)q;
+  if (c == 96 && h == 57 && w == 57)  // conv1 block of the 227x227 AlexNet
+    pool_lrn_bwd_kernel2<16, 96, 57, 57><<<(int)blocks, 256, 0, stream>>>(VL_BWD_ARGS);
+  else if (c == 256 && h == 28 && w == 28)  // conv2 block
+    pool_lrn_bwd_kernel2<32, 256, 28, 28><<<(int)blocks, 256, 0, stream>>>(VL_BWD_ARGS);
+  else if (lpp == 16)
+    pool_lrn_bwd_kernel2<16, 0, 0, 0><<<(int)blocks, 256, 0, stream>>>(VL_BWD_ARGS);
   else
-    pool_lrn_bwd_kernel2<32><<<(int)blocks, 256, 0, stream>>>(
-        reinterpret_cast<const bf16*>(x), reinterpret_cast<const bf16*>(dy), reinterpret_cast<const uint8_t*>(argmax),
-        reinterpret_cast<bf16*>(dx), dbias, h, w, c, p, q, alpha, beta, bias, total_pix);
+    pool_lrn_bwd_kernel2<32, 0, 0, 0><<<(int)blocks, 256, 0, stream>>>(VL_BWD_ARGS);
+#undef VL_BWD_ARGS
   VL_LAUNCHED();
   return 0;
 }

@@ -552,6 +552,27 @@ __global__ void pack_bf16_kernel(const float* __restrict__ src, int rows, int co
   }
 }
 
+// Transposed variant: dst[col][(r/src_grp)*dst_grp + r%src_grp] = src[r][col] (K-major operand of the forward
+// convolutions: one TMA box per k-block instead of one per 64 output channels).  32x32 tiles through shared memory.
+__global__ void pack_bf16_t_kernel(const float* __restrict__ src, int rows, int cols, bf16* __restrict__ dst, int dst_ld,
+                                   int src_grp, int dst_grp) {
+  __shared__ float tile[32][33];
+  const int k0 = blockIdx.x * 32, c0 = blockIdx.y * 32;  // k = packed row index, c = column of src
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int kk = k0 + i, col = c0 + threadIdx.x;
+    const int grp = kk / dst_grp, rr = kk - grp * dst_grp;
+    const long long r = (long long)grp * src_grp + rr;
+    float v = 0.f;
+    if (kk < dst_ld && rr < src_grp && r < rows && col < cols) v = src[r * cols + col];
+    tile[i][threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int col = c0 + i, kk = k0 + threadIdx.x;
+    if (col < cols && kk < dst_ld) dst[(long long)col * dst_ld + kk] = __float2bfloat16_rn(tile[threadIdx.x][i]);
+  }
+}
+
 __global__ void cast_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long long n) {
   const long long n8 = n >> 3;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n8;
@@ -698,6 +719,16 @@ extern "C" int vl_pack_bf16(const float* src, int32_t rows, int32_t cols, void* 
   const long long total = (long long)dst_rows * dst_ld;
   pack_bf16_kernel<<<sweep_grid(total, 256), 256, 0, stream>>>(src, rows, cols, reinterpret_cast<bf16*>(dst), dst_rows,
                                                                dst_ld, src_grp, dst_grp, total);
+  VL_LAUNCHED();
+  return 0;
+}
+
+extern "C" int vl_pack_bf16_t(const float* src, int32_t rows, int32_t cols, void* dst, int32_t dst_ld, int32_t src_grp,
+                              int32_t dst_grp, vl_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  VL_REQUIRE(src && dst && src_grp > 0 && dst_grp >= src_grp && dst_ld > 0, "vl_pack_bf16_t: bad arguments");
+  dim3 grid((dst_ld + 31) / 32, (cols + 31) / 32), block(32, 8);
+  pack_bf16_t_kernel<<<grid, block, 0, stream>>>(src, rows, cols, reinterpret_cast<bf16*>(dst), dst_ld, src_grp, dst_grp);
   VL_LAUNCHED();
   return 0;
 }

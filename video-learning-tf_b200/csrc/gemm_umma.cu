@@ -1,9 +1,11 @@
 // Tensor-core contraction core for the LRCN hot path (sm_100a only).
 //
 // One persistent, warp-specialised kernel: TMA (tiled or im2col mode) stages bf16 operand tiles in
-// 128B-swizzled shared memory, a single elected thread issues tcgen05.mma (UMMA 128 x BN x 16) into
+// 128B-swizzled shared memory, one elected lane issues tcgen05.mma (UMMA 128 x BN x 16) into
 // double-buffered TMEM accumulators, four epilogue warps drain TMEM with tcgen05.ld and apply
 // bias / ReLU / ReLU-gradient mask before vectorised stores (or split-K red.add for filter gradients).
+// A CTA tile is 128*msub rows x BN columns: with msub = 2 (BN <= 128) two 128-row sub-tiles share every
+// B load and every pipeline hand-shake, which is what the narrow-N convolutions (conv1, conv2, conv5) need.
 //
 // It replaces the TensorFlow ops of the reference's hot path:
 //   tf.nn.conv2d (+ split/concat groups)   models/alexnet/alexnet.py:15-31
@@ -27,23 +29,37 @@ typedef __nv_bfloat16 bf16;
 
 constexpr int BM = 128;                     // UMMA M (cta_group::1)
 constexpr int BK = 64;                      // bf16 elements per k-block = one 128B swizzle row
-constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
+constexpr int A_SUB_BYTES = BM * BK * 2;    // 16 KB per 128-row sub-tile and k-block
 constexpr int NUM_THREADS = 192;            // warp0 TMA, warp1 MMA (+TMEM alloc), warps 2..5 epilogue
 constexpr int TMEM_COLS = 512;              // 2 accumulator stages x 256 fp32 columns
 constexpr int ACC_STRIDE_COLS = 256;
 constexpr int MAX_STAGES = 8;
+constexpr int MAX_MSUB = 2;
 constexpr int SMEM_LIMIT = 232448;          // 227 KB opt-in maximum per CTA
 constexpr int BAR_REGION = 2048;            // mbarriers + TMEM slot (256 B) + bias slice (1 KB)
+
+// Division by a runtime-invariant divisor without the ~40-instruction software divide: q = (mulhi(n, m) + n) >> s
+// (round-up method; exact for 0 <= n < 2^31).
+struct FastDiv {
+  uint32_t m, s, d;
+};
+__device__ __forceinline__ int fd_div(int n, const FastDiv& f) {
+  return (int)((__umulhi((uint32_t)n, f.m) + (uint32_t)n) >> f.s);
+}
+__device__ __forceinline__ void fd_divmod(int n, const FastDiv& f, int& q, int& r) {
+  q = fd_div(n, f);
+  r = n - q * (int)f.d;
+}
 
 struct KParams {
   int M, N;  // valid extents per group
   int groups, num_m_blk, num_n_blk, split_k, kb_total, kb_per_split, total_tiles;
-  int BN;
-  int a_mode, b_mode;
+  int BN, msub;
   int a_goff, b_goff, c_goff;
-  int b_tap_stride;
+  int b_tap_stride, b_row_goff, b_tap_inner;
   int taps, cchunks, kw, flip;
   int P, Q, PQ, stride_h, stride_w, lower_h, lower_w, cin_g;
+  FastDiv fd_nblk, fd_mblk, fd_groups, fd_cchunks, fd_kw, fd_PQ, fd_Q;
   void* C;
   int c_ld, c_dtype, c_atomic, relu;
   const float* bias;
@@ -66,27 +82,20 @@ struct TileCoord {
 
 __device__ __forceinline__ TileCoord decode_tile(const KParams& p, int tile) {
   TileCoord t;
-  t.n_blk = tile % p.num_n_blk;
-  int r = tile / p.num_n_blk;
-  t.m_blk = r % p.num_m_blk;
-  r /= p.num_m_blk;
-  t.g = r % p.groups;
-  int split = r / p.groups;
+  int r, split;
+  fd_divmod(tile, p.fd_nblk, r, t.n_blk);
+  fd_divmod(r, p.fd_mblk, r, t.m_blk);
+  fd_divmod(r, p.fd_groups, split, t.g);
   t.kb_begin = split * p.kb_per_split;
   t.kb_end = min(p.kb_total, t.kb_begin + p.kb_per_split);
   return t;
 }
 
-__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_enc, uint32_t hi) {
-  uint32_t lo = ((smem_addr >> 4) & 0x3FFFu) | (lbo_enc << 16);
-  return (static_cast<uint64_t>(hi) << 32) | lo;
-}
-
 // The producer and the MMA issuer are WARP-UNIFORM loops: all 32 lanes run the loop control on values derived
-// from blockIdx / kernel parameters (so the compiler keeps them in uniform registers) and one elected lane issues
-// the TMA / tcgen05 instructions.  A single-lane (`lane == 0`) formulation was measured at ~450 cycles of issue
-// overhead per k-block (R2UR round trips and per-instruction ELECT loops), which capped every shape at <45 % of
-// the tensor pipe; see profiles/r01_gemm_probe_v1.txt.
+// from blockIdx / kernel parameters and one elected lane issues the TMA / tcgen05 instructions.  A single-lane
+// (`lane == 0`) formulation was measured at ~450 cycles of issue overhead per k-block (R2UR round trips and
+// per-instruction ELECT loops), which capped every shape below 45 % of the tensor pipe
+// (profiles/r01_gemm_probe.txt).
 template <int AM, int BMODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
     umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -132,12 +141,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
   const int num_stages = p.num_stages;
   const int stage_bytes = p.stage_bytes;
   const int total_tiles = p.total_tiles;
+  const int msub = p.msub;
+  const int BN = p.BN;
+  const uint32_t a_tile_bytes = (uint32_t)msub * A_SUB_BYTES;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    // The loop stays free of integer divisions: the (tap, channel-chunk) and pixel coordinates advance with adds
-    // and compares only.
-    const int BN = p.BN, cchunks = p.cchunks, kw = p.kw, taps = p.taps;
+    // The k-block loop stays free of integer divisions: the (tap, channel-chunk) and pixel coordinates advance
+    // with adds and compares only; the per-tile set-up uses multiply-shift division.
+    const int cchunks = p.cchunks, kw = p.kw, taps = p.taps;
     const bool walk_taps = (AM == VL_A_IM2COL_K) || taps > 1;
     const bool ld_a = !(p.dbg & 2), ld_b = !(p.dbg & 4);
     const int mn_step_rows = p.mn_step_rows, mn_step_rem = p.mn_step_rem;
@@ -145,86 +157,91 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(p, tile);
-      const int m0 = t.m_blk * BM;
+      const int m0 = t.m_blk * BM * msub;
       const int n0 = t.n_blk * BN;
       const int a_c0 = t.g * p.a_goff;
       const int b_c0 = t.g * p.b_goff;
-      // contraction walk state (per tile: one division pair, then incremental)
+      const int b_r0 = t.g * p.b_row_goff + n0;
+      // contraction walk state (per tile, then incremental)
       int tap = 0, cc = 0, tr = 0, ts = 0;
       if (walk_taps) {
-        tap = t.kb_begin / cchunks;
-        cc = t.kb_begin - tap * cchunks;
-        tr = tap / kw;
-        ts = tap - tr * kw;
+        fd_divmod(t.kb_begin, p.fd_cchunks, tap, cc);
+        fd_divmod(tap, p.fd_kw, tr, ts);
       } else {
         cc = t.kb_begin;
       }
-      // pixel of the first row of the tile (im2col K-major) / of the first k-block (transposed im2col)
+      // im2col K-major: base pixel of the first row of each 128-row sub-tile
+      int sub_wx[MAX_MSUB] = {0, 0}, sub_wy[MAX_MSUB] = {0, 0}, sub_n[MAX_MSUB] = {0, 0};
+      // transposed im2col: current pixel of the k-block, and the (channel, tap) of up to 2*msub 64-row chunks
       int pn = 0, pp = 0, pq = 0;
-      int wx = 0, wy = 0;  // TMA base-pixel coordinates
-      int mn_tap_r0 = 0, mn_tap_s0 = 0, mn_c0 = 0, mn_tap_r1 = 0, mn_tap_s1 = 0, mn_c1 = 0;
-      int a_valid = 2;
+      int mn_c[2 * MAX_MSUB] = {0, 0, 0, 0}, mn_tr[2 * MAX_MSUB] = {0, 0, 0, 0}, mn_ts[2 * MAX_MSUB] = {0, 0, 0, 0};
+      int a_valid = 2 * msub;
       if (AM == VL_A_IM2COL_K) {
-        pn = m0 / p.PQ;
-        int rem = m0 - pn * p.PQ;
-        pp = rem / p.Q;
-        pq = rem - pp * p.Q;
-        wx = pq * p.stride_w + p.lower_w;
-        wy = pp * p.stride_h + p.lower_h;
-      } else if (AM == VL_A_IM2COL_MN) {
-        const int pix = t.kb_begin * BK;
-        pn = pix / p.PQ;
-        int rem = pix - pn * p.PQ;
-        pp = rem / p.Q;
-        pq = rem - pp * p.Q;
-        const int chunks = taps * cchunks;
-        a_valid = min(2, chunks - t.m_blk * 2);
-        {
-          const int mc = t.m_blk * 2;
-          const int tp = mc / cchunks;
-          mn_c0 = a_c0 + (mc - tp * cchunks) * BK;
-          mn_tap_r0 = tp / kw;
-          mn_tap_s0 = tp - mn_tap_r0 * kw;
+#pragma unroll
+        for (int s = 0; s < MAX_MSUB; ++s) {
+          if (s < msub) {
+            int rem, ppp, pqq;
+            fd_divmod(m0 + s * BM, p.fd_PQ, sub_n[s], rem);
+            fd_divmod(rem, p.fd_Q, ppp, pqq);
+            sub_wx[s] = pqq * p.stride_w + p.lower_w;
+            sub_wy[s] = ppp * p.stride_h + p.lower_h;
+          }
         }
-        if (a_valid > 1) {
-          const int mc = t.m_blk * 2 + 1;
-          const int tp = mc / cchunks;
-          mn_c1 = a_c0 + (mc - tp * cchunks) * BK;
-          mn_tap_r1 = tp / kw;
-          mn_tap_s1 = tp - mn_tap_r1 * kw;
+      } else if (AM == VL_A_IM2COL_MN) {
+        int rem;
+        fd_divmod(t.kb_begin * BK, p.fd_PQ, pn, rem);
+        fd_divmod(rem, p.fd_Q, pp, pq);
+        const int chunks = taps * cchunks;
+        a_valid = min(2 * msub, chunks - t.m_blk * 2 * msub);
+#pragma unroll
+        for (int j = 0; j < 2 * MAX_MSUB; ++j) {
+          if (j < a_valid) {
+            int tp, ch;
+            fd_divmod(t.m_blk * 2 * msub + j, p.fd_cchunks, tp, ch);
+            mn_c[j] = a_c0 + ch * BK;
+            fd_divmod(tp, p.fd_kw, mn_tr[j], mn_ts[j]);
+          }
         }
       }
-      const uint32_t a_bytes = !ld_a ? 0u : (AM == VL_A_IM2COL_MN ? 8192u * a_valid : (uint32_t)A_STAGE_BYTES);
+      const uint32_t a_bytes = !ld_a ? 0u : (AM == VL_A_IM2COL_MN ? 8192u * a_valid : a_tile_bytes);
       const uint32_t bytes = (ld_b ? (uint32_t)p.b_stage_bytes : 0u) + a_bytes;
       for (int kb = t.kb_begin; kb < t.kb_end; ++kb) {
         mbar_wait_u32(empty_u32 + stage * 8, phase ^ 1u);
         const uint32_t sA = tiles_u32 + stage * stage_bytes;
-        const uint32_t sB = sA + A_STAGE_BYTES;
+        const uint32_t sB = sA + a_tile_bytes;
         const uint32_t fb = full_u32 + stage * 8;
         if (elect_one()) {
           mbar_expect_tx_u32(fb, bytes);
           // ---- A ----
           if (ld_a) {
             if (AM == VL_A_TILED_K) {
-              tma_load_2d_u32(sA, &tmA, fb, a_c0 + kb * BK, m0);
+#pragma unroll
+              for (int s = 0; s < MAX_MSUB; ++s)
+                if (s < msub) tma_load_2d_u32(sA + s * A_SUB_BYTES, &tmA, fb, a_c0 + kb * BK, m0 + s * BM);
             } else if (AM == VL_A_TILED_MN) {
-              tma_load_2d_u32(sA, &tmA, fb, a_c0 + m0, kb * BK);
-              tma_load_2d_u32(sA + 8192, &tmA, fb, a_c0 + m0 + 64, kb * BK);
+#pragma unroll
+              for (int j = 0; j < 2 * MAX_MSUB; ++j)
+                if (j < 2 * msub) tma_load_2d_u32(sA + j * 8192, &tmA, fb, a_c0 + m0 + j * 64, kb * BK);
             } else if (AM == VL_A_IM2COL_K) {
-              tma_load_im2col_4d_u32(sA, &tmA, fb, a_c0 + cc * BK, wx, wy, pn, (uint16_t)ts, (uint16_t)tr);
+#pragma unroll
+              for (int s = 0; s < MAX_MSUB; ++s)
+                if (s < msub)
+                  tma_load_im2col_4d_u32(sA + s * A_SUB_BYTES, &tmA, fb, a_c0 + cc * BK, sub_wx[s], sub_wy[s], sub_n[s],
+                                         (uint16_t)ts, (uint16_t)tr);
             } else {  // VL_A_IM2COL_MN: this k-block's 64 pixels start at (pn, pp, pq)
               const int bx = pq * p.stride_w + p.lower_w, by = pp * p.stride_h + p.lower_h;
-              tma_load_im2col_4d_u32(sA, &tmA, fb, mn_c0, bx, by, pn, (uint16_t)mn_tap_s0, (uint16_t)mn_tap_r0);
-              if (a_valid > 1)
-                tma_load_im2col_4d_u32(sA + 8192, &tmA, fb, mn_c1, bx, by, pn, (uint16_t)mn_tap_s1,
-                                       (uint16_t)mn_tap_r1);
+#pragma unroll
+              for (int j = 0; j < 2 * MAX_MSUB; ++j)
+                if (j < a_valid)
+                  tma_load_im2col_4d_u32(sA + j * 8192, &tmA, fb, mn_c[j], bx, by, pn, (uint16_t)mn_ts[j],
+                                         (uint16_t)mn_tr[j]);
             }
           }
           // ---- B ----
           if (ld_b) {
             if (BMODE == VL_B_TILED_K) {
               const int tapb = p.flip ? (taps - 1 - tap) : tap;
-              tma_load_2d_u32(sB, &tmB, fb, b_c0 + cc * BK, n0 + tapb * p.b_tap_stride);
+              tma_load_2d_u32(sB, &tmB, fb, b_c0 + tap * p.b_tap_inner + cc * BK, b_r0 + tapb * p.b_tap_stride);
             } else {
               for (int j = 0; j < BN; j += 64) tma_load_2d_u32(sB + j * 128, &tmB, fb, b_c0 + n0 + j, kb * BK);
             }
@@ -285,17 +302,25 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
         tc_fence_after();
         const uint32_t sA = tiles_u32 + stage * stage_bytes;
         const uint64_t adesc = a_hi | ((sA >> 4) & 0x3FFFu);
-        const uint64_t bdesc = b_hi | (((sA + A_STAGE_BYTES) >> 4) & 0x3FFFu);
+        const uint64_t bdesc = b_hi | (((sA + a_tile_bytes) >> 4) & 0x3FFFu);
         if (elect_one()) {
           if (do_mma) {
             if (!tail || ksteps_tail == BK / 16) {
 #pragma unroll
-              for (int k = 0; k < BK / 16; ++k)
-                umma_bf16(tmem_d, adesc + k * a_kstep, bdesc + k * b_kstep, idesc, accumulate | (uint32_t)k);
+              for (int s = 0; s < MAX_MSUB; ++s) {
+                if (s < msub) {
+#pragma unroll
+                  for (int k = 0; k < BK / 16; ++k)
+                    umma_bf16(tmem_d + s * BN, adesc + s * (A_SUB_BYTES >> 4) + k * a_kstep, bdesc + k * b_kstep, idesc,
+                              accumulate | (uint32_t)k);
+                }
+              }
             } else {
               // zero-padded K-steps of the last channel chunk (cin_g = 48 -> 3 of 4) are not issued at all
-              for (int k = 0; k < ksteps_tail; ++k)
-                umma_bf16(tmem_d, adesc + k * a_kstep, bdesc + k * b_kstep, idesc, accumulate | (uint32_t)k);
+              for (int s = 0; s < msub; ++s)
+                for (int k = 0; k < ksteps_tail; ++k)
+                  umma_bf16(tmem_d + s * BN, adesc + s * (A_SUB_BYTES >> 4) + k * a_kstep, bdesc + k * b_kstep, idesc,
+                            accumulate | (uint32_t)k);
             }
           }
           umma_commit_u32(empty_u32 + stage * 8);  // frees the smem slot once the MMAs have read it
@@ -315,125 +340,127 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
     const int epi_tid = threadIdx.x - 64;
     int local = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++local) {
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
       const TileCoord t = decode_tile(p, tile);
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
-      const int m0 = t.m_blk * BM;
-      const int n0 = t.n_blk * p.BN;
+      const int m0 = t.m_blk * BM * msub;
+      const int n0 = t.n_blk * BN;
       const int row_in_tile = quad * 32 + lane;
-      long long grow;
-      bool row_ok;
-      if (AM == VL_A_IM2COL_MN) {
-        int mc = t.m_blk * 2 + (row_in_tile >> 6);
-        int tap = mc / p.cchunks;
-        int cc = mc - tap * p.cchunks;
-        int ci = cc * 64 + (row_in_tile & 63);
-        row_ok = (mc < p.taps * p.cchunks) && (ci < p.cin_g);
-        grow = (long long)tap * p.cin_g + ci;
-      } else {
-        grow = m0 + row_in_tile;
-        row_ok = grow < p.M;
-      }
       const int gcol0 = t.g * p.c_goff + n0;  // global column of tile column 0
       // stage this tile's bias slice in shared memory once (instead of one global load per element)
       if (p.bias != nullptr) {
         asm volatile("bar.sync 1, 128;" ::: "memory");  // previous tile's readers are done
-        for (int j = epi_tid; j < p.BN; j += 128) sbias[j] = (n0 + j < p.N) ? __ldg(p.bias + gcol0 + j) : 0.f;
+        for (int j = epi_tid; j < BN; j += 128) sbias[j] = (n0 + j < p.N) ? __ldg(p.bias + gcol0 + j) : 0.f;
         asm volatile("bar.sync 1, 128;" ::: "memory");
       }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + acc * ACC_STRIDE_COLS;
       const bool vec_ok = (p.c_ld % 8 == 0) && (gcol0 % 8 == 0) && !p.c_atomic &&
                           (p.mask == nullptr || p.mask_ld % 8 == 0);
-
-      auto process = [&](const uint32_t (&v)[16], int c0) {
-        if (!row_ok || (p.dbg & 8)) return;
-        const int ncols = min(16, p.N - (n0 + c0));
-        if (ncols <= 0) return;
-        float f[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
-        if (p.bias != nullptr) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float4 bv = *reinterpret_cast<const float4*>(sbias + c0 + 4 * j);
-            f[4 * j] += bv.x;
-            f[4 * j + 1] += bv.y;
-            f[4 * j + 2] += bv.z;
-            f[4 * j + 3] += bv.w;
-          }
-        }
-        if (p.relu) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.0f);
-        }
-        if (p.mask != nullptr) {
-          const bf16* mrow = p.mask + grow * p.mask_ld + gcol0 + c0;
-          if (vec_ok && ncols == 16) {
-            uint4 m0v = *reinterpret_cast<const uint4*>(mrow);
-            uint4 m1v = *reinterpret_cast<const uint4*>(mrow + 8);
-            const bf16* mv0 = reinterpret_cast<const bf16*>(&m0v);
-            const bf16* mv1 = reinterpret_cast<const bf16*>(&m1v);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              if (!(__bfloat162float(mv0[j]) > 0.0f)) f[j] = 0.0f;
-              if (!(__bfloat162float(mv1[j]) > 0.0f)) f[8 + j] = 0.0f;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (j < ncols && !(__bfloat162float(mrow[j]) > 0.0f)) f[j] = 0.0f;
-          }
-        }
-        const long long off = grow * p.c_ld + gcol0 + c0;
-        if (p.c_dtype == VL_DT_BF16) {
-          bf16* out = reinterpret_cast<bf16*>(p.C) + off;
-          if (vec_ok && ncols == 16) {
-            uint32_t w[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
-              w[j] = *reinterpret_cast<uint32_t*>(&h);
-            }
-            *reinterpret_cast<uint4*>(out) = make_uint4(w[0], w[1], w[2], w[3]);
-            *reinterpret_cast<uint4*>(out + 8) = make_uint4(w[4], w[5], w[6], w[7]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (j < ncols) out[j] = __float2bfloat16_rn(f[j]);
-          }
+      for (int sub = 0; sub < msub; ++sub) {
+        long long grow;
+        bool row_ok;
+        if (AM == VL_A_IM2COL_MN) {
+          const int mc = (t.m_blk * msub + sub) * 2 + (row_in_tile >> 6);
+          int tap, cc;
+          fd_divmod(mc, p.fd_cchunks, tap, cc);
+          const int ci = cc * 64 + (row_in_tile & 63);
+          row_ok = (mc < p.taps * p.cchunks) && (ci < p.cin_g);
+          grow = (long long)tap * p.cin_g + ci;
         } else {
-          float* out = reinterpret_cast<float*>(p.C) + off;
-          if (p.c_atomic) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (j < ncols) atomicAdd(out + j, f[j]);
-          } else if (vec_ok && ncols == 16) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              *reinterpret_cast<float4*>(out + 4 * j) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (j < ncols) out[j] = f[j];
-          }
+          grow = m0 + sub * BM + row_in_tile;
+          row_ok = grow < p.M;
         }
-      };
+        const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + acc * ACC_STRIDE_COLS + sub * BN;
 
-      // software pipelined TMEM drain: the load of chunk i+1 is in flight while chunk i is processed
-      uint32_t va[16], vb[16];
-      tmem_ld_x16(taddr, va);
-      for (int c0 = 0; c0 < p.BN; c0 += 32) {
-        tmem_ld_wait();
-        const bool has_b = c0 + 16 < p.BN;
-        if (has_b) tmem_ld_x16(taddr + c0 + 16, vb);
-        process(va, c0);
-        if (has_b) {
+        auto process = [&](const uint32_t (&v)[16], int c0) {
+          if (!row_ok || (p.dbg & 8)) return;
+          const int ncols = min(16, p.N - (n0 + c0));
+          if (ncols <= 0) return;
+          float f[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 bv = *reinterpret_cast<const float4*>(sbias + c0 + 4 * j);
+              f[4 * j] += bv.x;
+              f[4 * j + 1] += bv.y;
+              f[4 * j + 2] += bv.z;
+              f[4 * j + 3] += bv.w;
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.0f);
+          }
+          if (p.mask != nullptr) {
+            const bf16* mrow = p.mask + grow * p.mask_ld + gcol0 + c0;
+            if (vec_ok && ncols == 16) {
+              uint4 m0v = *reinterpret_cast<const uint4*>(mrow);
+              uint4 m1v = *reinterpret_cast<const uint4*>(mrow + 8);
+              const bf16* mv0 = reinterpret_cast<const bf16*>(&m0v);
+              const bf16* mv1 = reinterpret_cast<const bf16*>(&m1v);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                if (!(__bfloat162float(mv0[j]) > 0.0f)) f[j] = 0.0f;
+                if (!(__bfloat162float(mv1[j]) > 0.0f)) f[8 + j] = 0.0f;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (j < ncols && !(__bfloat162float(mrow[j]) > 0.0f)) f[j] = 0.0f;
+            }
+          }
+          const long long off = grow * p.c_ld + gcol0 + c0;
+          if (p.c_dtype == VL_DT_BF16) {
+            bf16* out = reinterpret_cast<bf16*>(p.C) + off;
+            if (vec_ok && ncols == 16) {
+              uint32_t w[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+                w[j] = *reinterpret_cast<uint32_t*>(&h);
+              }
+              *reinterpret_cast<uint4*>(out) = make_uint4(w[0], w[1], w[2], w[3]);
+              *reinterpret_cast<uint4*>(out + 8) = make_uint4(w[4], w[5], w[6], w[7]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (j < ncols) out[j] = __float2bfloat16_rn(f[j]);
+            }
+          } else {
+            float* out = reinterpret_cast<float*>(p.C) + off;
+            if (p.c_atomic) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (j < ncols) atomicAdd(out + j, f[j]);
+            } else if (vec_ok && ncols == 16) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                *reinterpret_cast<float4*>(out + 4 * j) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (j < ncols) out[j] = f[j];
+            }
+          }
+        };
+
+        // software pipelined TMEM drain: the load of chunk i+1 is in flight while chunk i is processed
+        uint32_t va[16], vb[16];
+        tmem_ld_x16(taddr, va);
+        for (int c0 = 0; c0 < BN; c0 += 32) {
           tmem_ld_wait();
-          if (c0 + 32 < p.BN) tmem_ld_x16(taddr + c0 + 32, va);
-          process(vb, c0 + 16);
+          const bool has_b = c0 + 16 < BN;
+          if (has_b) tmem_ld_x16(taddr + c0 + 16, vb);
+          process(va, c0);
+          if (has_b) {
+            tmem_ld_wait();
+            if (c0 + 32 < BN) tmem_ld_x16(taddr + c0 + 32, va);
+            process(vb, c0 + 16);
+          }
         }
       }
       tc_fence_before();
@@ -497,10 +524,10 @@ int make_tiled_map(CUtensorMap* m, const void* base, long long inner, long long 
 }
 
 // NHWC bf16 tensor seen as (C, W, H, N); im2col boxes of `pixels` x 64 channels, 128B swizzle.
-int make_im2col_map(CUtensorMap* m, const void* base, const vl_conv_geom& g, int pixels) {
+int make_im2col_map(CUtensorMap* m, const void* base, const vl_conv_geom& g, int pixels, int c_dim) {
   VL_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base pointer must be 16B aligned");
   VL_REQUIRE(g.c % 8 == 0, "im2col TMA needs a channel count that is a multiple of 8 (c=%d)", g.c);
-  cuuint64_t dims[4] = {(cuuint64_t)g.c, (cuuint64_t)g.w, (cuuint64_t)g.h, (cuuint64_t)g.n};
+  cuuint64_t dims[4] = {(cuuint64_t)c_dim, (cuuint64_t)g.w, (cuuint64_t)g.h, (cuuint64_t)g.n};
   cuuint64_t strides[3] = {(cuuint64_t)g.c * 2, (cuuint64_t)g.c * g.w * 2, (cuuint64_t)g.c * g.w * g.h * 2};
   // TF SAME/VALID geometry: base pixel of output (p,q) is (p*stride - pad_top, q*stride - pad_left); the upper
   // corner bounds the last base pixel so that exactly P x Q positions are traversed per image.
@@ -518,6 +545,17 @@ int make_im2col_map(CUtensorMap* m, const void* base, const vl_conv_geom& g, int
 }
 
 int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+FastDiv make_fastdiv(int d) {
+  FastDiv f;
+  if (d < 1) d = 1;
+  f.d = (uint32_t)d;
+  uint32_t l = 0;
+  while ((1u << l) < (uint32_t)d) ++l;
+  f.s = l;
+  f.m = (uint32_t)(((1ull << 32) * ((1ull << l) - (uint64_t)d)) / (uint64_t)d + 1ull);
+  return f;
+}
 
 }  // namespace
 
@@ -537,12 +575,12 @@ extern "C" int vl_gemm(const vl_gemm_desc* d, const void* a, const void* b, void
   const vl_conv_geom& cg = d->conv;
 
   p.groups = d->groups;
-  p.a_mode = d->a_mode;
-  p.b_mode = d->b_mode;
   p.a_goff = d->a_goff;
   p.b_goff = d->b_goff;
   p.c_goff = d->c_goff;
   p.b_tap_stride = d->b_tap_stride;
+  p.b_row_goff = d->b_row_goff;
+  p.b_tap_inner = d->b_tap_inner;
   p.taps = 1;
   p.kw = 1;
   p.flip = 0;
@@ -576,25 +614,32 @@ extern "C" int vl_gemm(const vl_gemm_desc* d, const void* a, const void* b, void
     p.lower_w = -cg.pad_left;
     p.cin_g = cg.cin_g;
   }
+  int m_rows;  // rows of the (per group) output as tiled by 128-row sub-tiles
   if (d->a_mode == VL_A_IM2COL_K) {
     p.M = cg.n * cg.p * cg.q;
     VL_REQUIRE(d->m == p.M, "vl_gemm: m (%d) must equal n*p*q (%d) for im2col A", d->m, p.M);
     p.kb_total = p.taps * p.cchunks;
-    p.num_m_blk = ceil_div(p.M, BM);
+    m_rows = p.M;
   } else if (d->a_mode == VL_A_IM2COL_MN) {
     // M axis = (tap, 64-channel chunk); K axis = output pixels.
     p.M = p.taps * cg.cin_g;
     VL_REQUIRE(d->k == cg.n * cg.p * cg.q, "vl_gemm: k (%d) must equal n*p*q for transposed im2col A", d->k);
     p.kb_total = ceil_div(d->k, BK);
-    p.num_m_blk = ceil_div(p.taps * p.cchunks, 2);
+    m_rows = p.taps * p.cchunks * 64;
   } else {
     p.M = d->m;
     p.kb_total = ceil_div(d->k, BK);
-    p.num_m_blk = ceil_div(p.M, BM);
-    if (d->b_mode == VL_B_TILED_K && d->b_tap_stride > 0) {
-      VL_REQUIRE(false, "vl_gemm: b_tap_stride needs an im2col A operand");
-    }
+    m_rows = p.M;
+    VL_REQUIRE(!(d->b_mode == VL_B_TILED_K && (d->b_tap_stride > 0 || d->b_tap_inner > 0)),
+               "vl_gemm: b_tap_stride / b_tap_inner need an im2col A operand");
   }
+  // two 128-row sub-tiles per CTA tile when the accumulators fit (2 * BN <= 256 TMEM columns per stage) and there
+  // are enough rows to keep every SM busy with the halved tile count
+  p.msub = 1;
+  if (d->msub == 2 || (d->msub == 0 && 2 * BN <= ACC_STRIDE_COLS && ceil_div(m_rows, BM) >= 4)) p.msub = 2;
+  VL_REQUIRE(p.msub * BN <= ACC_STRIDE_COLS, "vl_gemm: msub %d x block_n %d exceeds the TMEM accumulator stage", p.msub,
+             BN);
+  p.num_m_blk = ceil_div(m_rows, BM * p.msub);
   if (!a_im2col) p.cchunks = p.kb_total;  // dense k-block walk: tap = 0, cc = kb
   p.ksteps_tail = BK / 16;
   p.mma_cchunks = p.cchunks;
@@ -611,12 +656,30 @@ extern "C" int vl_gemm(const vl_gemm_desc* d, const void* a, const void* b, void
   VL_REQUIRE(!(d->a_mode == VL_A_IM2COL_MN && d->b_mode == VL_B_TILED_K),
              "vl_gemm: transposed im2col A requires an N-major B");
   p.num_n_blk = ceil_div(d->n, BN);
-  p.split_k = d->split_k < 1 ? 1 : d->split_k;
+  const int out_tiles = p.num_m_blk * p.num_n_blk * p.groups;
+  p.split_k = d->split_k;
+  if (p.split_k == 0) {
+    // automatic split-K for the atomic (filter gradient) epilogue: about two waves of CTAs, >= 4 k-blocks each
+    p.split_k = 1;
+    if (d->c_atomic && d->c_dtype == VL_DT_F32) {
+      int want = (2 * vl::num_sms()) / (out_tiles > 0 ? out_tiles : 1);
+      int cap = p.kb_total >= 8 ? p.kb_total / 4 : 1;
+      p.split_k = want < 1 ? 1 : (want > cap ? cap : want);
+    }
+  }
+  if (p.split_k < 1) p.split_k = 1;
   if (p.split_k > p.kb_total) p.split_k = p.kb_total;
   p.kb_per_split = ceil_div(p.kb_total, p.split_k);
   p.split_k = ceil_div(p.kb_total, p.kb_per_split);  // no empty splits
   VL_REQUIRE(p.split_k == 1 || (d->c_atomic && d->c_dtype == VL_DT_F32), "vl_gemm: split_k needs fp32 atomic output");
-  p.total_tiles = p.num_m_blk * p.num_n_blk * p.groups * p.split_k;
+  p.total_tiles = out_tiles * p.split_k;
+  p.fd_nblk = make_fastdiv(p.num_n_blk);
+  p.fd_mblk = make_fastdiv(p.num_m_blk);
+  p.fd_groups = make_fastdiv(p.groups);
+  p.fd_cchunks = make_fastdiv(p.cchunks);
+  p.fd_kw = make_fastdiv(p.kw);
+  p.fd_PQ = make_fastdiv(p.PQ);
+  p.fd_Q = make_fastdiv(p.Q);
 
   {
     const char* e = getenv("VL_GEMM_DBG");
@@ -635,7 +698,7 @@ extern "C" int vl_gemm(const vl_gemm_desc* d, const void* a, const void* b, void
 
   // ---- smem pipeline ----
   p.b_stage_bytes = BN * 128;
-  p.stage_bytes = A_STAGE_BYTES + ((p.b_stage_bytes + 1023) / 1024) * 1024;
+  p.stage_bytes = p.msub * A_SUB_BYTES + ((p.b_stage_bytes + 1023) / 1024) * 1024;
   int stages = (SMEM_LIMIT - 1024 - BAR_REGION) / p.stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   VL_REQUIRE(stages >= 2, "vl_gemm: not enough shared memory for 2 stages");
@@ -664,18 +727,19 @@ extern "C" int vl_gemm(const vl_gemm_desc* d, const void* a, const void* b, void
     long long inner = (long long)d->a_goff * (d->groups - 1) + d->m;
     if (make_tiled_map(&tmA, a, inner, d->k, d->a_ld, 64, 64) != 0) return -1;
   } else {
-    if (make_im2col_map(&tmA, a, cg, d->a_mode == VL_A_IM2COL_K ? BM : 64) != 0) return -1;
+    if (make_im2col_map(&tmA, a, cg, d->a_mode == VL_A_IM2COL_K ? BM : 64, cg.c) != 0) return -1;
   }
   if (d->b_mode == VL_B_TILED_K) {
-    // rows = n (x taps for conv data-gradients), inner = contraction (+ group offsets)
+    // rows = n (x taps for conv data-gradients, x groups for K-major forward filters), inner = contraction
     long long inner, outer;
     if (d->a_mode == VL_A_IM2COL_K) {
-      inner = (long long)d->b_goff * (d->groups - 1) + (long long)p.cchunks * 64;
-      outer = (long long)p.taps * (d->b_tap_stride > 0 ? d->b_tap_stride : d->n);
-      if (d->b_tap_stride == 0) p.b_tap_stride = d->n;
+      const long long per_tap = d->b_tap_inner > 0 ? (long long)p.taps * d->b_tap_inner : cg.cin_g;
+      inner = (long long)d->b_goff * (d->groups - 1) + per_tap;
+      outer = (long long)d->b_row_goff * (d->groups - 1) +
+              (d->b_tap_stride > 0 ? (long long)p.taps * d->b_tap_stride : d->n);
     } else {
       inner = (long long)d->b_goff * (d->groups - 1) + d->k;
-      outer = d->n;
+      outer = (long long)d->b_row_goff * (d->groups - 1) + d->n;
     }
     if (make_tiled_map(&tmB, b, inner, outer, d->b_ld, 64, BN) != 0) return -1;
   } else {

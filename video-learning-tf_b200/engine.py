@@ -221,12 +221,11 @@ class Engine(object):
         cfg, sp, dev = self.cfg, self.sp, self.dev
         sh = {}
         s1s = sp["conv1_s2d"]
-        sh["conv1"] = torch.zeros(s1s.k_packed, 96, dtype=BF16, device=dev)
+        sh["conv1_fwd"] = torch.zeros(96, s1s.k_packed, dtype=BF16, device=dev)  # K-major
         for name in ("conv2", "conv3", "conv4", "conv5"):
             s = sp[name]
-            sh[name] = torch.zeros(s.taps * s.cin_g, s.cout, dtype=BF16, device=dev)  # HWIO as 2D
-            if s.cin_g % 64 != 0:
-                sh[name + "_packed"] = torch.zeros(s.k_packed, s.cout, dtype=BF16, device=dev)
+            sh[name] = torch.zeros(s.taps * s.cin_g, s.cout, dtype=BF16, device=dev)  # HWIO as 2D (data gradient)
+            sh[name + "_fwd"] = torch.zeros(s.cout, s.k_packed, dtype=BF16, device=dev)  # K-major, taps padded to 64
         sh["fc6"] = torch.zeros(sp["flat"], 4096, dtype=BF16, device=dev)
         names = dict(self.var_shapes)
         if "dcnn/fc7W" in names:
@@ -247,15 +246,14 @@ class Engine(object):
         """fp32 master -> bf16 tensor-core operands (after load and after every optimiser step)."""
         sh, sp = self.sh, self.sp
         s1 = sp["conv1"]
-        nv.call("vl_s2d_pack_filter", self.var("dcnn/conv1W"), sh["conv1"], s1.kh, s1.kw, 3, 96, s1.stride,
-                sp["conv1_s2d"].cchunks * 64)
+        nv.call("vl_s2d_pack_filter", self.var("dcnn/conv1W"), sh["conv1_fwd"], s1.kh, s1.kw, 3, 96, s1.stride,
+                sp["conv1_s2d"].cchunks * 64, 1)
         for name in ("conv2", "conv3", "conv4", "conv5"):
             s = sp[name]
             w = self.var2d("dcnn/%sW" % name)
             nv.call("vl_cast_f32_to_bf16", w, sh[name], w.numel())
-            if name + "_packed" in sh:
-                nv.call("vl_pack_bf16", w, s.taps * s.cin_g, s.cout, sh[name + "_packed"], s.k_packed, s.cout,
-                        s.cin_g, s.cchunks * 64)
+            nv.call("vl_pack_bf16_t", w, s.taps * s.cin_g, s.cout, sh[name + "_fwd"], s.k_packed, s.cin_g,
+                    s.cchunks * 64)
         for name in ("fc6", "fc7"):
             if name in sh:
                 w = self.var("dcnn/%sW" % name)
@@ -408,16 +406,16 @@ class Engine(object):
         nv.call("vl_frames_s2d", frames, 1 if is_u8 else 0, self._mean_dev(), xs, n, self.cfg.height, self.cfg.width,
                 s1.stride, s1.pad_top, s1.pad_left, s1s.h, s1s.w)
         a1 = A["a1"][:n]
-        K.conv_fwd(s1s, xs, sh["conv1"], self.var("dcnn/conv1b"), a1, relu=True)
+        K.conv_fwd(s1s, xs, sh["conv1_fwd"], self.var("dcnn/conv1b"), a1, relu=True)
         nv.call("vl_lrn_pool_fwd", a1, A["p1"][:n], A["arg1"][:n], n, s1.p, s1.q, 96, LRN["radius"], LRN["alpha"],
                 LRN["beta"], LRN["bias"])
         s2 = sp["conv2"]
-        K.conv_fwd(s2, A["p1"][:n], sh["conv2_packed"], self.var("dcnn/conv2b"), A["a2"][:n], relu=True)
+        K.conv_fwd(s2, A["p1"][:n], sh["conv2_fwd"], self.var("dcnn/conv2b"), A["a2"][:n], relu=True)
         nv.call("vl_lrn_pool_fwd", A["a2"][:n], A["p2"][:n], A["arg2"][:n], n, s2.p, s2.q, 256, LRN["radius"],
                 LRN["alpha"], LRN["beta"], LRN["bias"])
-        K.conv_fwd(sp["conv3"], A["p2"][:n], sh["conv3"], self.var("dcnn/conv3b"), A["a3"][:n], relu=True)
-        K.conv_fwd(sp["conv4"], A["a3"][:n], sh["conv4"], self.var("dcnn/conv4b"), A["a4"][:n], relu=True)
-        K.conv_fwd(sp["conv5"], A["a4"][:n], sh["conv5"], self.var("dcnn/conv5b"), A["a5"][:n], relu=True)
+        K.conv_fwd(sp["conv3"], A["p2"][:n], sh["conv3_fwd"], self.var("dcnn/conv3b"), A["a3"][:n], relu=True)
+        K.conv_fwd(sp["conv4"], A["a3"][:n], sh["conv4_fwd"], self.var("dcnn/conv4b"), A["a4"][:n], relu=True)
+        K.conv_fwd(sp["conv5"], A["a4"][:n], sh["conv5_fwd"], self.var("dcnn/conv5b"), A["a5"][:n], relu=True)
         s3 = sp["conv3"]
         nv.call("vl_maxpool_fwd", A["a5"][:n], A["p5"][:n], A["arg5"][:n], n, s3.p, s3.q, 256)
         flat = A["p5"][:n].view(n, sp["flat"])  # HWC-major flatten (alexnet.py:228)
@@ -503,7 +501,7 @@ class Engine(object):
         s = self.sp[name]
         n = x.shape[0]
         dw = self.var2d("dcnn/%sW" % name, self.grads)
-        K.conv_wgrad(s, x, dy, dw, split_k=self._split_k(s.taps * s.cchunks * 64, s.cout_g, n * s.p * s.q, s.groups))
+        K.conv_wgrad(s, x, dy, dw)  # split-K chosen by the library
         if not bias_done:
             nv.call("vl_colsum", dy, self.var("dcnn/%sb" % name, self.grads), n * s.p * s.q, s.cout, s.cout)
         if dx is not None:
@@ -582,8 +580,7 @@ class Engine(object):
                 self.var("dcnn/conv1b", self.grads), n, s1.p, s1.q, 96, LRN["radius"], LRN["alpha"], LRN["beta"],
                 LRN["bias"])
         s1s = sp["conv1_s2d"]
-        K.conv_wgrad(s1s, A["x_s2d"][:n], G["da1"][:n], self.dws1,
-                     split_k=self._split_k(s1s.taps * s1s.cchunks * 64, s1s.cout_g, n * s1s.p * s1s.q, 1))
+        K.conv_wgrad(s1s, A["x_s2d"][:n], G["da1"][:n], self.dws1)
         nv.call("vl_s2d_unpack_grad", self.dws1, self.var("dcnn/conv1W", self.grads), s1.kh, s1.kw, 3, 96, s1.stride)
 
     # ------------------------------------------------------------------------------------------

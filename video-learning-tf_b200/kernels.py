@@ -138,25 +138,29 @@ def linear_wgrad(x, dy, dw, split_k=1, n=None, block_n=0):
 # ----------------------------------------------------------------------------------------------------
 # convolutions: dcnn.conv (alexnet.py:15-31) and its gradients
 # ----------------------------------------------------------------------------------------------------
-def conv_fwd(spec, x, w_packed, bias, out, relu=True, block_n=0):
-    """out[N,P,Q,Cout] = act(conv2d_SAME(x[N,H,W,Cin], W) + bias); w_packed = bf16 [taps*cchunks*64, Cout]."""
+def conv_fwd(spec, x, w_kmajor, bias, out, relu=True, block_n=0, msub=0):
+    """out[N,P,Q,Cout] = act(conv2d(x[N,H,W,Cin], W) + bias); w_kmajor = bf16 [Cout, taps*cchunks*64] (K-major:
+    row = output channel, each tap's cin_g filter rows zero-padded to a multiple of 64)."""
     n = x.shape[0]
     d = nv.GemmDesc()
     d.m, d.n, d.k, d.groups = n * spec.p * spec.q, spec.cout_g, spec.k_packed, spec.groups
-    d.a_mode, d.b_mode = nv.A_IM2COL_K, nv.B_TILED_MN
-    d.a_goff, d.b_goff, d.c_goff = spec.cin_g, spec.cout_g, spec.cout_g
-    d.b_ld = spec.cout
+    d.a_mode, d.b_mode = nv.A_IM2COL_K, nv.B_TILED_K
+    d.a_goff, d.b_goff, d.c_goff = spec.cin_g, 0, spec.cout_g
+    d.b_row_goff = spec.cout_g
+    d.b_tap_inner = spec.cchunks * 64
+    d.b_ld = spec.k_packed
     d.c_ld = spec.cout
     d.c_dtype = nv.DT_BF16 if out.dtype == BF16 else nv.DT_F32
     d.relu = 1 if relu else 0
     d.split_k = 1
     d.block_n = block_n
+    d.msub = msub
     d.conv = spec.geom(n)
-    nv.gemm(d, x, w_packed, out, bias)
+    nv.gemm(d, x, w_kmajor, out, bias)
     return out
 
 
-def conv_dgrad(spec, dy, w_hwio, dx, relu_mask=None, block_n=0):
+def conv_dgrad(spec, dy, w_hwio, dx, relu_mask=None, block_n=0, msub=0):
     """dx[N,H,W,Cin] = conv2d_backprop_input(dy[N,P,Q,Cout], W); w_hwio = bf16 [taps*cin_g, Cout] (HWIO as 2D)."""
     n = dy.shape[0]
     d = nv.GemmDesc()
@@ -169,6 +173,7 @@ def conv_dgrad(spec, dy, w_hwio, dx, relu_mask=None, block_n=0):
     d.c_dtype = nv.DT_BF16 if dx.dtype == BF16 else nv.DT_F32
     d.split_k = 1
     d.block_n = block_n
+    d.msub = msub
     d.conv = spec.geom_dgrad(n)
     if relu_mask is not None:
         d.mask_ld = spec.cin
@@ -176,7 +181,7 @@ def conv_dgrad(spec, dy, w_hwio, dx, relu_mask=None, block_n=0):
     return dx
 
 
-def conv_wgrad(spec, x, dy, dw, split_k=1, block_n=0):
+def conv_wgrad(spec, x, dy, dw, split_k=0, block_n=0, msub=0):
     """dw[taps*cin_g, Cout] (fp32, HWIO as 2D) += conv2d_backprop_filter(x, dy); split-K over output pixels."""
     n = x.shape[0]
     d = nv.GemmDesc()
@@ -189,6 +194,7 @@ def conv_wgrad(spec, x, dy, dw, split_k=1, block_n=0):
     d.c_atomic = 1
     d.split_k = split_k
     d.block_n = block_n
+    d.msub = msub
     d.conv = spec.geom(n)
     assert dw.dtype == F32
     nv.gemm(d, x, dy, dw)
@@ -196,9 +202,10 @@ def conv_wgrad(spec, x, dy, dw, split_k=1, block_n=0):
 
 
 def pack_conv_weight_host(spec, w_hwio):
-    """HWIO fp32 -> bf16 [taps*cchunks*64, Cout] with each tap's cin_g rows zero-padded to a 64 multiple."""
+    """HWIO fp32 -> K-major bf16 [Cout, taps*cchunks*64] with each tap's cin_g rows zero-padded to a 64 multiple
+    (torch restatement of vl_pack_bf16_t, for tests and probes)."""
     kh, kw, cin_g, cout = w_hwio.shape
     w = w_hwio.reshape(kh * kw, cin_g, cout)
     packed = torch.zeros(kh * kw, spec.cchunks * 64, cout, dtype=BF16, device=w_hwio.device)
     packed[:, :cin_g, :] = w.to(BF16)
-    return packed.reshape(spec.k_packed, cout).contiguous()
+    return packed.reshape(spec.k_packed, cout).t().contiguous()
