@@ -212,10 +212,36 @@ def run_ours(args):
     ms_step = ms_total / args.steps
     value = world * CLIPS_PER_GPU / (ms_step * 1e-3)
 
-    # ---- end to end from host buffers (pinned staging + H2D inside the timed region, D2H of the step scalars) ----
-    e2e_steps = max(2, args.steps // 2)
-    ms_e2e = timed(lambda i: eng.train_step(frames_host, onehot_host, lr_table_value(eng.global_step)),
-                   e2e_steps, 2) / e2e_steps
+    # ---- end to end from host buffers: every step copies its uint8 frames + int32 labels from PINNED host memory
+    # (H2D inside the timed region, double buffered on a copy stream so that the copy of step i+1 overlaps the
+    # compute of step i) and reads the step scalars back (D2H, the step's only synchronisation) ----
+    pin_frames = torch.from_numpy(frames_host).pin_memory()
+    pin_onehot = torch.from_numpy(onehot_host).pin_memory()
+
+    def e2e_loop(nsteps):
+        nxt = eng.prefetch(pin_frames, pin_onehot, 0)
+        for i in range(nsteps):
+            fd, od, ev, done = nxt
+            if i + 1 < nsteps:
+                nxt = eng.prefetch(pin_frames, pin_onehot, (i + 1) % 2)
+            torch.cuda.current_stream().wait_event(ev)
+            eng.train_step(fd, od, lr_table_value(eng.global_step))
+            done.record()
+
+    e2e_steps = max(2, args.steps)
+    e2e_loop(2)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    e2e_loop(e2e_steps)
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms_e2e], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e2e = float(t.item())
+    ms_e2e /= e2e_steps
     e2e_value = world * CLIPS_PER_GPU / (ms_e2e * 1e-3)
 
     # ---- roofline of the dominant kernel (umma_gemm_kernel): device time of all its launches in one step ----
@@ -266,7 +292,8 @@ def run_ours(args):
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "clips/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": int(frames_host.nbytes + onehot_host.nbytes), "d2h_bytes_per_step": 32,
-                "input": "uint8 frames + int32 one-hot labels in host memory, staged through pinned buffers"},
+                "input": "uint8 frames + int32 one-hot labels in pinned host memory, H2D on a copy stream "
+                         "(double buffered) inside the timed region; Engine.prefetch + Engine.train_step"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": achieved / peak_tf, "traffic": None, "peak_source": peak_src + " (sustained bf16)",

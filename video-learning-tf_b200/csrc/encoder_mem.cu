@@ -495,6 +495,51 @@ __global__ void pool_lrn_bwd_kernel(const bf16* __restrict__ x, const bf16* __re
 // ------------------------------------------------------------------------------------------------
 constexpr int COLSUM_THREADS = 256;
 
+// Vector path (c % 8 == 0, ld % 8 == 0, c/8 <= 256): each thread owns one 16-byte column chunk and strides over
+// rows, four independent loads in flight; partial sums meet in shared memory, one atomicAdd per column and CTA.
+__global__ void __launch_bounds__(COLSUM_THREADS)
+    colsum_vec_kernel(const bf16* __restrict__ dy, float* __restrict__ out, long long rows, int c, int ld,
+                      long long rows_per_block) {
+  __shared__ float red[2048];
+  const int cpr = c >> 3;
+  const int lanes = COLSUM_THREADS / cpr;  // rows handled in parallel by one CTA
+  const int ch = threadIdx.x % cpr;
+  const int rl = threadIdx.x / cpr;
+  for (int i = threadIdx.x; i < c; i += COLSUM_THREADS) red[i] = 0.f;
+  __syncthreads();
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  const long long r1 = min(rows, r0 + rows_per_block);
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  if (rl < lanes) {
+    const bf16* base = dy + ch * 8;
+    long long r = r0 + rl;
+    for (; r + 3LL * lanes < r1; r += 4LL * lanes) {
+      Bf16x8 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const Bf16x8*>(base + (r + (long long)u * lanes) * ld);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float f[8];
+        unpack8(v[u], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += f[j];
+      }
+    }
+    for (; r < r1; r += lanes) {
+      float f[8];
+      unpack8(*reinterpret_cast<const Bf16x8*>(base + r * ld), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += f[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(&red[ch * 8 + j], acc[j]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < c; i += COLSUM_THREADS) atomicAdd(out + i, red[i]);
+}
+
 __global__ void colsum_kernel(const bf16* __restrict__ dy, float* __restrict__ out, long long rows, int c, int ld,
                               int ct, int ty_count, long long rows_per_block) {
   __shared__ float2 red[COLSUM_THREADS];
@@ -698,6 +743,17 @@ extern "C" int vl_maxpool_bwd(const void* dy, const void* argmax, void* dx, cons
 extern "C" int vl_colsum(const void* dy, float* out, int64_t rows, int32_t c, int32_t ld, vl_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   VL_REQUIRE(dy && out && rows > 0 && c > 0 && ld >= c, "vl_colsum: bad arguments");
+  if (c % 8 == 0 && ld % 8 == 0 && c / 8 <= COLSUM_THREADS && (reinterpret_cast<uintptr_t>(dy) & 15) == 0) {
+    const int lanes = COLSUM_THREADS / (c / 8);
+    long long blocks = (long long)vl::num_sms() * 8;
+    long long rpb = (rows + blocks - 1) / blocks;
+    if (rpb < 4LL * lanes) rpb = 4LL * lanes;
+    blocks = (rows + rpb - 1) / rpb;
+    colsum_vec_kernel<<<(int)blocks, COLSUM_THREADS, 0, stream>>>(reinterpret_cast<const bf16*>(dy), out, rows, c, ld,
+                                                                  rpb);
+    VL_LAUNCHED();
+    return 0;
+  }
   int ct = (c + 1) / 2;
   if (ct > 128) ct = 128;
   int ty = COLSUM_THREADS / ct;

@@ -357,7 +357,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const bool vec_ok = (p.c_ld % 8 == 0) && (gcol0 % 8 == 0) && !p.c_atomic &&
+                          ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
                           (p.mask == nullptr || p.mask_ld % 8 == 0);
+      const bool vec4_ok = (p.c_ld % 4 == 0) && (gcol0 % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);  // 16-byte aligned fp32 quads (vector red.add)
       for (int sub = 0; sub < msub; ++sub) {
         long long grow;
         bool row_ok;
@@ -433,9 +435,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
           } else {
             float* out = reinterpret_cast<float*>(p.C) + off;
             if (p.c_atomic) {
+              if (vec4_ok && ncols == 16) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j)
-                if (j < ncols) atomicAdd(out + j, f[j]);
+                for (int j = 0; j < 4; ++j)
+                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(out + 4 * j), "f"(f[4 * j]),
+                               "f"(f[4 * j + 1]), "f"(f[4 * j + 2]), "f"(f[4 * j + 3])
+                               : "memory");
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                  if (j < ncols) atomicAdd(out + j, f[j]);
+              }
             } else if (vec_ok && ncols == 16) {
 #pragma unroll
               for (int j = 0; j < 4; ++j)
@@ -689,7 +699,8 @@ extern "C" int vl_gemm(const vl_gemm_desc* d, const void* a, const void* b, void
   p.C = c;
   p.c_ld = d->c_ld;
   p.c_dtype = d->c_dtype;
-  p.c_atomic = d->c_atomic;
+  // C must be zeroed by the caller for the atomic epilogue, so a single split may store (vectorised) instead
+  p.c_atomic = d->c_atomic && p.split_k > 1;
   p.relu = d->relu;
   p.bias = bias;
   p.mask = reinterpret_cast<const bf16*>(relu_mask);

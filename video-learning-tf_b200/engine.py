@@ -384,9 +384,44 @@ class Engine(object):
             dst = self.A["frames_u8"] if is_u8 else self.A["frames_f32"]
             dst[:n].copy_(pin[:n], non_blocking=True)
             return dst[:n], is_u8, n
-        assert isinstance(frames, torch.Tensor) and frames.is_cuda and frames.is_contiguous()
-        assert frames.dtype in (torch.uint8, F32)
+        assert isinstance(frames, torch.Tensor) and frames.is_contiguous() and frames.dtype in (torch.uint8, F32)
+        if not frames.is_cuda:
+            # host tensor (ideally pinned): one asynchronous H2D copy straight into the device staging buffer
+            n = frames.shape[0]
+            if n > self.max_frames:
+                raise ValueError("batch of %d frames exceeds the engine capacity %d" % (n, self.max_frames))
+            is_u8 = frames.dtype == torch.uint8
+            if not is_u8 and self.A["frames_f32"] is None:
+                self.A["frames_f32"] = torch.empty(self.max_frames, cfg.height, cfg.width, 3, dtype=F32,
+                                                   device=self.dev)
+            dst = self.A["frames_u8"] if is_u8 else self.A["frames_f32"]
+            dst[:n].copy_(frames, non_blocking=True)
+            return dst[:n], is_u8, n
         return frames, frames.dtype == torch.uint8, frames.shape[0]
+
+    def prefetch(self, frames_pinned, onehot_pinned, slot):
+        """Enqueue the H2D copy of one batch (pinned host tensors: uint8 frames [n,H,W,3], int32 one-hot [b,C]) on the
+        copy stream into device slot `slot` (0/1) and return (frames_dev, onehot_dev, event).  The compute stream
+        must wait for `event` before `train_step(frames_dev, onehot_dev, ...)`; with two slots the copy of batch
+        i+1 overlaps the step of batch i."""
+        if not hasattr(self, "_copy_stream"):
+            self._copy_stream = torch.cuda.Stream(device=self.dev)
+            self._slots = {}
+        n, b = frames_pinned.shape[0], onehot_pinned.shape[0]
+        key = (slot, frames_pinned.dtype)
+        if key not in self._slots:
+            self._slots[key] = (torch.empty(self.max_frames, self.cfg.height, self.cfg.width, 3,
+                                            dtype=frames_pinned.dtype, device=self.dev),
+                                torch.empty(self.max_clips, self.cfg.num_classes, dtype=torch.int32, device=self.dev),
+                                torch.cuda.Event())
+        fd, od, done = self._slots[key]
+        self._copy_stream.wait_event(done)  # the step that last read this slot has finished
+        with torch.cuda.stream(self._copy_stream):
+            fd[:n].copy_(frames_pinned, non_blocking=True)
+            od[:b].copy_(onehot_pinned, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self._copy_stream)
+        return fd[:n], od[:b], ev, done
 
     # ------------------------------------------------------------------------------------------
     # forward
@@ -567,6 +602,10 @@ class Engine(object):
         df6 = G["df6"][:n]
         flat = A["p5"][:n].view(n, sp["flat"])
         self._dense_bwd(flat, df6, "dcnn/fc6W", "dcnn/fc6b")
+        if self.world > 1:
+            # fc6/fc7/LSTM/output gradients (89 % of the bytes) are final here: their all-reduce runs on NCCL's
+            # stream while the convolution gradients below are still being computed
+            self._early_reduce = parallel.allreduce_async(self.grads[self.var_off["dcnn/fc6W"]:], self.group)
         K.linear_dgrad(df6, sh["fc6"], G["dp5"][:n].view(n, sp["flat"]))
         nv.call("vl_maxpool_bwd", G["dp5"][:n], A["arg5"][:n], G["da5"][:n], A["a5"][:n], n, s3.p, s3.q, 256)
         self._conv_bwd("conv5", A["a4"][:n], G["da5"][:n], G["da4"][:n], A["a4"][:n])
@@ -616,7 +655,8 @@ class Engine(object):
         dfeat = self._head_bwd(n)
         self._encoder_bwd(dfeat, n)
         if self.world > 1:
-            parallel.allreduce_gradients(self.grads, self.scalars[4:6], self.group)
+            parallel.allreduce_gradients(self.grads[:self.var_off["dcnn/fc6W"]], self.scalars[4:6], self.group)
+            parallel.wait(self._early_reduce)
         nv.call("vl_grad_sqnorms", self.grads, self.arena_n, self.seg_offsets, len(self.var_shapes), self.sqnorms)
         clip = float(cfg.clip_norm) if cfg.clip_norm else 0.0
         nv.call("vl_clip_scalars", self.sqnorms, len(self.var_shapes), clip, 1.0, self.scalars)

@@ -30,6 +30,21 @@ def allreduce_gradients(flat_grads, scalars=None, group=None):
         dist.all_reduce(scalars, op=dist.ReduceOp.SUM, group=group)
 
 
+def allreduce_async(flat_slice, group=None):
+    """Start summing a slice of the gradient arena over ranks; returns a handle for `wait` (None when world == 1).
+    NCCL orders the collective after the work already enqueued on the current stream and runs it on its own
+    stream, so kernels enqueued afterwards overlap with the transfer."""
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return None
+    return dist.all_reduce(flat_slice, op=dist.ReduceOp.SUM, group=group, async_op=True)
+
+
+def wait(handle):
+    """Make the current stream wait for an `allreduce_async` handle."""
+    if handle is not None:
+        handle.wait()
+
+
 def gather_logits(local_logits, group=None):
     """Validation: all ranks' clip logits on every rank, in rank order (contiguous shards -> original order)."""
     if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
