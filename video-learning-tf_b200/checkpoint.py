@@ -87,3 +87,26 @@ def restore(engine, prefix, ignorable=("global_step",), is_validation=False):
             snap = pickle.load(f)
     info("Restored %s: batch %d, epoch %d, global step %d" % (prefix, snap[0], snap[1], snap[2]))
     return snap
+
+
+def load_alexnet_npy(engine, path, skip=("fc8",)):
+    """Initialise the encoder from the Caffe-converted `bvlc_alexnet.npy` the reference uses (alexnet.py:50-52,
+    69-71: a pickled dict layer -> [W, b], HWIO filters).  Layers whose shape does not match the model (fc8 for a
+    class count other than 1000) or that are listed in `skip` keep their current values."""
+    blob = np.load(path, allow_pickle=True, encoding="latin1").item()
+    shapes = dict(engine.var_shapes)
+    sd = {}
+    for layer, wb in blob.items():
+        if layer in skip:
+            continue
+        for suffix, arr in zip(("W", "b"), wb):
+            name = "dcnn/%s%s" % (layer, suffix)
+            arr = np.asarray(arr, dtype=np.float32)
+            if name in shapes and tuple(shapes[name]) == tuple(arr.shape):
+                sd[name] = arr
+            elif name in shapes:
+                warning("bvlc_alexnet.npy: %s has shape %s, model wants %s (kept random init)" % (
+                    name, arr.shape, shapes[name]))
+    engine.load_state_dict(sd, strict=False)
+    info("Loaded %d variables from %s" % (len(sd), path))
+    return sorted(sd)
