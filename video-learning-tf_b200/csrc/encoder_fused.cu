@@ -16,6 +16,7 @@
 #include "../../include/vlb200.h"
 
 #include <atomic>
+#include <cstdlib>
 
 namespace vl {
 extern std::atomic<long long> g_launches;
@@ -45,7 +46,7 @@ __device__ __forceinline__ Bf16x8 pack8(const float (&f)[8]) {
 }
 __device__ __forceinline__ float sqrt_approx(float x) {
   float y;
-  asm("sqrt.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
 __device__ __forceinline__ float rsqrt_approx(float x) {
@@ -84,6 +85,33 @@ __device__ __forceinline__ void lrn_scale8(const float (&x)[8], int l, int cpr, 
   sq[11] = rt[1];
 #pragma unroll
   for (int j = 0; j < 8; ++j) s[j] = fmaf(alpha, ((sq[j] + sq[j + 1]) + sq[j + 2]) + (sq[j + 3] + sq[j + 4]), bias);
+}
+
+// Multi-chunk form: a lane owns NE = 8*CPL consecutive channels, LPP lanes hold one pixel (LPP*NE == c for the
+// instantiated geometries, so no lane idles).  Halo = the two neighbours on each side, exchanged by shuffle.
+template <int LPP, int NE>
+__device__ __forceinline__ void halo2n(const float (&v)[NE], int l, float (&left)[2], float (&right)[2]) {
+  left[0] = __shfl_up_sync(0xffffffffu, v[NE - 2], 1, LPP);
+  left[1] = __shfl_up_sync(0xffffffffu, v[NE - 1], 1, LPP);
+  right[0] = __shfl_down_sync(0xffffffffu, v[0], 1, LPP);
+  right[1] = __shfl_down_sync(0xffffffffu, v[1], 1, LPP);
+  if (l == 0) left[0] = left[1] = 0.f;
+  if (l == LPP - 1) right[0] = right[1] = 0.f;
+}
+// w[j] = v[j-2] + ... + v[j+2] over the pixel's channel axis (zero outside), for the lane's NE channels
+template <int LPP, int NE>
+__device__ __forceinline__ void window5n(const float (&v)[NE], int l, float (&w)[NE]) {
+  float lf[2], rt[2];
+  halo2n<LPP, NE>(v, l, lf, rt);
+  float e[NE + 4];
+  e[0] = lf[0];
+  e[1] = lf[1];
+#pragma unroll
+  for (int j = 0; j < NE; ++j) e[2 + j] = v[j];
+  e[NE + 2] = rt[0];
+  e[NE + 3] = rt[1];
+#pragma unroll
+  for (int j = 0; j < NE; ++j) w[j] = ((e[j] + e[j + 1]) + e[j + 2]) + (e[j + 3] + e[j + 4]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -207,12 +235,13 @@ __global__ void s2d_unpack_grad_kernel(const float* __restrict__ dws, float* __r
 // input pixel of the strip (LPP lanes per pixel, 16 B per lane) into shared memory as bf16; phase 2 pools 3x3/2
 // windows out of shared memory.  beta = 0.75 fast path: s^-0.75 = rsqrt(s) * sqrt(rsqrt(s)).
 // ------------------------------------------------------------------------------------------------
-template <int LPP>
+template <int LPP, int CPL>
 __global__ void __launch_bounds__(512)
     lrn_pool_fwd_kernel2(const bf16* __restrict__ x, bf16* __restrict__ y, uint8_t* __restrict__ arg, int h, int w, int c,
                          int p, int q, int rows_out, int strips, float alpha, float bias) {
   extern __shared__ uint8_t smem_raw[];
   bf16* tile = reinterpret_cast<bf16*>(smem_raw);  // [(2*rows_out+1)][w][c]
+  constexpr int NE = 8 * CPL;                      // channels per lane; LPP * NE == c (host guarantees it)
   const int strip = blockIdx.x % strips;
   const int nn = blockIdx.x / strips;
   const int p0 = strip * rows_out;
@@ -224,35 +253,41 @@ __global__ void __launch_bounds__(512)
   const int ngrp = blockDim.x / LPP;
   const bf16* xin = x + ((long long)nn * h + 2 * p0) * w * c;
   const int npix = in_rows * w;
-  // phase 1: two pixels per lane group and iteration (both loads are in flight before the first use); all lanes of a
-  // group take part in the shuffles, also the padded chunk slots l >= cpr
-  for (int pix0 = 0; pix0 < npix; pix0 += 2 * ngrp) {
-    int pix[2];
-    bool live[2];
-    float v[2][8];
+  // phase 1: LPP lanes hold one pixel (NE channels each, CPL independent 16-byte loads in flight per lane); every
+  // lane of a group takes part in the halo shuffles
+  for (int pix0 = 0; pix0 < npix; pix0 += ngrp) {
+    const int pix = pix0 + grp;
+    const bool live = pix < npix;
+    float v[NE];
+    if (live) {
+      Bf16x8 in[CPL];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      pix[u] = pix0 + u * ngrp + grp;
-      live[u] = pix[u] < npix && l < cpr;
-      if (live[u]) {
-        unpack8(*reinterpret_cast<const Bf16x8*>(xin + (long long)pix[u] * c + l * 8), v[u]);
-      } else {
+      for (int k = 0; k < CPL; ++k) in[k] = *reinterpret_cast<const Bf16x8*>(xin + (long long)pix * c + l * NE + 8 * k);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[u][j] = 0.f;
+      for (int k = 0; k < CPL; ++k) {
+        float t8[8];
+        unpack8(in[k], t8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[8 * k + j] = t8[j];
       }
-    }
+    } else {
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      float s[8];
-      lrn_scale8<LPP>(v[u], l, cpr, alpha, bias, s);
-      if (live[u]) {
+      for (int j = 0; j < NE; ++j) v[j] = 0.f;
+    }
+    float sq[NE], ssum[NE];
+#pragma unroll
+    for (int j = 0; j < NE; ++j) sq[j] = v[j] * v[j];
+    window5n<LPP, NE>(sq, l, ssum);
+    if (live) {
+#pragma unroll
+      for (int k = 0; k < CPL; ++k) {
         float o[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float rs = rsqrt_approx(s[j]);
-          o[j] = v[u][j] * (rs * sqrt_approx(rs));
+          const float rs = rsqrt_approx(fmaf(alpha, ssum[8 * k + j], bias));
+          o[j] = v[8 * k + j] * (rs * sqrt_approx(rs));
         }
-        *reinterpret_cast<Bf16x8*>(tile + pix[u] * c + l * 8) = pack8(o);
+        *reinterpret_cast<Bf16x8*>(tile + pix * c + l * NE + 8 * k) = pack8(o);
       }
     }
   }
@@ -427,6 +462,134 @@ __global__ void __launch_bounds__(256, 3)
   }
 }
 
+// Instantiated-geometry version: C_ = LPP * 8 * CPL channels, every lane live, CPL independent 16-byte loads per
+// lane in flight.  Same arithmetic as pool_lrn_bwd_kernel2.
+template <int LPP, int CPL, int C_, int H_, int W_>
+__global__ void __launch_bounds__(128)
+    pool_lrn_bwd_kernel3(const bf16* __restrict__ x, const bf16* __restrict__ dy, const uint8_t* __restrict__ arg,
+                         bf16* __restrict__ dx, float* __restrict__ dbias, int n, float alpha, float beta, float bias) {
+  constexpr int NE = 8 * CPL;
+  constexpr int c = C_, h = H_, w = W_;
+  constexpr int p = (h - 3) / 2 + 1, q = (w - 3) / 2 + 1;
+  static_assert(LPP * NE == C_, "lanes x channels per lane must cover the channel axis exactly");
+  __shared__ float bsum[C_];
+  const int l = threadIdx.x % LPP;
+  const int grp = threadIdx.x / LPP;
+  constexpr int ngrp = 128 / LPP;
+  const int c0 = l * NE;
+  if (dbias != nullptr) {
+    for (int i = threadIdx.x; i < c; i += blockDim.x) bsum[i] = 0.f;
+    __syncthreads();
+  }
+  float bacc[NE];
+#pragma unroll
+  for (int j = 0; j < NE; ++j) bacc[j] = 0.f;
+  const float k2ab = 2.0f * alpha * beta;
+  const int rows_total = n * h;
+  for (int row = blockIdx.x; row < rows_total; row += gridDim.x) {
+    const int nn = row / h;
+    const int hh = row - nn * h;
+    const int p_lo = max(0, (hh - 1) >> 1), p_hi = min(p - 1, hh >> 1);
+    const bf16* xrow = x + (long long)row * (w * c);
+    bf16* dxrow = dx + (long long)row * (w * c);
+    const bf16* dyimg = dy + (long long)nn * (p * q * c);
+    const uint8_t* argimg = arg + (long long)nn * (p * q * c);
+    for (int ww0 = 0; ww0 < w; ww0 += ngrp) {
+      const int ww = ww0 + grp;
+      const bool live = ww < w;
+      float xv[NE], gv[NE];
+#pragma unroll
+      for (int j = 0; j < NE; ++j) xv[j] = gv[j] = 0.f;
+      if (live) {
+        Bf16x8 xin[CPL];
+#pragma unroll
+        for (int k = 0; k < CPL; ++k) xin[k] = *reinterpret_cast<const Bf16x8*>(xrow + ww * c + c0 + 8 * k);
+        __nv_bfloat162 g2[4 * CPL];
+#pragma unroll
+        for (int i = 0; i < 4 * CPL; ++i) g2[i] = __floats2bfloat162_rn(0.f, 0.f);
+        const int q_lo = max(0, (ww - 1) >> 1), q_hi = min(q - 1, ww >> 1);
+        for (int pp = p_lo; pp <= p_hi; ++pp) {
+          const int r3 = (hh - 2 * pp) * 3;
+          for (int qq = q_lo; qq <= q_hi; ++qq) {
+            const int o = (pp * q + qq) * c + c0;
+            const uint32_t code4 = (uint32_t)(r3 + ww - 2 * qq) * 0x01010101u;
+#pragma unroll
+            for (int k = 0; k < CPL; ++k) {
+              const uint4 g = *reinterpret_cast<const uint4*>(dyimg + o + 8 * k);
+              const uint2 a = *reinterpret_cast<const uint2*>(argimg + o + 8 * k);
+              const uint32_t mlo = __vcmpeq4(a.x, code4), mhi = __vcmpeq4(a.y, code4);
+              const uint32_t gw[4] = {g.x & __byte_perm(mlo, 0, 0x1100), g.y & __byte_perm(mlo, 0, 0x3322),
+                                      g.z & __byte_perm(mhi, 0, 0x1100), g.w & __byte_perm(mhi, 0, 0x3322)};
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                g2[4 * k + i] = __hadd2(g2[4 * k + i], *reinterpret_cast<const __nv_bfloat162*>(&gw[i]));
+            }
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < CPL; ++k) {
+          float t8[8];
+          unpack8(xin[k], t8);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) xv[8 * k + j] = t8[j];
+        }
+#pragma unroll
+        for (int i = 0; i < 4 * CPL; ++i) {
+          const float2 t = __bfloat1622float2(g2[i]);
+          gv[2 * i] = t.x;
+          gv[2 * i + 1] = t.y;
+        }
+      }
+      float sq[NE], ssum[NE];
+#pragma unroll
+      for (int j = 0; j < NE; ++j) sq[j] = xv[j] * xv[j];
+      window5n<LPP, NE>(sq, l, ssum);
+      float pw[NE], tt[NE], tsum[NE];
+#pragma unroll
+      for (int j = 0; j < NE; ++j) {
+        const float sc = fmaf(alpha, ssum[j], bias);
+        float inv;
+        if (beta == 0.75f) {
+          const float rs = rsqrt_approx(sc);
+          pw[j] = rs * sqrt_approx(rs);
+          inv = rs * rs;
+        } else {
+          pw[j] = __powf(sc, -beta);
+          inv = __fdividef(1.0f, sc);
+        }
+        tt[j] = (gv[j] * xv[j]) * (pw[j] * inv);
+      }
+      window5n<LPP, NE>(tt, l, tsum);
+      if (live) {
+#pragma unroll
+        for (int k = 0; k < CPL; ++k) {
+          float out[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int e = 8 * k + j;
+            const float g = fmaf(gv[e], pw[e], -(k2ab * xv[e]) * tsum[e]);
+            out[j] = xv[e] > 0.f ? g : 0.f;  // ReLU gradient of the producing conv
+          }
+          const Bf16x8 packed = pack8(out);
+          *reinterpret_cast<Bf16x8*>(dxrow + ww * c + c0 + 8 * k) = packed;
+          if (dbias != nullptr) {
+            float rb[8];
+            unpack8(packed, rb);  // the bias gradient sums the bf16 values that are stored (as vl_colsum would)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) bacc[8 * k + j] += rb[j];
+          }
+        }
+      }
+    }
+  }
+  if (dbias != nullptr) {
+#pragma unroll
+    for (int j = 0; j < NE; ++j) atomicAdd(&bsum[c0 + j], bacc[j]);
+    __syncthreads();
+    for (int i = threadIdx.x; i < c; i += blockDim.x) atomicAdd(dbias + i, bsum[i]);
+  }
+}
+
 }  // namespace
 
 #define VL_LAUNCHED()                  \
@@ -502,25 +665,29 @@ extern "C" int vl_lrn_pool_fwd(const void* x, void* y, void* argmax, int32_t n, 
   rows_out = (p + strips - 1) / strips;  // balance the strips
   const size_t smem = (size_t)(2 * rows_out + 1) * row_bytes;
   const int grid = n * strips;
-  if (c <= 128) {
-    static bool attr = false;
-    if (!attr) {
-      VL_CHECK_CUDA(cudaFuncSetAttribute(lrn_pool_fwd_kernel2<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
-      attr = true;
-    }
-    lrn_pool_fwd_kernel2<16><<<grid, 512, smem, stream>>>(reinterpret_cast<const bf16*>(x), reinterpret_cast<bf16*>(y),
-                                                          reinterpret_cast<uint8_t*>(argmax), h, w, c, p, q, rows_out,
-                                                          strips, alpha, bias);
-  } else {
-    static bool attr = false;
-    if (!attr) {
-      VL_CHECK_CUDA(cudaFuncSetAttribute(lrn_pool_fwd_kernel2<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
-      attr = true;
-    }
-    lrn_pool_fwd_kernel2<32><<<grid, 512, smem, stream>>>(reinterpret_cast<const bf16*>(x), reinterpret_cast<bf16*>(y),
-                                                          reinterpret_cast<uint8_t*>(argmax), h, w, c, p, q, rows_out,
-                                                          strips, alpha, bias);
-  }
+#define VL_FWD_LAUNCH(LPP_, CPL_)                                                                                       \
+  do {                                                                                                                 \
+    static bool attr = false;                                                                                          \
+    if (!attr) {                                                                                                       \
+      VL_CHECK_CUDA(cudaFuncSetAttribute(lrn_pool_fwd_kernel2<LPP_, CPL_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                         112 * 1024));                                                                 \
+      attr = true;                                                                                                     \
+    }                                                                                                                  \
+    lrn_pool_fwd_kernel2<LPP_, CPL_><<<grid, 512, smem, stream>>>(                                                      \
+        reinterpret_cast<const bf16*>(x), reinterpret_cast<bf16*>(y), reinterpret_cast<uint8_t*>(argmax), h, w, c, p, \
+        q, rows_out, strips, alpha, bias);                                                                             \
+  } while (0)
+  if (c == 96)
+    VL_FWD_LAUNCH(4, 3);
+  else if (c == 256)
+    VL_FWD_LAUNCH(32, 1);
+  else if (c == 128)
+    VL_FWD_LAUNCH(16, 1);
+  else if (c == 64)
+    VL_FWD_LAUNCH(8, 1);
+  else
+    return vl_lrn_pool_fwd_generic(x, y, argmax, n, h, w, c, radius, alpha, beta, bias, stream_);
+#undef VL_FWD_LAUNCH
   VL_LAUNCHED();
   return 0;
 }
@@ -542,9 +709,18 @@ extern "C" int vl_pool_lrn_bwd(const void* x, const void* dy, const void* argmax
       reinterpret_cast<bf16*>(dx), dbias, n, h, w, c, alpha, beta, bias
   (void)p;
   (void)q;
-  if (c == 96 && h == 57 && w == 57)  // conv1 block of the 227x227 AlexNet
+  const long long blocks3 = (long long)n * h < (long long)vl::num_sms() * 12 ? (long long)n * h : (long long)vl::num_sms() * 12;
+  if (c == 96 && h == 57 && w == 57 && !getenv("VL_LRN_BWD_V2"))  // conv1 block of the 227x227 AlexNet
+    pool_lrn_bwd_kernel3<4, 3, 96, 57, 57><<<(int)blocks3, 128, 0, stream>>>(
+        reinterpret_cast<const bf16*>(x), reinterpret_cast<const bf16*>(dy), reinterpret_cast<const uint8_t*>(argmax),
+        reinterpret_cast<bf16*>(dx), dbias, n, alpha, beta, bias);
+  else if (c == 256 && h == 28 && w == 28 && getenv("VL_LRN_BWD_V3"))  // conv2 block (slower than kernel2: 612 vs 555 us)
+    pool_lrn_bwd_kernel3<16, 2, 256, 28, 28><<<(int)blocks3, 128, 0, stream>>>(
+        reinterpret_cast<const bf16*>(x), reinterpret_cast<const bf16*>(dy), reinterpret_cast<const uint8_t*>(argmax),
+        reinterpret_cast<bf16*>(dx), dbias, n, alpha, beta, bias);
+  else if (c == 96 && h == 57 && w == 57)
     pool_lrn_bwd_kernel2<16, 96, 57, 57><<<(int)blocks, 256, 0, stream>>>(VL_BWD_ARGS);
-  else if (c == 256 && h == 28 && w == 28)  // conv2 block
+  else if (c == 256 && h == 28 && w == 28)
     pool_lrn_bwd_kernel2<32, 256, 28, 28><<<(int)blocks, 256, 0, stream>>>(VL_BWD_ARGS);
   else if (lpp == 16)
     pool_lrn_bwd_kernel2<16, 0, 0, 0><<<(int)blocks, 256, 0, stream>>>(VL_BWD_ARGS);
