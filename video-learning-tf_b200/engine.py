@@ -174,6 +174,7 @@ class Engine(object):
         if cfg.optimizer == "adam":
             self.adam_m = torch.zeros(off, dtype=F32, device=self.dev)
             self.adam_v = torch.zeros(off, dtype=F32, device=self.dev)
+        self._side = torch.cuda.Stream(device=self.dev)  # filter gradients (off the backward critical path)
         self._alloc_shadows()
         self._alloc_activations()
         self.load_state_dict(params if params is not None else init_variables(cfg))
@@ -533,14 +534,22 @@ class Engine(object):
         nv.call("vl_colsum", dy, self.var(bname, self.grads), dy.shape[0], n_cols, dy.stride(0))
 
     def _conv_bwd(self, name, x, dy, dx, relu_mask, bias_done=False):
+        """Gradients of one convolution.  The data gradient stays on the main stream (it is the critical path of the
+        backward pass); the filter / bias gradients only feed the optimiser, so they run on the side stream where
+        they overlap the issue-bound LRN/pool gradient kernels of the main chain."""
         s = self.sp[name]
         n = x.shape[0]
         dw = self.var2d("dcnn/%sW" % name, self.grads)
-        K.conv_wgrad(s, x, dy, dw)  # split-K chosen by the library
-        if not bias_done:
-            nv.call("vl_colsum", dy, self.var("dcnn/%sb" % name, self.grads), n * s.p * s.q, s.cout, s.cout)
+        main = torch.cuda.current_stream()
+        ready = torch.cuda.Event()
+        ready.record(main)  # dy is complete
         if dx is not None:
             K.conv_dgrad(s, dy, self.sh[name], dx, relu_mask=relu_mask)
+        self._side.wait_event(ready)
+        with torch.cuda.stream(self._side):
+            K.conv_wgrad(s, x, dy, dw)  # split-K chosen by the library
+            if not bias_done:
+                nv.call("vl_colsum", dy, self.var("dcnn/%sb" % name, self.grads), n * s.p * s.q, s.cout, s.cout)
 
     def _head_bwd(self, n):
         """From d(loss)/d(logits) down to d(loss)/d(frame features); returns the bf16 feature gradient."""
@@ -621,6 +630,7 @@ class Engine(object):
         s1s = sp["conv1_s2d"]
         K.conv_wgrad(s1s, A["x_s2d"][:n], G["da1"][:n], self.dws1)
         nv.call("vl_s2d_unpack_grad", self.dws1, self.var("dcnn/conv1W", self.grads), s1.kh, s1.kw, 3, 96, s1.stride)
+        torch.cuda.current_stream().wait_stream(self._side)  # join: every filter gradient is in the arena
 
     # ------------------------------------------------------------------------------------------
     # training step
