@@ -57,6 +57,8 @@ if "--profile" in sys.argv:
         evs.sort(key=lambda e: e.time_range.start)
         tot = sum(e.device_time for e in evs)
         print("== %s: %d kernels, %.1f us device time ==" % (what, len(evs), tot))
+        t0 = evs[0].time_range.start if evs else 0
         for i, e in enumerate(evs):
-            name = re.sub(r"\(.*", "", e.name).replace("(anonymous namespace)::", "").replace("void ", "")[:48]
-            print("%3d %-48s %9.1f us" % (i, name, e.device_time))
+            name = re.sub(r"<unnamed>::|\(anonymous namespace\)::|void ", "", e.name)
+            name = re.sub(r"\(.*", "", name)[:44]
+            print("%3d %-44s start %9.1f  dur %8.1f us" % (i, name, e.time_range.start - t0, e.device_time))

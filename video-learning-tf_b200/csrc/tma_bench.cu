@@ -190,3 +190,106 @@ extern "C" int vl_debug_sync_bench(int32_t variant, int32_t stages, int32_t iter
   VL_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Development probe 3: can a K-major SWIZZLE_128B operand be addressed at an arbitrary ROW offset (start address
+// = tile + off * 128 B, descriptor "base offset" = (start >> 7) & 7)?  D[128][n] = W[128][64] * X[off + j][64]^T.
+// mode bit 0: set the base-offset field; bit 1: shift the A operand instead of B (then D[i][j] = X[off+i] . W[j]).
+// ------------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(128, 1)
+    shift_mma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX, int off, int n,
+                     int mode, float* out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* done = bar + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 64);
+  uint8_t* sW = smem + 1024;            // 128 rows x 128 B
+  uint8_t* sX = smem + 1024 + 16384;    // 512 rows x 128 B
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    mbar_init(done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(bar, 16384 + 65536);
+    tma_load_2d(sW, &tmW, bar, 0, 0);
+    tma_load_2d(sX, &tmX, bar, 0, 0);
+    tma_load_2d(sX + 32768, &tmX, bar, 0, 256);
+    mbar_wait(bar, 0);
+    tc_fence_after();
+    const bool shift_a = mode & 2;
+    const uint32_t a_addr = shift_a ? smem_u32(sX) + off * 128 : smem_u32(sW);
+    const uint32_t b_addr = shift_a ? smem_u32(sW) : smem_u32(sX) + off * 128;
+    auto desc = [&](uint32_t addr) {
+      uint64_t d = (static_cast<uint64_t>((1024u >> 4) | (1u << 14) | (2u << 29)) << 32) | (1ull << 16) |
+                   ((addr >> 4) & 0x3FFFu);
+      if (mode & 1) d |= static_cast<uint64_t>((addr >> 7) & 7u) << 49;
+      return d;
+    };
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+    // K-steps advance by 32 B inside the swizzle row; the base offset refers to the row phase of the start address
+    for (int k = 0; k < 4; ++k) umma_bf16(tmem_base, desc(a_addr + k * 32), desc(b_addr + k * 32), idesc, (uint32_t)k);
+    umma_commit(done);
+    mbar_wait(done, 0);
+    tc_fence_after();
+  }
+  __syncthreads();
+  tc_fence_after();
+  // 4 warps read their 32-lane quadrant
+  const uint32_t taddr = tmem_base + (uint32_t(warp * 32) << 16);
+  for (int c0 = 0; c0 < n; c0 += 16) {
+    uint32_t v[16];
+    tmem_ld_x16(taddr + c0, v);
+    tmem_ld_wait();
+    for (int j = 0; j < 16; ++j) out[(warp * 32 + (threadIdx.x & 31)) * n + c0 + j] = __uint_as_float(v[j]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+}  // namespace
+
+extern "C" int vl_debug_shift_mma(const void* w, const void* x, int32_t x_rows, int32_t off, int32_t n, int32_t mode,
+                                  float* out, vl_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  cudaDriverEntryPointQueryResult qr;
+  void* fn = nullptr;
+  VL_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr));
+  auto enc = reinterpret_cast<vlb_dbg::EncodeTiledFn>(fn);
+  CUtensorMap tmW, tmX;
+  cuuint32_t estr[2] = {1, 1};
+  {
+    cuuint64_t dims[2] = {64, 128};
+    cuuint64_t strides[1] = {128};
+    cuuint32_t box[2] = {64, 128};
+    VL_REQUIRE(enc(&tmW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS, "encode W failed");
+  }
+  {
+    cuuint64_t dims[2] = {64, (cuuint64_t)x_rows};
+    cuuint64_t strides[1] = {128};
+    cuuint32_t box[2] = {64, 256};
+    VL_REQUIRE(enc(&tmX, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(x), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS, "encode X failed");
+  }
+  VL_CHECK_CUDA(cudaFuncSetAttribute(shift_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+  shift_mma_kernel<<<1, 128, 1024 + 1024 + 16384 + 65536, stream>>>(tmW, tmX, off, n, mode, out);
+  VL_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -175,6 +175,7 @@ class Engine(object):
             self.adam_m = torch.zeros(off, dtype=F32, device=self.dev)
             self.adam_v = torch.zeros(off, dtype=F32, device=self.dev)
         self._side = torch.cuda.Stream(device=self.dev)  # filter gradients (off the backward critical path)
+        self._side2 = torch.cuda.Stream(device=self.dev)  # second half-batch chain of the conv1/conv2 backward
         self._alloc_shadows()
         self._alloc_activations()
         self.load_state_dict(params if params is not None else init_variables(cfg))
@@ -620,15 +621,40 @@ class Engine(object):
         self._conv_bwd("conv5", A["a4"][:n], G["da5"][:n], G["da4"][:n], A["a4"][:n])
         self._conv_bwd("conv4", A["a3"][:n], G["da4"][:n], G["da3"][:n], A["a3"][:n])
         self._conv_bwd("conv3", A["p2"][:n], G["da3"][:n], G["dp2"][:n], None)
-        nv.call("vl_pool_lrn_bwd", A["a2"][:n], G["dp2"][:n], A["arg2"][:n], G["da2"][:n],
-                self.var("dcnn/conv2b", self.grads), n, s2.p, s2.q, 256, LRN["radius"], LRN["alpha"], LRN["beta"],
-                LRN["bias"])
-        self._conv_bwd("conv2", A["p1"][:n], G["da2"][:n], G["dp1"][:n], None, bias_done=True)
-        nv.call("vl_pool_lrn_bwd", A["a1"][:n], G["dp1"][:n], A["arg1"][:n], G["da1"][:n],
-                self.var("dcnn/conv1b", self.grads), n, s1.p, s1.q, 96, LRN["radius"], LRN["alpha"], LRN["beta"],
-                LRN["bias"])
+        # conv2 / conv1 blocks: the issue-bound LRN/pool gradient kernels and the tensor-bound contractions use
+        # different pipes, so the batch is split in two halves that run the chain
+        #     pool_lrn_bwd2 -> conv2 dgrad -> pool_lrn_bwd1 -> conv1 wgrad
+        # on two streams; the LRN kernel of one half overlaps the contraction of the other.  conv2's filter gradient
+        # (needs both halves of da2) stays on the filter-gradient stream.
+        main = torch.cuda.current_stream()
         s1s = sp["conv1_s2d"]
-        K.conv_wgrad(s1s, A["x_s2d"][:n], G["da1"][:n], self.dws1)
+        dp2_ready = torch.cuda.Event()
+        dp2_ready.record(main)
+        halves = [(0, n // 2), (n // 2, n)] if n >= 2 else [(0, n)]
+        da2_ready = []
+        for i, (lo, hi) in enumerate(halves):
+            st = main if i == 0 else self._side2
+            if st is not main:
+                st.wait_event(dp2_ready)
+            m = hi - lo
+            with torch.cuda.stream(st):
+                nv.call("vl_pool_lrn_bwd", A["a2"][lo:hi], G["dp2"][lo:hi], A["arg2"][lo:hi], G["da2"][lo:hi],
+                        self.var("dcnn/conv2b", self.grads), m, s2.p, s2.q, 256, LRN["radius"], LRN["alpha"],
+                        LRN["beta"], LRN["bias"])
+                ev = torch.cuda.Event()
+                ev.record(st)
+                da2_ready.append(ev)
+                K.conv_dgrad(s2, G["da2"][lo:hi], self.sh["conv2"], G["dp1"][lo:hi])
+                nv.call("vl_pool_lrn_bwd", A["a1"][lo:hi], G["dp1"][lo:hi], A["arg1"][lo:hi], G["da1"][lo:hi],
+                        self.var("dcnn/conv1b", self.grads), m, s1.p, s1.q, 96, LRN["radius"], LRN["alpha"],
+                        LRN["beta"], LRN["bias"])
+                K.conv_wgrad(s1s, A["x_s2d"][lo:hi], G["da1"][lo:hi], self.dws1)  # split-K atomics: halves add up
+        for ev in da2_ready:
+            self._side.wait_event(ev)
+        with torch.cuda.stream(self._side):
+            K.conv_wgrad(s2, A["p1"][:n], G["da2"][:n], self.var2d("dcnn/conv2W", self.grads))
+        if len(halves) > 1:
+            main.wait_stream(self._side2)
         nv.call("vl_s2d_unpack_grad", self.dws1, self.var("dcnn/conv1W", self.grads), s1.kh, s1.kw, 3, 96, s1.stride)
         torch.cuda.current_stream().wait_stream(self._side)  # join: every filter gradient is in the arena
 
