@@ -88,6 +88,29 @@ int vl_gemm(const vl_gemm_desc* desc, const void* a, const void* b, void* c, con
             const void* relu_mask, vl_stream_t stream);
 
 
+/* Tap-shifted stride-1 convolution for the narrow-channel layers (conv1 in space-to-depth form, conv2, conv2's data
+ * gradient): one tiled TMA box per (row tile, 64-channel chunk) with the padding materialised by out-of-bounds zero
+ * fill, every filter tap = the same shared-memory tile shifted by (r*Wp+s) rows, output channels on the M side and
+ * flat positions on the N side of tcgen05.mma.  out[n][Ho][Wo][c_ld] (bf16) = act(conv(x, w) + bias) with
+ * Ho = h + pad_top + pad_bottom - kh + 1, Wo = w + pad_left + pad_right - kw + 1 (alexnet.py:15-31).
+ * w_kmajor: bf16 [w_rows][w_ld], row = (group, output channel), column = (tap, input channel padded to 64). */
+typedef struct vl_conv_flat_desc {
+  int32_t n, h, w, c;                 /* NHWC input; c = all channels (all groups)                          */
+  int32_t kh, kw;
+  int32_t pad_top, pad_left, pad_bottom, pad_right;
+  int32_t groups, cin_g, cout_g;      /* contraction / output channels per group                           */
+  int32_t flip_taps;                  /* 1: tap (r,s) uses the filter of tap (kh-1-r, kw-1-s) (data gradient) */
+  int32_t w_rows, w_ld;               /* rows and row pitch (elements) of w_kmajor                          */
+  int32_t c_ld;                       /* channel pitch of out                                               */
+  int32_t relu;
+} vl_conv_flat_desc;
+int vl_conv_flat(const vl_conv_flat_desc* desc, const void* x, const void* w_kmajor, const float* bias, void* out,
+                 vl_stream_t stream);
+/* K-major filter of the data gradient: dst[g*cin_g+ci][tap*kpad+co] = src[tap*cin_g+ci][g*cout_g+co], kpad =
+ * cout_g rounded up to 64; src = HWIO fp32 as 2-D [taps*cin_g][groups*cout_g]. */
+int vl_pack_dgrad_kmajor(const float* src, void* dst, int32_t taps, int32_t cin_g, int32_t cout_g, int32_t groups,
+                         vl_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Memory-bound kernels of the AlexNet encoder (HBM roofline).
  * ---------------------------------------------------------------------------------------------- */

@@ -44,6 +44,12 @@ for name, s in specs.items():
     cases.append((name + " fwd", flops, lambda s=s, x=x, wp=wp, b=b, y=y: K.conv_fwd(s, x, wp, b, y, relu=True)))
     if dx is not None:
         cases.append((name + " dgrad", flops, lambda s=s, dy=dy, wd=wd, dx=dx: K.conv_dgrad(s, dy, wd, dx)))
+    if s.cout_g <= 128:
+        cases.append((name + " fwd FLAT", flops, lambda s=s, x=x, wp=wp, b=b, y=y: K.conv_fwd_flat(s, x, wp, b, y, relu=True)))
+    if dx is not None and s.cin_g <= 128:
+        kpad = -(-s.cout_g // 64) * 64
+        wdk = torch.randn(s.cin, s.taps * kpad, device=dev).to(bf)
+        cases.append((name + " dgrad FLAT", flops, lambda s=s, dy=dy, wdk=wdk, dx=dx: K.conv_dgrad_flat(s, dy, wdk, dx)))
     cases.append((name + " wgrad", flops, lambda s=s, x=x, dy=dy, dw=dw: K.conv_wgrad(s, x, dy, dw)))
 # dense layers
 for name, m, kk, nn in (("fc6", n, 9216, 4096), ("fc7", n, 4096, 4096)):
@@ -64,4 +70,4 @@ for name, flops, fn in cases:
         os.environ["VL_GEMM_DBG"] = str(dbg)
         row.append(timed(fn))
     os.environ["VL_GEMM_DBG"] = "0"
-    print("%-14s" % name + "".join("%11.1f us" % t for t in row) + "   %8.1f" % (flops / row[0] / 1e6), flush=True)
+    print("%-16s" % name + "".join("%11.1f us" % t for t in row) + "   %8.1f" % (flops / row[0] / 1e6), flush=True)

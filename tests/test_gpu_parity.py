@@ -101,6 +101,31 @@ def test_conv1_patches_and_gemm_vs_oracle(vl):
     assert torch.equal(col, col2)
 
 
+@pytest.mark.parametrize("name,n,h,cin,cout,k,groups", [
+    ("conv2", 3, 28, 96, 256, 5, 2), ("conv5", 2, 13, 384, 256, 3, 2), ("conv3", 2, 13, 256, 384, 3, 1),
+    ("odd", 2, 9, 64, 32, 3, 1)])
+def test_tap_shifted_conv_fwd_dgrad_vs_oracle(vl, name, n, h, cin, cout, k, groups):
+    """csrc/conv_flat.cu: input tile staged once, filter taps as shifted shared-memory descriptors, channels on M."""
+    nv, K = vl["nv"], vl["K"]
+    rng = np.random.default_rng(19)
+    x = bf16_round(rng.standard_normal((n, h, h, cin)))
+    w = bf16_round(rng.standard_normal((k, k, cin // groups, cout)) * 0.05)
+    b = rng.standard_normal(cout).astype(np.float32)
+    dy = bf16_round(rng.standard_normal((n, h, h, cout)))
+    y_ref = O.relu(O.conv2d_same(x, w, b, 1, groups))
+    dx_ref, _, _ = O.conv2d_same_backward(x, w, dy, 1, groups)
+    spec = K.ConvSpec(h, h, cin, cout, k, k, 1, groups)
+    out = torch.full((n, h, h, cout), float("nan"), dtype=torch.bfloat16, device="cuda")
+    K.conv_fwd_flat(spec, dev(x, torch.bfloat16), K.pack_conv_weight_host(spec, dev(w)), dev(b), out, relu=True)
+    assert rel(out.float().cpu().numpy(), y_ref) < BF16_TOL
+    kpad = -(-spec.cout_g // 64) * 64
+    wd = torch.empty(cin, spec.taps * kpad, dtype=torch.bfloat16, device="cuda")
+    nv.call("vl_pack_dgrad_kmajor", dev(w.reshape(-1, cout)), wd, spec.taps, spec.cin_g, spec.cout_g, groups)
+    dx = torch.full((n, h, h, cin), float("nan"), dtype=torch.bfloat16, device="cuda")
+    K.conv_dgrad_flat(spec, dev(dy, torch.bfloat16), wd, dx)
+    assert rel(dx.float().cpu().numpy(), dx_ref) < BF16_TOL
+
+
 def test_conv1_space_to_depth_path_vs_oracle(vl):
     """conv1 (11x11 stride 4 SAME, alexnet.py:60-77) as space-to-depth + 3x3 VALID im2col-TMA convolution."""
     nv, K, E = vl["nv"], vl["K"], vl["E"]
@@ -131,6 +156,9 @@ def test_conv1_space_to_depth_path_vs_oracle(vl):
     K.conv_fwd(s1s, xs, wp, dev(b), out, relu=True)
     y_ref = O.relu(O.conv2d_same(bf16_round(x), w, b, 4, 1))
     assert rel(out.float().cpu().numpy(), y_ref) < BF16_TOL
+    out2 = torch.full_like(out, float("nan"))
+    K.conv_fwd_flat(s1s, xs, wp, dev(b), out2, relu=True)  # tap-shifted kernel: same result up to summation order
+    assert rel(out2.float().cpu().numpy(), y_ref) < BF16_TOL
     # filter gradient through the space-to-depth form, scattered back to HWIO
     dy = bf16_round(rng.standard_normal((n, 57, 57, 96)))
     _, dw_ref, _ = O.conv2d_same_backward(bf16_round(x), w, dy, 4, 1, need_dx=False)

@@ -29,6 +29,12 @@ class GemmDesc(ctypes.Structure):
         ("conv", ConvGeom)]
 
 
+class ConvFlatDesc(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in (
+        "n", "h", "w", "c", "kh", "kw", "pad_top", "pad_left", "pad_bottom", "pad_right", "groups", "cin_g", "cout_g",
+        "flip_taps", "w_rows", "w_ld", "c_ld", "relu")]
+
+
 class NativeError(RuntimeError):
     pass
 
@@ -59,6 +65,8 @@ def _declare(L):
     u64 = ctypes.c_uint64
     sigs = {
         "vl_gemm": [ctypes.POINTER(GemmDesc), vp, vp, vp, vp, vp, vp],
+        "vl_conv_flat": [ctypes.POINTER(ConvFlatDesc), vp, vp, vp, vp, vp],
+        "vl_pack_dgrad_kmajor": [vp, vp, i32, i32, i32, i32, vp],
         "vl_conv1_patches": [vp, i32, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp],
         "vl_lrn_fwd": [vp, vp, i64, i32, i32, f32, f32, f32, vp],
         "vl_lrn_bwd": [vp, vp, vp, i64, i32, i32, f32, f32, f32, i32, vp],
@@ -96,7 +104,7 @@ def _declare(L):
         fn.argtypes = argtypes
 
 
-EXPORTS = ["vl_last_error", "vl_version", "vl_device_sm_count", "vl_launch_count", "vl_gemm", "vl_conv1_patches",
+EXPORTS = ["vl_last_error", "vl_version", "vl_device_sm_count", "vl_launch_count", "vl_gemm", "vl_conv_flat", "vl_pack_dgrad_kmajor", "vl_conv1_patches",
            "vl_lrn_fwd", "vl_lrn_bwd", "vl_maxpool_fwd", "vl_maxpool_bwd", "vl_colsum", "vl_pack_bf16",
            "vl_cast_f32_to_bf16", "vl_transpose_f32", "vl_lstm_fwd", "vl_lstm_bwd", "vl_lrn_pool_fwd", "vl_pool_lrn_bwd",
            "vl_lstm_fwd_cluster", "vl_lstm_bwd_cluster", "vl_frames_s2d", "vl_pack_bf16_t", "vl_s2d_pack_filter", "vl_s2d_unpack_grad",
@@ -122,6 +130,10 @@ def stream_handle():
 
 def gemm(desc, a, b, c, bias=None, relu_mask=None):
     check(lib().vl_gemm(ctypes.byref(desc), ptr(a), ptr(b), ptr(c), ptr(bias), ptr(relu_mask), stream_handle()))
+
+
+def conv_flat(desc, x, w, bias, out):
+    check(lib().vl_conv_flat(ctypes.byref(desc), ptr(x), ptr(w), ptr(bias), ptr(out), stream_handle()))
 
 
 def call(name, *args):

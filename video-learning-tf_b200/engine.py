@@ -443,16 +443,16 @@ class Engine(object):
         nv.call("vl_frames_s2d", frames, 1 if is_u8 else 0, self._mean_dev(), xs, n, self.cfg.height, self.cfg.width,
                 s1.stride, s1.pad_top, s1.pad_left, s1s.h, s1s.w)
         a1 = A["a1"][:n]
-        K.conv_fwd(s1s, xs, sh["conv1_fwd"], self.var("dcnn/conv1b"), a1, relu=True)
+        K.conv_fwd_flat(s1s, xs, sh["conv1_fwd"], self.var("dcnn/conv1b"), a1, relu=True)  # tap-shifted kernel
         nv.call("vl_lrn_pool_fwd", a1, A["p1"][:n], A["arg1"][:n], n, s1.p, s1.q, 96, LRN["radius"], LRN["alpha"],
                 LRN["beta"], LRN["bias"])
         s2 = sp["conv2"]
-        K.conv_fwd(s2, A["p1"][:n], sh["conv2_fwd"], self.var("dcnn/conv2b"), A["a2"][:n], relu=True)
+        K.conv_fwd_flat(s2, A["p1"][:n], sh["conv2_fwd"], self.var("dcnn/conv2b"), A["a2"][:n], relu=True)
         nv.call("vl_lrn_pool_fwd", A["a2"][:n], A["p2"][:n], A["arg2"][:n], n, s2.p, s2.q, 256, LRN["radius"],
                 LRN["alpha"], LRN["beta"], LRN["bias"])
         K.conv_fwd(sp["conv3"], A["p2"][:n], sh["conv3_fwd"], self.var("dcnn/conv3b"), A["a3"][:n], relu=True)
         K.conv_fwd(sp["conv4"], A["a3"][:n], sh["conv4_fwd"], self.var("dcnn/conv4b"), A["a4"][:n], relu=True)
-        K.conv_fwd(sp["conv5"], A["a4"][:n], sh["conv5_fwd"], self.var("dcnn/conv5b"), A["a5"][:n], relu=True)
+        K.conv_fwd_flat(sp["conv5"], A["a4"][:n], sh["conv5_fwd"], self.var("dcnn/conv5b"), A["a5"][:n], relu=True)
         s3 = sp["conv3"]
         nv.call("vl_maxpool_fwd", A["a5"][:n], A["p5"][:n], A["arg5"][:n], n, s3.p, s3.q, 256)
         flat = A["p5"][:n].view(n, sp["flat"])  # HWC-major flatten (alexnet.py:228)

@@ -160,6 +160,43 @@ def conv_fwd(spec, x, w_kmajor, bias, out, relu=True, block_n=0, msub=0):
     return out
 
 
+def conv_fwd_flat(spec, x, w_kmajor, bias, out, relu=True):
+    """Same contract as conv_fwd for stride-1 convolutions with cout_g <= 128, through the tap-shifted kernel
+    (csrc/conv_flat.cu): the input tile is staged once per row tile instead of once per tap."""
+    assert spec.stride == 1 and out.dtype == BF16
+    n = x.shape[0]
+    d = nv.ConvFlatDesc()
+    d.n, d.h, d.w, d.c = n, spec.h, spec.w, spec.cin
+    d.kh, d.kw = spec.kh, spec.kw
+    d.pad_top, d.pad_left, d.pad_bottom, d.pad_right = spec.pad_top, spec.pad_left, spec.pad_bottom, spec.pad_right
+    d.groups, d.cin_g, d.cout_g = spec.groups, spec.cin_g, spec.cout_g
+    d.flip_taps = 0
+    d.w_rows, d.w_ld = spec.cout, spec.k_packed
+    d.c_ld = spec.cout
+    d.relu = 1 if relu else 0
+    nv.conv_flat(d, x, w_kmajor, bias, out)
+    return out
+
+
+def conv_dgrad_flat(spec, dy, w_dgrad_kmajor, dx):
+    """dx = conv2d_backprop_input(dy, W) for a stride-1 SAME convolution with cin_g <= 128: a "full" correlation of
+    dy with the flipped filter; w_dgrad_kmajor = vl_pack_dgrad_kmajor(W) [cin, taps * roundup64(cout_g)]."""
+    assert spec.stride == 1 and dx.dtype == BF16
+    n = dy.shape[0]
+    d = nv.ConvFlatDesc()
+    d.n, d.h, d.w, d.c = n, spec.p, spec.q, spec.cout
+    d.kh, d.kw = spec.kh, spec.kw
+    d.pad_top, d.pad_left = spec.kh - 1 - spec.pad_top, spec.kw - 1 - spec.pad_left
+    d.pad_bottom, d.pad_right = spec.kh - 1 - spec.pad_bottom, spec.kw - 1 - spec.pad_right
+    d.groups, d.cin_g, d.cout_g = spec.groups, spec.cout_g, spec.cin_g
+    d.flip_taps = 1
+    d.w_rows, d.w_ld = spec.cin, spec.taps * (-(-spec.cout_g // 64) * 64)
+    d.c_ld = spec.cin
+    d.relu = 0
+    nv.conv_flat(d, dy, w_dgrad_kmajor, None, dx)
+    return dx
+
+
 def conv_dgrad(spec, dy, w_hwio, dx, relu_mask=None, block_n=0, msub=0):
     """dx[N,H,W,Cin] = conv2d_backprop_input(dy[N,P,Q,Cout], W); w_hwio = bf16 [taps*cin_g, Cout] (HWIO as 2D)."""
     n = dy.shape[0]
