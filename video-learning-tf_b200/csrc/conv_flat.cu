@@ -31,10 +31,10 @@ namespace {
 using namespace vl::ptx;
 typedef __nv_bfloat16 bf16;
 
-constexpr int NUM_THREADS = 320;  // warp0 TMA, warp1 MMA (+TMEM alloc), warps 2..9 epilogue (two groups of four)
+constexpr int EPI_GROUPS = 2;                           // epilogue groups of four warps (one per TMEM lane quadrant)
+constexpr int NUM_THREADS = 64 + EPI_GROUPS * 128;      // warp0 TMA, warp1 MMA (+TMEM alloc), then the epilogue warps
 constexpr int TMEM_COLS = 512;    // 2 accumulator stages x 256 fp32 columns
 constexpr int ACC_STRIDE_COLS = 256;
-constexpr int W_STAGE_BYTES = 128 * 64 * 2;  // one tap x chunk of the filter: 128 rows x 128 B
 constexpr int MAX_W_STAGES = 8;
 constexpr int MAX_X_STAGES = 2;
 constexpr int SMEM_LIMIT = 232448;
@@ -59,6 +59,9 @@ struct FParams {
   int c_goff, c_ld;
   int x_stage_bytes, x_box_bytes, x_stages, w_stages;
   int tpg;                             // filter taps per weight-ring stage (one hand-shake per group of taps)
+  int w_tap_bytes;                     // bytes of one (tap, chunk) filter box: rows x 128 B
+  int w_region;                        // bytes of the filter area (ring or resident copy)
+  int resident;                        // 1: the whole filter stays in shared memory (loaded once per CTA)
   FastDiv fd_mblk, fd_groups, fd_rt, fd_kw;
   void* C;
   int relu;
@@ -119,7 +122,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], 8);
+      mbar_init(&tmem_empty[s], 4 * EPI_GROUPS);
     }
     fence_barrier_init();
   }
@@ -143,6 +146,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     const bool ld_w = !(p.dbg & 4);
     int ws = 0, xs = 0;
     uint32_t wph = 0, xph = 0;
+    if (p.resident) {
+      // the whole filter (taps x chunks boxes) is loaded once and stays resident for every tile of this CTA
+      if (elect_one()) {
+        mbar_expect_tx_u32(wf_u32, ld_w ? (uint32_t)(taps * cchunks * p.w_tap_bytes) : 0u);
+        if (ld_w)
+          for (int i = 0; i < taps * cchunks; ++i) {  // box i = (chunk i / taps, tap i % taps [flipped])
+            const int tp = i % taps, tapw = p.flip ? (taps - 1 - tp) : tp;
+            tma_load_2d_u32(w_u32 + i * p.w_tap_bytes, &tmW, wf_u32, (tapw * cchunks + i / taps) * 64, 0);
+          }
+      }
+      __syncwarp();
+    }
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const FTile t = decode(p, tile);
       const int row0 = t.rt * p.R - p.pad_top;  // first input row of the tile
@@ -163,15 +178,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
         // filter column of tap t and chunk cc: (t * cchunks + cc) * 64, walked forwards or (flipped) backwards
         int kcoord = (p.flip ? (taps - 1) * cchunks + cc : cc) * 64;
         const int kstep = (p.flip ? -cchunks : cchunks) * 64;
-        for (int tap0 = 0; tap0 < taps; tap0 += p.tpg) {
+        for (int tap0 = 0; tap0 < taps && !p.resident; tap0 += p.tpg) {
           const int nt = min(p.tpg, taps - tap0);
           mbar_wait_u32(we_u32 + ws * 8, wph ^ 1u);
           if (elect_one()) {
-            mbar_expect_tx_u32(wf_u32 + ws * 8, ld_w ? (uint32_t)(nt * W_STAGE_BYTES) : 0u);
+            mbar_expect_tx_u32(wf_u32 + ws * 8, ld_w ? (uint32_t)(nt * p.w_tap_bytes) : 0u);
             if (ld_w) {
-              uint32_t dst = w_u32 + ws * p.tpg * W_STAGE_BYTES;
+              uint32_t dst = w_u32 + ws * p.tpg * p.w_tap_bytes;
               int kc = kcoord;
-              for (int j = 0; j < nt; ++j, dst += W_STAGE_BYTES, kc += kstep)
+              for (int j = 0; j < nt; ++j, dst += p.w_tap_bytes, kc += kstep)
                 tma_load_2d_u32(dst, &tmW, wf_u32 + ws * 8, kc, w_row);
             }
           }
@@ -198,6 +213,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     int ws = 0, xs = 0;
     uint32_t wph = 0, xph = 0;
     int local = 0;
+    const int tpg_eff = p.resident ? taps : tpg;  // resident filter: one group = all taps, no weight hand-shake
+    if (p.resident) mbar_wait_u32(wf_u32, 0);
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
@@ -210,11 +227,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
         const int ksteps = min(4, (p.cin_g - cc * 64 + 15) >> 4);  // zero-padded K-steps are never issued
         uint32_t b_lo = ((x_u32 + xs * p.x_stage_bytes) >> 4) & 0x3FFFu;  // descriptor start of tap (0,0), 16-byte units
         int ts = 0;
-        for (int tap0 = 0; tap0 < taps; tap0 += tpg) {
-          const int nt = min(tpg, taps - tap0);
-          mbar_wait_u32(wf_u32 + ws * 8, wph);
+        for (int tap0 = 0; tap0 < taps; tap0 += tpg_eff) {
+          const int nt = min(tpg_eff, taps - tap0);
+          if (!p.resident) mbar_wait_u32(wf_u32 + ws * 8, wph);
           tc_fence_after();
-          uint32_t a_lo = ((w_u32 + ws * tpg * W_STAGE_BYTES) >> 4) & 0x3FFFu;
+          uint32_t a_lo = ((w_u32 + (p.resident ? cc * taps : ws * tpg) * p.w_tap_bytes) >> 4) & 0x3FFFu;
           if (elect_one()) {
             if (do_mma) {
               for (int j = 0; j < nt; ++j) {
@@ -233,7 +250,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
                     umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, accumulate | (uint32_t)k);
                 }
                 accumulate = 1;
-                a_lo += W_STAGE_BYTES >> 4;
+                a_lo += (uint32_t)(p.w_tap_bytes >> 4);
                 b_lo += 8;
                 if (++ts == kw) {
                   ts = 0;
@@ -241,7 +258,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
                 }
               }
             }
-            umma_commit_u32(we_u32 + ws * 8);
+            if (!p.resident) umma_commit_u32(we_u32 + ws * 8);
             if (tap0 + nt == taps) umma_commit_u32(xe_u32 + xs * 8);  // the input tile is free after its last tap
           }
           // (accumulate, a_lo, b_lo, ts advance in the elected lane only: elect.sync picks the same lane every time)
@@ -264,14 +281,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     // Each thread owns one output channel (TMEM lane).  16 positions at a time are transposed through a small
     // double-buffered shared-memory stage ([position][channel] bf16) so that global stores are 16-byte vectors over
     // the channel axis (one contiguous 2*mc-byte run per position) instead of 2-byte scatters.
-    // Eight epilogue warps: warp % 4 selects the TMEM lane quadrant, (warp - 2) / 4 the group; group 0 drains the
-    // even 16-position chunks, group 1 the odd ones (a single warp sustains only ~650 cycles per chunk).
+    // EPI_GROUPS x 4 epilogue warps: warp % 4 selects the TMEM lane quadrant, (warp - 2) / 4 the group; group g
+    // drains the 16-position chunks g, g + EPI_GROUPS, ... (a single warp sustains only ~650 cycles per chunk).
     const int quad = warp & 3;
     const int grp = (warp - 2) >> 2;
     const int etid = (threadIdx.x - 64) & 127;  // 0..127 inside the group
     const int m_local = quad * 32 + lane;
     bf16* out = reinterpret_cast<bf16*>(p.C);
-    bf16* stage = reinterpret_cast<bf16*>(w_tiles + p.w_stages * p.tpg * W_STAGE_BYTES) + grp * (2 * 16 * 128);  // [2][16][128]
+    bf16* stage = reinterpret_cast<bf16*>(w_tiles + p.w_region) + grp * (2 * 16 * 128);  // [2][16][128] per group  // [2][16][128]
     int local = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
       const FTile t = decode(p, tile);
@@ -312,10 +329,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
             sb[j * 128 + m_local] = __float2bfloat16_rn(f);
           }
         }
-        if (grp == 0)
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-        else
-          asm volatile("bar.sync 2, 128;" ::: "memory");
+        asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory");
         if (!(p.dbg & 8)) {
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
@@ -332,7 +346,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
             }
           }
         }
-        col_c += 32;  // the other group handles the chunk in between
+        col_c += 16 * EPI_GROUPS;  // the other groups handle the chunks in between
         while (col_c >= p.Wp) {
           col_c -= p.Wp;
           ++row_c;
@@ -341,14 +355,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
       uint32_t va[16], vb[16];
       const int first = grp * 16;
       if (first < p.npos && !(p.dbg & 64)) tmem_ld_x16(taddr + first, va);
-      for (int c0 = first; c0 < p.npos && !(p.dbg & 64); c0 += 64) {
+      constexpr int STEP = 16 * EPI_GROUPS;
+      for (int c0 = first; c0 < p.npos && !(p.dbg & 64); c0 += 2 * STEP) {
         tmem_ld_wait();
-        const bool has_b = c0 + 32 < p.npos;
-        if (has_b) tmem_ld_x16(taddr + c0 + 32, vb);
+        const bool has_b = c0 + STEP < p.npos;
+        if (has_b) tmem_ld_x16(taddr + c0 + STEP, vb);
         emit(va, 0);
         if (has_b) {
           tmem_ld_wait();
-          if (c0 + 64 < p.npos) tmem_ld_x16(taddr + c0 + 64, va);
+          if (c0 + 2 * STEP < p.npos) tmem_ld_x16(taddr + c0 + 2 * STEP, va);
           emit(vb, 1);
         }
       }
@@ -466,19 +481,34 @@ extern "C" int vl_conv_flat(const vl_conv_flat_desc* d, const void* x, const voi
   p.x_box_bytes = box_rows * p.Wp * 128;
   p.x_stage_bytes = ((p.x_box_bytes + 1023) / 1024) * 1024;
   p.x_stages = MAX_X_STAGES;
-  const int STAGE_BYTES = 2 * 2 * 16 * 128 * 2;  // epilogue transposition stages (two groups, double buffered)
+  const int STAGE_BYTES = EPI_GROUPS * 2 * 16 * 128 * 2;  // epilogue transposition stages (per group, double buffered)
   const int w_avail = SMEM_LIMIT - 1024 - BAR_REGION - STAGE_BYTES - 1024 - p.x_stages * p.x_stage_bytes;
+  // filter box: only the rows that exist (8-row swizzle atoms); the UMMA reads 128 rows, the surplus lanes are
+  // never stored
+  int w_box_rows = d->w_rows < 128 ? ((d->w_rows + 7) / 8) * 8 : 128;
+  if (p.m_blks > 1 || p.groups > 1) w_box_rows = 128;
+  p.w_tap_bytes = w_box_rows * 128;
+  // resident filter when it fits (conv1: 9 taps x 96 rows = 108 KB) and is the same for every tile
+  p.resident = (p.m_blks == 1 && p.groups == 1 && p.taps * p.cchunks * p.w_tap_bytes + (128 - w_box_rows) * 128 <= w_avail &&
+                !getenv("VL_FLAT_NO_RESIDENT"))
+                   ? 1
+                   : 0;
   // taps per weight stage: a whole filter row if two such stages fit (one mbarrier hand-shake costs ~350 cycles, a
   // 128 x 240 x 16 UMMA 120), else as many taps as still allow double buffering
   p.tpg = d->kw;
   if (getenv("VL_FLAT_TPG")) p.tpg = atoi(getenv("VL_FLAT_TPG"));
-  while (p.tpg > 1 && w_avail / (p.tpg * W_STAGE_BYTES) < 2) --p.tpg;
-  int w_stages = w_avail / (p.tpg * W_STAGE_BYTES);
+  while (p.tpg > 1 && w_avail / (p.tpg * p.w_tap_bytes) < 2) --p.tpg;
+  int w_stages = w_avail / (p.tpg * p.w_tap_bytes);
   if (w_stages > MAX_W_STAGES) w_stages = MAX_W_STAGES;
-  VL_REQUIRE(w_stages >= 2, "vl_conv_flat: not enough shared memory (input tile %d B)", p.x_stage_bytes);
+  int w_region = w_stages * p.tpg * p.w_tap_bytes;
+  if (p.resident) {
+    w_stages = 1;
+    w_region = ((p.taps * p.cchunks * p.w_tap_bytes + (128 - w_box_rows) * 128 + 1023) / 1024) * 1024;
+  }
+  VL_REQUIRE(w_stages >= 2 || p.resident, "vl_conv_flat: not enough shared memory (input tile %d B)", p.x_stage_bytes);
   p.w_stages = w_stages;
-  const int smem_bytes =
-      1024 + BAR_REGION + p.x_stages * p.x_stage_bytes + w_stages * p.tpg * W_STAGE_BYTES + STAGE_BYTES + 1024;
+  p.w_region = w_region;
+  const int smem_bytes = 1024 + BAR_REGION + p.x_stages * p.x_stage_bytes + w_region + STAGE_BYTES + 1024;
   // instruction descriptor: D=f32, A=B=bf16 K-major, N>>3 at bit 17, M>>4 at bit 24
   p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.npos >> 3) << 17) | ((128u >> 4) << 24);
 
@@ -497,7 +527,7 @@ extern "C" int vl_conv_flat(const vl_conv_flat_desc* d, const void* x, const voi
     const long long k_total = (long long)p.taps * p.cchunks * 64;
     cuuint64_t dims[2] = {(cuuint64_t)k_total, (cuuint64_t)d->w_rows};
     cuuint64_t strides[1] = {(cuuint64_t)d->w_ld * 2};
-    cuuint32_t box[2] = {64, 128};
+    cuuint32_t box[2] = {64, (cuuint32_t)w_box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = g_encode(&tmW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w_kmajor), dims, strides, box,
                           estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,

@@ -111,7 +111,7 @@ extern "C" int vl_debug_tma_bench(const void* base, int32_t im2col, int32_t n_im
 // ------------------------------------------------------------------------------------------------
 namespace {
 __global__ void __launch_bounds__(64, 1)
-    sync_bench_kernel(int variant, int stages, int iters, int bn, long long* out_cycles) {
+    sync_bench_kernel(int variant, int stages, int iters, int bn, int bm, long long* out_cycles) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem);
@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(64, 1)
       if (++stage == stages) { stage = 0; phase ^= 1u; }
     }
   } else {
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | (((uint32_t)bm >> 4) << 24);
     const uint64_t hi = (static_cast<uint64_t>((1024u >> 4) | (1u << 14) | (2u << 29)) << 32) | (1ull << 16);
     int stage = 0;
     uint32_t phase = 0;
@@ -180,13 +180,13 @@ __global__ void __launch_bounds__(64, 1)
 }
 }  // namespace
 
-extern "C" int vl_debug_sync_bench(int32_t variant, int32_t stages, int32_t iters, int32_t bn, int32_t grid,
+extern "C" int vl_debug_sync_bench(int32_t variant, int32_t stages, int32_t iters, int32_t bn, int32_t bm, int32_t grid,
                                    long long* out_cycles, vl_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   VL_REQUIRE(stages >= 1 && stages <= 4, "stages 1..4");
   const int smem = 2048 + stages * 49152;
   VL_CHECK_CUDA(cudaFuncSetAttribute(sync_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-  sync_bench_kernel<<<grid, 64, smem, stream>>>(variant, stages, iters, bn, out_cycles);
+  sync_bench_kernel<<<grid, 64, smem, stream>>>(variant, stages, iters, bn, bm, out_cycles);
   VL_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
