@@ -115,13 +115,13 @@ __device__ __forceinline__ void window5n(const float (&v)[NE], int l, float (&w)
 }
 
 // ------------------------------------------------------------------------------------------------
-// frames -> space-to-depth bf16.  One CTA per (frame, block row).  The S image rows are read with aligned 32-bit
-// loads (uint8 input: 4 pixels-channels per load), mean-subtracted, rounded to bf16 and written straight to their
-// permuted position of the output row in shared memory: out[bx][(dy*S+dx)*3+c] = frame[S*by-pt+dy][S*bx-pl+dx][c];
-// the finished row (wb * S*S*3 bf16, contiguous in HBM) is then copied out with 16-byte stores.
+// frames -> space-to-depth bf16.  One CTA per (frame, block row), one thread per image pixel: its 3 channels of the
+// S image rows are mean-subtracted, rounded to bf16 and written straight to their permuted position of the output
+// row in shared memory: out[bx][(dy*S+dx)*3+c] = frame[S*by-pt+dy][S*bx-pl+dx][c]; the finished row
+// (wb * S*S*3 bf16, contiguous in HBM) is then copied out with 16-byte stores.
 // ------------------------------------------------------------------------------------------------
 template <bool U8, int S>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
     frames_s2d_kernel(const void* __restrict__ frames_, const float* __restrict__ mean3, bf16* __restrict__ out, int h,
                       int w, int pad_top, int pad_left, int hb, int wb, long long total_elems) {
   extern __shared__ uint8_t smem_raw[];
@@ -136,52 +136,36 @@ __global__ void __launch_bounds__(128)
     m[1] = mean3[1];
     m[2] = mean3[2];
   }
-  const int row_elems = w * 3;
-  const int lead = pad_left * 3;
   // zero fill (SAME padding and rows outside the image)
   for (int i = threadIdx.x; i < wb * CBLK / 8; i += blockDim.x) reinterpret_cast<uint4*>(orow_s)[i] = make_uint4(0, 0, 0, 0);
   __syncthreads();
+  // one thread per image pixel x: its 3 channels of the S image rows go to block bx = (x+pad_left)/S, slot dx
+  for (int x = threadIdx.x; x < w; x += blockDim.x) {
+    const int bx = (x + pad_left) / S, dx = (x + pad_left) - bx * S;
+    bf16* dstp = orow_s + bx * CBLK + dx * 3;
 #pragma unroll
-  for (int dy = 0; dy < S; ++dy) {
-    const int y = by * S - pad_top + dy;
-    if (y < 0 || y >= h) continue;
-    const long long row_off = ((long long)nn * h + y) * row_elems;  // element offset of the image row
-    if (U8) {
-      const uint8_t* base = reinterpret_cast<const uint8_t*>(frames_);
-      const int mis = (int)((reinterpret_cast<uintptr_t>(base) + row_off) & 3);  // bytes before the row in word 0
-      const uint32_t* words = reinterpret_cast<const uint32_t*>(base + row_off - mis);
-      const int nwords = (mis + row_elems + 3) >> 2;
-      for (int wi = threadIdx.x; wi < nwords; wi += blockDim.x) {
-        uint32_t word;
-        if (row_off - mis + 4LL * (wi + 1) <= total_elems) {
-          word = __ldg(words + wi);
-        } else {  // the last word of the buffer: never read past the caller's allocation
-          word = 0;
-          for (int k = 0; k < 4; ++k) {
-            const long long o = row_off - mis + 4LL * wi + k;
-            if (o < total_elems) word |= (uint32_t)base[o] << (8 * k);
-          }
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int xe = wi * 4 + k - mis;  // x*3 + c inside the image row
-          if (xe >= 0 && xe < row_elems) {
-            const int e = xe + lead;
-            const int bx = e / SEG, r = e - bx * SEG;
-            const float v = (float)((word >> (8 * k)) & 0xffu) - m[xe % 3];
-            orow_s[bx * CBLK + dy * SEG + r] = __float2bfloat16_rn(v);
-          }
-        }
+    for (int dy = 0; dy < S; ++dy) {
+      const int y = by * S - pad_top + dy;
+      if (y < 0 || y >= h) continue;
+      const long long off = (((long long)nn * h + y) * w + x) * 3;
+      float v0, v1, v2;
+      if (U8) {
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(frames_) + off;
+        v0 = (float)__ldg(src) - m[0];
+        v1 = (float)__ldg(src + 1) - m[1];
+        v2 = (float)__ldg(src + 2) - m[2];
+      } else {
+        const float* src = reinterpret_cast<const float*>(frames_) + off;
+        v0 = __ldg(src);
+        v1 = __ldg(src + 1);
+        v2 = __ldg(src + 2);
       }
-    } else {
-      const float* src = reinterpret_cast<const float*>(frames_) + row_off;
-      for (int xe = threadIdx.x; xe < row_elems; xe += blockDim.x) {
-        const int e = xe + lead;
-        const int bx = e / SEG, r = e - bx * SEG;
-        orow_s[bx * CBLK + dy * SEG + r] = __float2bfloat16_rn(__ldg(src + xe));
-      }
+      dstp[dy * SEG] = __float2bfloat16_rn(v0);
+      dstp[dy * SEG + 1] = __float2bfloat16_rn(v1);
+      dstp[dy * SEG + 2] = __float2bfloat16_rn(v2);
     }
   }
+  (void)total_elems;
   __syncthreads();
   uint4* dst = reinterpret_cast<uint4*>(out + ((long long)nn * hb + by) * wb * CBLK);
   for (int i = threadIdx.x; i < wb * CBLK / 8; i += blockDim.x) dst[i] = reinterpret_cast<const uint4*>(orow_s)[i];
@@ -610,10 +594,10 @@ extern "C" int vl_frames_s2d(const void* frames, int32_t is_u8, const float* mea
   VL_REQUIRE(smem <= 48 * 1024, "vl_frames_s2d: image row too wide (%zu bytes of shared memory)", smem);
   const int grid = n * hb;
   if (is_u8)
-    frames_s2d_kernel<true, 4><<<grid, 128, smem, stream>>>(frames, mean3, reinterpret_cast<bf16*>(out), h, w, pad_top,
+    frames_s2d_kernel<true, 4><<<grid, 256, smem, stream>>>(frames, mean3, reinterpret_cast<bf16*>(out), h, w, pad_top,
                                                             pad_left, hb, wb, (long long)n * h * w * 3);
   else
-    frames_s2d_kernel<false, 4><<<grid, 128, smem, stream>>>(frames, mean3, reinterpret_cast<bf16*>(out), h, w, pad_top,
+    frames_s2d_kernel<false, 4><<<grid, 256, smem, stream>>>(frames, mean3, reinterpret_cast<bf16*>(out), h, w, pad_top,
                                                              pad_left, hb, wb, (long long)n * h * w * 3);
   VL_LAUNCHED();
   return 0;
@@ -709,7 +693,10 @@ extern "C" int vl_pool_lrn_bwd(const void* x, const void* dy, const void* argmax
       reinterpret_cast<bf16*>(dx), dbias, n, h, w, c, alpha, beta, bias
   (void)p;
   (void)q;
-  const long long blocks3 = (long long)n * h < (long long)vl::num_sms() * 12 ? (long long)n * h : (long long)vl::num_sms() * 12;
+  // CTAs per SM of the instantiated kernels: 12 queued (3 resident) by default; VL_LRN_BWD_CTAS=2 leaves registers
+  // for a co-resident contraction CTA of another stream
+  const int per_sm = getenv("VL_LRN_BWD_CTAS") ? atoi(getenv("VL_LRN_BWD_CTAS")) : 4;
+  const long long blocks3 = (long long)n * h < (long long)vl::num_sms() * per_sm ? (long long)n * h : (long long)vl::num_sms() * per_sm;
   if (c == 96 && h == 57 && w == 57 && !getenv("VL_LRN_BWD_V2"))  // conv1 block of the 227x227 AlexNet
     pool_lrn_bwd_kernel3<4, 3, 96, 57, 57><<<(int)blocks3, 128, 0, stream>>>(
         reinterpret_cast<const bf16*>(x), reinterpret_cast<const bf16*>(dy), reinterpret_cast<const uint8_t*>(argmax),
