@@ -46,8 +46,11 @@ enum {
   VL_A_IM2COL_MN = 3  /* A = im2col(NHWC)^T: M = (tap, channel), K = output pixels          */
 };
 enum {
-  VL_B_TILED_K = 0,  /* B stored [N][K] row-major (K contiguous)  */
-  VL_B_TILED_MN = 1  /* B stored [K][N] row-major (N contiguous)  */
+  VL_B_TILED_K = 0,   /* B stored [N][K] row-major (K contiguous)  */
+  VL_B_TILED_MN = 1,  /* B stored [K][N] row-major (N contiguous)  */
+  VL_B_IM2COL_MN = 2  /* B = im2col(NHWC)^T: N = (tap, channel chunk of 64), K = output pixels; with A = dy^T
+                         (VL_A_TILED_MN) this is the filter gradient with the output channels on the M side; C
+                         [taps*cin_g][c_ld] fp32 is written transposed (row = (tap, ci), column = group column + m) */
 };
 enum { VL_DT_BF16 = 0, VL_DT_F32 = 1 };
 

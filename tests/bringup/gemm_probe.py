@@ -51,6 +51,7 @@ for name, s in specs.items():
         wdk = torch.randn(s.cin, s.taps * kpad, device=dev).to(bf)
         cases.append((name + " dgrad FLAT", flops, lambda s=s, dy=dy, wdk=wdk, dx=dx: K.conv_dgrad_flat(s, dy, wdk, dx)))
     cases.append((name + " wgrad", flops, lambda s=s, x=x, dy=dy, dw=dw: K.conv_wgrad(s, x, dy, dw)))
+    cases.append((name + " wgrad T", flops, lambda s=s, x=x, dy=dy, dw=dw: K.conv_wgrad_t(s, x, dy, dw)))
 # dense layers
 for name, m, kk, nn in (("fc6", n, 9216, 4096), ("fc7", n, 4096, 4096)):
     x = torch.randn(m, kk, device=dev).to(bf)

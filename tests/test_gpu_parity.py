@@ -73,6 +73,10 @@ def test_conv_fwd_dgrad_wgrad_vs_oracle(vl, name, n, h, cin, cout, k, groups):
     dw = torch.zeros(k * k * (cin // groups), cout, dtype=torch.float32, device="cuda")
     K.conv_wgrad(spec, xd, dyd, dw, split_k=3)
     assert rel(dw.cpu().numpy().reshape(dw_ref.shape), dw_ref) < 1e-3  # fp32 accumulate of bf16 products
+    for split in (1, 5):  # operands swapped (output channels on M, im2col^T on N): same gradient
+        dwt = torch.zeros_like(dw)
+        K.conv_wgrad_t(spec, xd, dyd, dwt, split_k=split)
+        assert rel(dwt.cpu().numpy().reshape(dw_ref.shape), dw_ref) < 1e-3
     db = torch.zeros(cout, dtype=torch.float32, device="cuda")
     vl["nv"].call("vl_colsum", dyd, db, n * h * h, cout, cout)
     assert rel(db.cpu().numpy(), db_ref) < 1e-3
@@ -167,6 +171,9 @@ def test_conv1_space_to_depth_path_vs_oracle(vl):
     dw = torch.empty(11, 11, 3, 96, device="cuda")
     nv.call("vl_s2d_unpack_grad", dws, dw, 11, 11, 3, 96, 4)
     assert rel(dw.cpu().numpy(), dw_ref) < 1e-3
+    dws2 = torch.zeros_like(dws)
+    K.conv_wgrad_t(s1s, xs, dev(dy, torch.bfloat16), dws2)
+    assert rel(dws2.cpu().numpy(), dws.cpu().numpy()) < 1e-3
 
 
 @pytest.mark.parametrize("c", [96, 256])

@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libvlb200.so")
 
 # enums (include/vlb200.h)
 A_TILED_K, A_TILED_MN, A_IM2COL_K, A_IM2COL_MN = 0, 1, 2, 3
-B_TILED_K, B_TILED_MN = 0, 1
+B_TILED_K, B_TILED_MN, B_IM2COL_MN = 0, 1, 2
 DT_BF16, DT_F32 = 0, 1
 
 

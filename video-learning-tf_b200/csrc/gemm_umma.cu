@@ -203,8 +203,26 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
           }
         }
       }
+      int b_valid = 0;  // transposed-im2col B: 64-column chunks (tap, channel chunk) of this n-block
+      if (BMODE == VL_B_IM2COL_MN) {
+        int rem;
+        fd_divmod(t.kb_begin * BK, p.fd_PQ, pn, rem);
+        fd_divmod(rem, p.fd_Q, pp, pq);
+        const int per_blk = BN >> 6;
+        b_valid = min(per_blk, taps * cchunks - t.n_blk * per_blk);
+#pragma unroll
+        for (int j = 0; j < 2 * MAX_MSUB; ++j) {
+          if (j < b_valid) {
+            int tp, ch;
+            fd_divmod(t.n_blk * per_blk + j, p.fd_cchunks, tp, ch);
+            mn_c[j] = b_c0 + ch * BK;
+            fd_divmod(tp, p.fd_kw, mn_tr[j], mn_ts[j]);
+          }
+        }
+      }
       const uint32_t a_bytes = !ld_a ? 0u : (AM == VL_A_IM2COL_MN ? 8192u * a_valid : a_tile_bytes);
-      const uint32_t bytes = (ld_b ? (uint32_t)p.b_stage_bytes : 0u) + a_bytes;
+      const uint32_t b_bytes = !ld_b ? 0u : (BMODE == VL_B_IM2COL_MN ? 8192u * b_valid : (uint32_t)p.b_stage_bytes);
+      const uint32_t bytes = b_bytes + a_bytes;
       for (int kb = t.kb_begin; kb < t.kb_end; ++kb) {
         mbar_wait_u32(empty_u32 + stage * 8, phase ^ 1u);
         const uint32_t sA = tiles_u32 + stage * stage_bytes;
@@ -242,6 +260,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
             if (BMODE == VL_B_TILED_K) {
               const int tapb = p.flip ? (taps - 1 - tap) : tap;
               tma_load_2d_u32(sB, &tmB, fb, b_c0 + tap * p.b_tap_inner + cc * BK, b_r0 + tapb * p.b_tap_stride);
+            } else if (BMODE == VL_B_IM2COL_MN) {  // this k-block's 64 pixels start at (pn, pp, pq)
+              const int bx = pq * p.stride_w + p.lower_w, by = pp * p.stride_h + p.lower_h;
+#pragma unroll
+              for (int j = 0; j < 2 * MAX_MSUB; ++j)
+                if (j < b_valid)
+                  tma_load_im2col_4d_u32(sB + j * 8192, &tmB, fb, mn_c[j], bx, by, pn, (uint16_t)mn_ts[j],
+                                         (uint16_t)mn_tr[j]);
             } else {
               for (int j = 0; j < BN; j += 64) tma_load_2d_u32(sB + j * 128, &tmB, fb, b_c0 + n0 + j, kb * BK);
             }
@@ -249,7 +274,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
         }
         __syncwarp();
         // ---- advance the contraction walk ----
-        if (AM == VL_A_IM2COL_MN) {
+        if (AM == VL_A_IM2COL_MN || BMODE == VL_B_IM2COL_MN) {
           pq += mn_step_rem;  // advance 64 pixels = mn_step_rows rows + mn_step_rem pixels
           pp += mn_step_rows;
           if (pq >= p.Q) {
@@ -378,6 +403,24 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 
         auto process = [&](const uint32_t (&v)[16], int c0) {
           if (!row_ok || (p.dbg & 8)) return;
+          if (BMODE == VL_B_IM2COL_MN) {
+            // filter gradient with the filter taps on the N side: C[(tap, ci)][g * c_goff + row]; consecutive lanes
+            // (rows = output channels) hit consecutive addresses, so the red.adds of a warp coalesce
+            int tap, cc;
+            fd_divmod((n0 + c0) >> 6, p.fd_cchunks, tap, cc);
+            const int ci0 = cc * 64 + (c0 & 63);
+            const int ncols = (tap < p.taps) ? min(16, p.cin_g - ci0) : 0;
+            float* outp = reinterpret_cast<float*>(p.C) + ((long long)tap * p.cin_g + ci0) * p.c_ld + t.g * p.c_goff + grow;
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (j < ncols) {
+                if (p.c_atomic)
+                  atomicAdd(outp + (long long)j * p.c_ld, __uint_as_float(v[j]));
+                else
+                  outp[(long long)j * p.c_ld] = __uint_as_float(v[j]);
+              }
+            return;
+          }
           const int ncols = min(16, p.N - (n0 + c0));
           if (ncols <= 0) return;
           float f[16];
@@ -581,7 +624,8 @@ extern "C" int vl_gemm(const vl_gemm_desc* d, const void* a, const void* b, void
   memset(&p, 0, sizeof(p));
   const bool a_im2col = d->a_mode == VL_A_IM2COL_K || d->a_mode == VL_A_IM2COL_MN;
   const bool a_mn = d->a_mode == VL_A_TILED_MN || d->a_mode == VL_A_IM2COL_MN;
-  const bool b_mn = d->b_mode == VL_B_TILED_MN;
+  const bool b_mn = d->b_mode == VL_B_TILED_MN || d->b_mode == VL_B_IM2COL_MN;
+  const bool b_im2col = d->b_mode == VL_B_IM2COL_MN;
   const vl_conv_geom& cg = d->conv;
 
   p.groups = d->groups;
@@ -609,7 +653,7 @@ extern "C" int vl_gemm(const vl_gemm_desc* d, const void* a, const void* b, void
   p.N = d->n;
 
   // ---- contraction decomposition ----
-  if (a_im2col) {
+  if (a_im2col || b_im2col) {
     VL_REQUIRE(cg.kh > 0 && cg.kw > 0 && cg.p > 0 && cg.q > 0 && cg.cin_g > 0, "vl_gemm: bad conv geometry");
     p.taps = cg.kh * cg.kw;
     p.kw = cg.kw;
@@ -643,6 +687,12 @@ extern "C" int vl_gemm(const vl_gemm_desc* d, const void* a, const void* b, void
     VL_REQUIRE(!(d->b_mode == VL_B_TILED_K && (d->b_tap_stride > 0 || d->b_tap_inner > 0)),
                "vl_gemm: b_tap_stride / b_tap_inner need an im2col A operand");
   }
+  if (b_im2col) {
+    VL_REQUIRE(d->a_mode == VL_A_TILED_MN, "vl_gemm: transposed im2col B needs an M-major tiled A (dy^T)");
+    VL_REQUIRE(d->k == cg.n * cg.p * cg.q, "vl_gemm: k (%d) must equal n*p*q for transposed im2col B", d->k);
+    VL_REQUIRE(d->n == p.taps * p.cchunks * 64, "vl_gemm: n must be taps * ceil(cin_g/64) * 64 for transposed im2col B");
+    VL_REQUIRE(d->c_dtype == VL_DT_F32 && BN <= 64 * 2 * MAX_MSUB, "vl_gemm: transposed im2col B: fp32 output, block_n <= 256");
+  }
   // two 128-row sub-tiles per CTA tile when the accumulators fit (2 * BN <= 256 TMEM columns per stage) and there
   // are enough rows to keep every SM busy with the halved tile count
   p.msub = 1;
@@ -650,14 +700,17 @@ extern "C" int vl_gemm(const vl_gemm_desc* d, const void* a, const void* b, void
   VL_REQUIRE(p.msub * BN <= ACC_STRIDE_COLS, "vl_gemm: msub %d x block_n %d exceeds the TMEM accumulator stage", p.msub,
              BN);
   p.num_m_blk = ceil_div(m_rows, BM * p.msub);
+  const int conv_cchunks = p.cchunks;
   if (!a_im2col) p.cchunks = p.kb_total;  // dense k-block walk: tap = 0, cc = kb
+  if (b_im2col) p.cchunks = conv_cchunks;  // the chunk -> (tap, channel chunk) decode of the B loads / epilogue
   p.ksteps_tail = BK / 16;
   p.mma_cchunks = p.cchunks;
   if (d->a_mode == VL_A_IM2COL_K)
     p.ksteps_tail = ceil_div(cg.cin_g - (p.cchunks - 1) * 64, 16);
   else if (!a_im2col)
     p.ksteps_tail = ceil_div(d->k - (p.kb_total - 1) * BK, 16);
-  if (d->a_mode == VL_A_IM2COL_MN) {
+  if (b_im2col) p.ksteps_tail = BK / 16;
+  if (d->a_mode == VL_A_IM2COL_MN || b_im2col) {
     p.mma_cchunks = 1 << 30;  // the contraction runs over pixels: no per-tap tail
     p.mn_step_rows = BK / cg.q;
     p.mn_step_rem = BK % cg.q;
@@ -753,6 +806,8 @@ extern "C" int vl_gemm(const vl_gemm_desc* d, const void* a, const void* b, void
       outer = (long long)d->b_row_goff * (d->groups - 1) + d->n;
     }
     if (make_tiled_map(&tmB, b, inner, outer, d->b_ld, 64, BN) != 0) return -1;
+  } else if (b_im2col) {
+    if (make_im2col_map(&tmB, b, cg, 64, cg.c) != 0) return -1;
   } else {
     long long inner = (long long)d->b_goff * (d->groups - 1) + d->n;
     long long outer = (d->a_mode == VL_A_IM2COL_K) ? (long long)p.kb_total * 64 : d->k;
@@ -770,7 +825,7 @@ extern "C" int vl_gemm(const vl_gemm_desc* d, const void* a, const void* b, void
     }                                                                                                           \
     umma_gemm_kernel<AMODE, BMODE_><<<grid, NUM_THREADS, smem_bytes, stream>>>(tmA, tmB, p);                    \
   } while (0)
-  const int combo = d->a_mode * 2 + d->b_mode;
+  const int combo = b_im2col ? 100 : d->a_mode * 2 + d->b_mode;
   switch (combo) {
     case VL_A_TILED_K * 2 + VL_B_TILED_K: VL_LAUNCH_GEMM(VL_A_TILED_K, VL_B_TILED_K); break;
     case VL_A_TILED_K * 2 + VL_B_TILED_MN: VL_LAUNCH_GEMM(VL_A_TILED_K, VL_B_TILED_MN); break;
@@ -779,6 +834,7 @@ extern "C" int vl_gemm(const vl_gemm_desc* d, const void* a, const void* b, void
     case VL_A_IM2COL_K * 2 + VL_B_TILED_K: VL_LAUNCH_GEMM(VL_A_IM2COL_K, VL_B_TILED_K); break;
     case VL_A_IM2COL_K * 2 + VL_B_TILED_MN: VL_LAUNCH_GEMM(VL_A_IM2COL_K, VL_B_TILED_MN); break;
     case VL_A_IM2COL_MN * 2 + VL_B_TILED_MN: VL_LAUNCH_GEMM(VL_A_IM2COL_MN, VL_B_TILED_MN); break;
+    case 100: VL_LAUNCH_GEMM(VL_A_TILED_MN, VL_B_IM2COL_MN); break;
     default: VL_REQUIRE(false, "vl_gemm: unsupported operand mode combination a=%d b=%d", d->a_mode, d->b_mode);
   }
 #undef VL_LAUNCH_GEMM

@@ -176,6 +176,7 @@ class Engine(object):
             self.adam_v = torch.zeros(off, dtype=F32, device=self.dev)
         self._side = torch.cuda.Stream(device=self.dev)  # filter gradients (off the backward critical path)
         self._side2 = torch.cuda.Stream(device=self.dev)  # second half-batch chain of the conv1/conv2 backward
+        self._streams = (self._side, self._side2)
         self._alloc_shadows()
         self._alloc_activations()
         self.load_state_dict(params if params is not None else init_variables(cfg))
@@ -648,7 +649,7 @@ class Engine(object):
                 nv.call("vl_pool_lrn_bwd", A["a1"][lo:hi], G["dp1"][lo:hi], A["arg1"][lo:hi], G["da1"][lo:hi],
                         self.var("dcnn/conv1b", self.grads), m, s1.p, s1.q, 96, LRN["radius"], LRN["alpha"],
                         LRN["beta"], LRN["bias"])
-                K.conv_wgrad(s1s, A["x_s2d"][lo:hi], G["da1"][lo:hi], self.dws1)  # split-K atomics: halves add up
+                K.conv_wgrad_t(s1s, A["x_s2d"][lo:hi], G["da1"][lo:hi], self.dws1)  # split-K atomics: halves add up
         for ev in da2_ready:
             self._side.wait_event(ev)
         with torch.cuda.stream(self._side):
@@ -661,6 +662,15 @@ class Engine(object):
     # ------------------------------------------------------------------------------------------
     # training step
     # ------------------------------------------------------------------------------------------
+    def set_serial(self, serial):
+        """serial=True runs every kernel of the step on the caller's stream (no overlap between the backward chains):
+        used by bench.py to time each contraction launch in isolation for the roofline."""
+        if serial:
+            cur = torch.cuda.current_stream()
+            self._side, self._side2 = cur, cur
+        else:
+            self._side, self._side2 = self._streams
+
     def train_step(self, frames, onehot, lr, dropout_mask=None, apply_update=True):
         """One `sess.run([loss, lr, global_step, optimizer])` (run_task.py:44, train.py:199-222).
 

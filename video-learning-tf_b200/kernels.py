@@ -238,6 +238,29 @@ def conv_wgrad(spec, x, dy, dw, split_k=0, block_n=0, msub=0):
     return dw
 
 
+def conv_wgrad_t(spec, x, dy, dw, split_k=0, block_n=0):
+    """Same contract as conv_wgrad with the operands swapped: output channels (dy^T) on the M side, the (tap, channel
+    chunk) axis of im2col(x)^T on the N side.  Every UMMA is 128 x block_n x 16 with block_n = 192 / 256 instead of
+    a narrow cout-wide one, and the split-K red.adds of a warp coalesce."""
+    n = x.shape[0]
+    chunks = spec.taps * spec.cchunks
+    d = nv.GemmDesc()
+    d.m, d.n, d.k, d.groups = spec.cout_g, chunks * 64, n * spec.p * spec.q, spec.groups
+    d.a_mode, d.b_mode = nv.A_TILED_MN, nv.B_IM2COL_MN
+    d.a_goff, d.b_goff, d.c_goff = spec.cout_g, spec.cin_g, spec.cout_g
+    d.a_ld = spec.cout
+    d.c_ld = spec.cout
+    d.c_dtype = nv.DT_F32
+    d.c_atomic = 1
+    d.split_k = split_k
+    d.block_n = block_n or (192 if chunks % 3 == 0 else 256)
+    d.msub = 1
+    d.conv = spec.geom(n)
+    assert dw.dtype == F32
+    nv.gemm(d, dy, x, dw)
+    return dw
+
+
 def pack_conv_weight_host(spec, w_hwio):
     """HWIO fp32 -> K-major bf16 [Cout, taps*cchunks*64] with each tap's cin_g rows zero-padded to a 64 multiple
     (torch restatement of vl_pack_bf16_t, for tests and probes)."""
