@@ -44,9 +44,9 @@ for name, s in specs.items():
     cases.append((name + " fwd", flops, lambda s=s, x=x, wp=wp, b=b, y=y: K.conv_fwd(s, x, wp, b, y, relu=True)))
     if dx is not None:
         cases.append((name + " dgrad", flops, lambda s=s, dy=dy, wd=wd, dx=dx: K.conv_dgrad(s, dy, wd, dx)))
-    if s.cout_g <= 128:
+    if True:
         cases.append((name + " fwd FLAT", flops, lambda s=s, x=x, wp=wp, b=b, y=y: K.conv_fwd_flat(s, x, wp, b, y, relu=True)))
-    if dx is not None and s.cin_g <= 128:
+    if dx is not None:
         kpad = -(-s.cout_g // 64) * 64
         wdk = torch.randn(s.cin, s.taps * kpad, device=dev).to(bf)
         cases.append((name + " dgrad FLAT", flops, lambda s=s, dy=dy, wdk=wdk, dx=dx: K.conv_dgrad_flat(s, dy, wdk, dx)))

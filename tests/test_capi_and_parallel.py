@@ -89,7 +89,11 @@ def _dp_worker(rank, world, port, q):
     loss_l, g_l, logits_l = grads(x[lo:hi], y[lo:hi], parallel.local_grad_scale(hi - lo, world))
     flat = torch.from_numpy(g_l.reshape(-1).copy())
     scal = torch.tensor([float(loss_l), 0.0])
-    parallel.allreduce_gradients(flat, scal)
+    # the engine's schedule: the tail of the arena is reduced asynchronously first, the head + scalars later
+    cut = flat.numel() // 3
+    early = parallel.allreduce_async(flat[cut:])
+    parallel.allreduce_gradients(flat[:cut], scal)
+    parallel.wait(early)
     gathered = parallel.gather_logits(torch.from_numpy(logits_l))
     loss_ref, g_ref, logits_ref = grads(x, y, 1.0 / clips)
     ok = (np.allclose(flat.numpy().reshape(d, c), g_ref, atol=1e-6) and
