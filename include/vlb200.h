@@ -132,6 +132,13 @@ int vl_conv1_patches(const void* frames, int is_u8, const float* mean3, void* co
  * kh x kw stride-s SAME convolution equals a ceil(kh/s) x ceil(kw/s) stride-1 VALID convolution over s*s*3 channels. */
 int vl_frames_s2d(const void* frames, int32_t is_u8, const float* mean3, void* out, int32_t n, int32_t h, int32_t w,
                   int32_t s, int32_t pad_top, int32_t pad_left, int32_t hb, int32_t wb, vl_stream_t stream);
+/* Same staging with the reference's read-time preprocessing fused in (dataset_.py:444-461 crop_image, :498-500
+ * rand_mirror, :521-530 sub_mean): frames are stored as [n][hr][wr][3]; crops = DEVICE int32 [n][3] = (y0, x0, mirror)
+ * selects the h x w window at (y0, x0) of frame i, read right-to-left when mirror != 0.  crops may be NULL when
+ * hr == h and wr == w. */
+int vl_frames_s2d_crop(const void* frames, int32_t is_u8, const float* mean3, void* out, int32_t n, int32_t hr,
+                       int32_t wr, const int32_t* crops, int32_t h, int32_t w, int32_t s, int32_t pad_top,
+                       int32_t pad_left, int32_t hb, int32_t wb, vl_stream_t stream);
 /* Filter of that convolution: HWIO fp32 [kh][kw][cin][cout] -> bf16 [taps][chunk][cout] (chunk >= s*s*cin rows per
  * tap, zero padded), and the inverse scatter of its filter gradient dws[taps*s*s*cin][cout] -> HWIO dw. */
 int vl_s2d_pack_filter(const float* src, void* dst, int32_t kh, int32_t kw, int32_t cin, int32_t cout, int32_t s,

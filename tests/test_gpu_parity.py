@@ -176,6 +176,29 @@ def test_conv1_space_to_depth_path_vs_oracle(vl):
     assert rel(dws2.cpu().numpy(), dws.cpu().numpy()) < 1e-3
 
 
+def test_staging_with_crop_and_mirror_bit_exact(vl):
+    """vl_frames_s2d_crop == numpy crop (dataset_.py:444-461) + mirror (:498-500) + mean (:494-495) + space-to-depth."""
+    nv = vl["nv"]
+    rng = np.random.default_rng(31)
+    n, hr, wr = 5, 240, 320
+    raw = rng.integers(0, 256, size=(n, hr, wr, 3), dtype=np.uint8)
+    crops = np.stack([rng.integers(0, hr - 227, n), rng.integers(0, wr - 227, n), rng.integers(0, 2, n)], 1).astype(np.int32)
+    crops[0] = (0, 0, 0)
+    crops[1] = (hr - 227, wr - 227, 1)
+    mean = np.array([99.197148, 105.293620, 109.503945], np.float32)
+    xs = torch.empty(n, 59, 59, 48, dtype=torch.bfloat16, device="cuda")
+    nv.call("vl_frames_s2d_crop", dev(raw), 1, dev(mean), xs, n, hr, wr, dev(crops), 227, 227, 4, 4, 4, 59, 59)
+    ref = np.zeros((n, 59, 59, 48), np.float32)
+    for i, (y0, x0, mir) in enumerate(crops):
+        img = raw[i, y0:y0 + 227, x0:x0 + 227, :].astype(np.float32)
+        if mir:
+            img = img[:, ::-1, :]
+        pad = np.zeros((236, 236, 3), np.float32)
+        pad[4:231, 4:231] = img - mean
+        ref[i] = pad.reshape(59, 4, 59, 4, 3).transpose(0, 2, 1, 3, 4).reshape(59, 59, 48)
+    assert np.array_equal(xs.float().cpu().numpy(), bf16_round(ref))
+
+
 @pytest.mark.parametrize("c", [96, 256])
 def test_lrn_fwd_bwd_vs_oracle(vl, c):
     nv = vl["nv"]

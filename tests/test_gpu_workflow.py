@@ -71,3 +71,53 @@ def test_run_task_train_then_resume_then_validate(tmp_path):
     with open(tmp_path / "run" / tot, "rb") as f:
         logits = pickle.load(f)
     assert logits.shape == (5, 101) and logits.dtype == np.float32  # one fused row per video (val.py:124-137 format)
+
+
+def test_run_task_on_a_serialized_tfrecord_dataset(tmp_path):
+    """train on `<path>.tfrecord` + `<path>.size` as written by the reference's serialize.py, read without
+    TensorFlow, cropped / mirrored / mean-subtracted on the device; and the engine's forward on those batches equals
+    its forward on the numpy-preprocessed frames."""
+    import random
+    import torch
+    import vlb200  # noqa: F401
+    from vlb200 import run_task, tfrecord
+    from vlb200.defs import defs
+    from vlb200.engine import Engine, EngineConfig
+    from vlb200.feeder import Dataset
+
+    rng = np.random.default_rng(5)
+    cpv, fpc, raw_shape = [1, 2, 1], 2, (240, 250, 3)
+    base = str(tmp_path / "ucf_like")
+    with open(base + ".tfrecord", "wb") as f:
+        for v, c in enumerate(cpv):
+            for _ in range(c * fpc):
+                tfrecord.write_record(f, tfrecord.serialize_frame(rng.integers(0, 256, size=raw_shape, dtype=np.uint8), [v]))
+    tfrecord.write_size_file(base + ".size", cpv, fpc)
+
+    def mutate(run):
+        run["data"] = {"ucf": {"data_format": "defs.data_format.tfrecord", "data_path": base,
+                               "image_shape": "(227, 227, 3)", "raw_image_shape": "(240, 250, 3)",
+                               "imgproc": ["defs.imgproc.rand_crop", "defs.imgproc.rand_mirror", "defs.imgproc.sub_mean"],
+                               "mean_image": [99.197148, 105.293620, 109.503945], "num_frames_per_clip": fpc,
+                               "phase": "defs.phase.train", "tag": "defs.dataset_tag.main"}}
+        run["train"]["batch_size"] = 2
+        run["train"]["epochs"] = 1
+    run_task.main(_cfg("config2_lrcn_train.yml", tmp_path, mutate))
+    names = [l.strip() for l in open(tmp_path / "run" / "checkpoints" / "checkpoint") if l.strip()]
+    assert names and names[-1].endswith("ep_1_btch_2_gs_2.graph-2")
+
+    # device preprocessing == numpy preprocessing on the same draws
+    opts = types.SimpleNamespace(name="t", data_format=defs.data_format.tfrecord, data_path=base, image_shape=(227, 227, 3),
+                                 num_frames_per_clip=fpc, imgproc=[defs.imgproc.rand_crop, defs.imgproc.rand_mirror],
+                                 raw_image_shape=raw_shape, verify_records="full", mean_image=None)
+    ds = Dataset(opts, batch_size=3, num_classes=101, epochs=1, save_freq_per_epoch=1)
+    random.seed(9)
+    frames, onehot, _ = ds.next_batch()
+    mean = (99.197148, 105.293620, 109.503945)
+    cfg = EngineConfig(workflow="lrcn", fusion="avg", fpc=fpc, num_classes=101, lstm_hidden=256, mean=mean)
+    eng = Engine(cfg, max_clips=4)
+    got = eng.forward(frames, ds.last_crops)
+    pre = np.stack([(frames[i, y:y + 227, x:x + 227][:, ::-1] if m else frames[i, y:y + 227, x:x + 227]).astype(np.float32)
+                    - np.array(mean, np.float32) for i, (y, x, m) in enumerate(ds.last_crops)])
+    ref = eng.forward(pre)  # fp32 feed of already-preprocessed frames (feeder.py:97-100 contract)
+    assert np.array_equal(got, ref)

@@ -74,6 +74,7 @@ def _declare(L):
         "vl_maxpool_bwd": [vp, vp, vp, vp, i32, i32, i32, i32, vp],
         "vl_colsum": [vp, vp, i64, i32, i32, vp],
         "vl_frames_s2d": [vp, i32, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp],
+        "vl_frames_s2d_crop": [vp, i32, vp, vp, i32, i32, i32, vp, i32, i32, i32, i32, i32, i32, i32, vp],
         "vl_s2d_pack_filter": [vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],
         "vl_pack_bf16_t": [vp, i32, i32, vp, i32, i32, i32, vp],
         "vl_s2d_unpack_grad": [vp, vp, i32, i32, i32, i32, i32, vp],
@@ -107,7 +108,7 @@ def _declare(L):
 EXPORTS = ["vl_last_error", "vl_version", "vl_device_sm_count", "vl_launch_count", "vl_gemm", "vl_conv_flat", "vl_pack_dgrad_kmajor", "vl_conv1_patches",
            "vl_lrn_fwd", "vl_lrn_bwd", "vl_maxpool_fwd", "vl_maxpool_bwd", "vl_colsum", "vl_pack_bf16",
            "vl_cast_f32_to_bf16", "vl_transpose_f32", "vl_lstm_fwd", "vl_lstm_bwd", "vl_lrn_pool_fwd", "vl_pool_lrn_bwd",
-           "vl_lstm_fwd_cluster", "vl_lstm_bwd_cluster", "vl_frames_s2d", "vl_pack_bf16_t", "vl_s2d_pack_filter", "vl_s2d_unpack_grad",
+           "vl_lstm_fwd_cluster", "vl_lstm_bwd_cluster", "vl_frames_s2d", "vl_frames_s2d_crop", "vl_pack_bf16_t", "vl_s2d_pack_filter", "vl_s2d_unpack_grad",
            "vl_lrn_pool_fwd_generic", "vl_pool_lrn_bwd_generic", "vl_segment_pool_fwd",
            "vl_segment_pool_bwd", "vl_dropout_mask", "vl_mul", "vl_softmax_ce", "vl_grad_sqnorms",
            "vl_clip_scalars", "vl_sgd_update", "vl_adam_update"]

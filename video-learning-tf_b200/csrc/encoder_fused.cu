@@ -123,7 +123,8 @@ __device__ __forceinline__ void window5n(const float (&v)[NE], int l, float (&w)
 template <bool U8, int S>
 __global__ void __launch_bounds__(256)
     frames_s2d_kernel(const void* __restrict__ frames_, const float* __restrict__ mean3, bf16* __restrict__ out, int h,
-                      int w, int pad_top, int pad_left, int hb, int wb, long long total_elems) {
+                      int w, int pad_top, int pad_left, int hb, int wb, int hr, int wr,
+                      const int32_t* __restrict__ crops) {
   extern __shared__ uint8_t smem_raw[];
   bf16* orow_s = reinterpret_cast<bf16*>(smem_raw);  // [wb][S*S*3]
   constexpr int SEG = S * 3;                          // contiguous source elements per (bx, dy)
@@ -139,15 +140,23 @@ __global__ void __launch_bounds__(256)
   // zero fill (SAME padding and rows outside the image)
   for (int i = threadIdx.x; i < wb * CBLK / 8; i += blockDim.x) reinterpret_cast<uint4*>(orow_s)[i] = make_uint4(0, 0, 0, 0);
   __syncthreads();
+  // crop window of this frame inside the stored (hr x wr) frame and horizontal mirror (dataset_.py:444-461,498-500)
+  int y0 = 0, x0 = 0, mirror = 0;
+  if (crops != nullptr) {
+    y0 = crops[nn * 3];
+    x0 = crops[nn * 3 + 1];
+    mirror = crops[nn * 3 + 2];
+  }
   // one thread per image pixel x: its 3 channels of the S image rows go to block bx = (x+pad_left)/S, slot dx
   for (int x = threadIdx.x; x < w; x += blockDim.x) {
     const int bx = (x + pad_left) / S, dx = (x + pad_left) - bx * S;
     bf16* dstp = orow_s + bx * CBLK + dx * 3;
+    const int xs = x0 + (mirror ? (w - 1 - x) : x);
 #pragma unroll
     for (int dy = 0; dy < S; ++dy) {
       const int y = by * S - pad_top + dy;
       if (y < 0 || y >= h) continue;
-      const long long off = (((long long)nn * h + y) * w + x) * 3;
+      const long long off = (((long long)nn * hr + (y0 + y)) * wr + xs) * 3;
       float v0, v1, v2;
       if (U8) {
         const uint8_t* src = reinterpret_cast<const uint8_t*>(frames_) + off;
@@ -165,7 +174,6 @@ __global__ void __launch_bounds__(256)
       dstp[dy * SEG + 2] = __float2bfloat16_rn(v2);
     }
   }
-  (void)total_elems;
   __syncthreads();
   uint4* dst = reinterpret_cast<uint4*>(out + ((long long)nn * hb + by) * wb * CBLK);
   for (int i = threadIdx.x; i < wb * CBLK / 8; i += blockDim.x) dst[i] = reinterpret_cast<const uint4*>(orow_s)[i];
@@ -582,25 +590,33 @@ __global__ void __launch_bounds__(128)
     VL_CHECK_CUDA(cudaGetLastError()); \
   } while (0)
 
-extern "C" int vl_frames_s2d(const void* frames, int32_t is_u8, const float* mean3, void* out, int32_t n, int32_t h,
-                             int32_t w, int32_t s, int32_t pad_top, int32_t pad_left, int32_t hb, int32_t wb,
-                             vl_stream_t stream_) {
+extern "C" int vl_frames_s2d_crop(const void* frames, int32_t is_u8, const float* mean3, void* out, int32_t n,
+                                  int32_t hr, int32_t wr, const int32_t* crops, int32_t h, int32_t w, int32_t s,
+                                  int32_t pad_top, int32_t pad_left, int32_t hb, int32_t wb, vl_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   VL_REQUIRE(frames && out && hb > 0 && wb > 0, "vl_frames_s2d: bad arguments");
   VL_REQUIRE(s == 4, "vl_frames_s2d: only stride 4 (conv1, alexnet.py:76) is instantiated");
   VL_REQUIRE((wb * s * s * 3) % 8 == 0, "vl_frames_s2d: wb*s*s*3 must be a multiple of 8");
   VL_REQUIRE((w + pad_left) * 3 <= wb * s * 3, "vl_frames_s2d: image row does not fit the block row");
+  VL_REQUIRE(hr >= h && wr >= w, "vl_frames_s2d: stored frame %dx%d smaller than the network input %dx%d", hr, wr, h, w);
+  VL_REQUIRE(crops != nullptr || (hr == h && wr == w), "vl_frames_s2d: crop offsets are required when the stored frame is larger");
   const size_t smem = (size_t)wb * s * s * 3 * sizeof(bf16);
   VL_REQUIRE(smem <= 48 * 1024, "vl_frames_s2d: image row too wide (%zu bytes of shared memory)", smem);
   const int grid = n * hb;
   if (is_u8)
     frames_s2d_kernel<true, 4><<<grid, 256, smem, stream>>>(frames, mean3, reinterpret_cast<bf16*>(out), h, w, pad_top,
-                                                            pad_left, hb, wb, (long long)n * h * w * 3);
+                                                            pad_left, hb, wb, hr, wr, crops);
   else
     frames_s2d_kernel<false, 4><<<grid, 256, smem, stream>>>(frames, mean3, reinterpret_cast<bf16*>(out), h, w, pad_top,
-                                                             pad_left, hb, wb, (long long)n * h * w * 3);
+                                                             pad_left, hb, wb, hr, wr, crops);
   VL_LAUNCHED();
   return 0;
+}
+
+extern "C" int vl_frames_s2d(const void* frames, int32_t is_u8, const float* mean3, void* out, int32_t n, int32_t h,
+                             int32_t w, int32_t s, int32_t pad_top, int32_t pad_left, int32_t hb, int32_t wb,
+                             vl_stream_t stream_) {
+  return vl_frames_s2d_crop(frames, is_u8, mean3, out, n, h, w, nullptr, h, w, s, pad_top, pad_left, hb, wb, stream_);
 }
 
 extern "C" int vl_s2d_pack_filter(const float* src, void* dst, int32_t kh, int32_t kw, int32_t cin, int32_t cout,

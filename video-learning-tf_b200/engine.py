@@ -288,8 +288,8 @@ class Engine(object):
             return torch.empty(*shape, dtype=dtype, device=dev)
 
         A = {}
-        A["frames_u8"] = act(n, cfg.height, cfg.width, 3, dtype=torch.uint8)
-        A["frames_f32"] = None  # allocated lazily: only the reference-compatible fp32 feed needs it
+        self._frame_bufs = {}  # host-fed frames are staged per stored shape / dtype (allocated on first use)
+        self._crops_dev = torch.zeros(n, 3, dtype=torch.int32, device=dev)
         s1s = sp["conv1_s2d"]
         A["x_s2d"] = act(n, s1s.h, s1s.w, s1s.cin)
         A["a1"] = act(n, s1.p, s1.q, 96)
@@ -361,46 +361,65 @@ class Engine(object):
     # ------------------------------------------------------------------------------------------
     # input staging
     # ------------------------------------------------------------------------------------------
+    def _frame_buffer(self, shape_hw, dtype):
+        """Device staging buffer [max_frames, h, w, 3] for host-fed frames of one stored shape (allocated on first use)."""
+        key = (int(shape_hw[0]), int(shape_hw[1]), dtype)
+        buf = self._frame_bufs.get(key)
+        if buf is None:
+            buf = torch.empty(self.max_frames, key[0], key[1], 3, dtype=dtype, device=self.dev)
+            self._frame_bufs[key] = buf
+        return buf
+
     def _stage_frames(self, frames):
         """Accept what `feeder.get_feed_dict` produces (a list / array of float32 HWC frames, feeder.py:97-100),
-        a uint8 array (mean subtracted on device), or a device tensor.  Returns (tensor, is_u8, n_frames)."""
-        cfg = self.cfg
+        a uint8 array (mean subtracted on device), or a device tensor; frames may be stored larger than the network
+        input (raw_image_shape) when crop offsets accompany them.  Returns (device tensor, is_u8, n_frames)."""
         if isinstance(frames, (list, tuple)):
             frames = np.stack([np.asarray(f) for f in frames], axis=0)
         if isinstance(frames, np.ndarray):
-            n = frames.shape[0]
-            if n > self.max_frames:
-                raise ValueError("batch of %d frames exceeds the engine capacity %d" % (n, self.max_frames))
-            is_u8 = frames.dtype == np.uint8
-            if not is_u8:
+            if frames.dtype != np.uint8:
                 frames = np.ascontiguousarray(frames, dtype=np.float32)
-                if self.A["frames_f32"] is None:
-                    self.A["frames_f32"] = torch.empty(self.max_frames, cfg.height, cfg.width, 3, dtype=F32,
-                                                       device=self.dev)
-            key = ("u8" if is_u8 else "f32")
+            host = torch.from_numpy(np.ascontiguousarray(frames))
+            key = (tuple(host.shape[1:3]), host.dtype)
             pin = self._pinned.get(key)
             if pin is None:
-                pin = torch.empty(self.max_frames, cfg.height, cfg.width, 3,
-                                  dtype=torch.uint8 if is_u8 else F32).pin_memory()
+                pin = torch.empty(self.max_frames, host.shape[1], host.shape[2], 3, dtype=host.dtype).pin_memory()
                 self._pinned[key] = pin
-            pin[:n].copy_(torch.from_numpy(np.ascontiguousarray(frames)))
-            dst = self.A["frames_u8"] if is_u8 else self.A["frames_f32"]
-            dst[:n].copy_(pin[:n], non_blocking=True)
-            return dst[:n], is_u8, n
+            if host.shape[0] > self.max_frames:
+                raise ValueError("batch of %d frames exceeds the engine capacity %d" % (host.shape[0], self.max_frames))
+            pin[:host.shape[0]].copy_(host)
+            frames = pin[:host.shape[0]]
         assert isinstance(frames, torch.Tensor) and frames.is_contiguous() and frames.dtype in (torch.uint8, F32)
+        n = frames.shape[0]
+        if n > self.max_frames:
+            raise ValueError("batch of %d frames exceeds the engine capacity %d" % (n, self.max_frames))
         if not frames.is_cuda:
             # host tensor (ideally pinned): one asynchronous H2D copy straight into the device staging buffer
-            n = frames.shape[0]
-            if n > self.max_frames:
-                raise ValueError("batch of %d frames exceeds the engine capacity %d" % (n, self.max_frames))
-            is_u8 = frames.dtype == torch.uint8
-            if not is_u8 and self.A["frames_f32"] is None:
-                self.A["frames_f32"] = torch.empty(self.max_frames, cfg.height, cfg.width, 3, dtype=F32,
-                                                   device=self.dev)
-            dst = self.A["frames_u8"] if is_u8 else self.A["frames_f32"]
+            dst = self._frame_buffer(frames.shape[1:3], frames.dtype)
             dst[:n].copy_(frames, non_blocking=True)
-            return dst[:n], is_u8, n
-        return frames, frames.dtype == torch.uint8, frames.shape[0]
+            frames = dst[:n]
+        return frames, frames.dtype == torch.uint8, n
+
+    def _stage_crops(self, crops, frames, n):
+        """Per-frame (y0, x0, mirror) int32 triples on the device; None when the frames already have the input shape."""
+        hr, wr = int(frames.shape[1]), int(frames.shape[2])
+        if crops is None:
+            if (hr, wr) != (self.cfg.height, self.cfg.width):
+                raise ValueError("frames are stored %dx%d but the network input is %dx%d: crop offsets are required" % (
+                    hr, wr, self.cfg.height, self.cfg.width))
+            return None
+        if not isinstance(crops, torch.Tensor):
+            crops = torch.from_numpy(np.ascontiguousarray(np.asarray(crops, dtype=np.int32)))
+        if tuple(crops.shape) != (n, 3):
+            raise ValueError("crops must be int32 [%d, 3] (y0, x0, mirror), got %s" % (n, tuple(crops.shape)))
+        if not crops.is_cuda:
+            c = crops.numpy()
+            if (c[:, 0] < 0).any() or (c[:, 1] < 0).any() or (c[:, 0] + self.cfg.height > hr).any() or \
+                    (c[:, 1] + self.cfg.width > wr).any():
+                raise ValueError("crop window leaves the stored %dx%d frame" % (hr, wr))
+            self._crops_dev[:n].copy_(crops, non_blocking=True)
+            return self._crops_dev[:n]
+        return crops.to(torch.int32).contiguous()
 
     def prefetch(self, frames_pinned, onehot_pinned, slot):
         """Enqueue the H2D copy of one batch (pinned host tensors: uint8 frames [n,H,W,3], int32 one-hot [b,C]) on the
@@ -435,14 +454,15 @@ class Engine(object):
             self._mean_t = torch.tensor(m, dtype=F32, device=self.dev)
         return self._mean_t
 
-    def _encoder_fwd(self, frames, is_u8, n, training):
+    def _encoder_fwd(self, frames, is_u8, n, training, crops=None):
         A, sp, sh = self.A, self.sp, self.sh
         s1 = sp["conv1"]
         (p1h, p1w), (p2h, p2w), (p5h, p5w) = sp["pool1"], sp["pool2"], sp["pool5"]
         s1s = sp["conv1_s2d"]
         xs = A["x_s2d"][:n]
-        nv.call("vl_frames_s2d", frames, 1 if is_u8 else 0, self._mean_dev(), xs, n, self.cfg.height, self.cfg.width,
-                s1.stride, s1.pad_top, s1.pad_left, s1s.h, s1s.w)
+        nv.call("vl_frames_s2d_crop", frames, 1 if is_u8 else 0, self._mean_dev(), xs, n, int(frames.shape[1]),
+                int(frames.shape[2]), crops, self.cfg.height, self.cfg.width, s1.stride, s1.pad_top, s1.pad_left,
+                s1s.h, s1s.w)
         a1 = A["a1"][:n]
         K.conv_fwd_flat(s1s, xs, sh["conv1_fwd"], self.var("dcnn/conv1b"), a1, relu=True)  # tap-shifted kernel
         nv.call("vl_lrn_pool_fwd", a1, A["p1"][:n], A["arg1"][:n], n, s1.p, s1.q, 96, LRN["radius"], LRN["alpha"],
@@ -507,17 +527,18 @@ class Engine(object):
 
     _injected_mask = None
 
-    def forward_device(self, frames, training=False):
-        """Enqueue the forward pass; returns the device logits [clips, C] (fp32)."""
+    def forward_device(self, frames, training=False, crops=None):
+        """Enqueue the forward pass; returns the device logits [clips, C] (fp32).  `crops` (int32 [n, 3]: y0, x0, mirror)
+        applies the reference's read-time crop / mirror (dataset_.py:444-461,498-500) on the device."""
         frames, is_u8, n = self._stage_frames(frames)
         if n % self.cfg.fpc != 0:
             raise ValueError("number of frames (%d) is not a multiple of num_frames_per_clip (%d)" % (n, self.cfg.fpc))
-        feat = self._encoder_fwd(frames, is_u8, n, training)
+        feat = self._encoder_fwd(frames, is_u8, n, training, self._stage_crops(crops, frames, n))
         return self._head_fwd(feat, n, training)
 
-    def forward(self, frames):
+    def forward(self, frames, crops=None):
         """`sess.run(model.logits, fdict)` (run_task.py:95): float32 ndarray [clips, C] on the host."""
-        return self.forward_device(frames, training=False).cpu().numpy()
+        return self.forward_device(frames, training=False, crops=crops).cpu().numpy()
 
     # ------------------------------------------------------------------------------------------
     # backward
@@ -671,7 +692,7 @@ class Engine(object):
         else:
             self._side, self._side2 = self._streams
 
-    def train_step(self, frames, onehot, lr, dropout_mask=None, apply_update=True):
+    def train_step(self, frames, onehot, lr, dropout_mask=None, apply_update=True, crops=None):
         """One `sess.run([loss, lr, global_step, optimizer])` (run_task.py:44, train.py:199-222).
 
         frames: host/device frames of `clips * fpc` images; onehot: int32 [clips, C] (utils_.labels_to_one_hot).
@@ -693,7 +714,7 @@ class Engine(object):
             if lab.shape != (b, c):
                 raise ValueError("labels shape %s does not match [%d, %d]" % (lab.shape, b, c))
             A["labels"][:b].copy_(torch.from_numpy(lab), non_blocking=True)
-        feat = self._encoder_fwd(frames, is_u8, n, True)
+        feat = self._encoder_fwd(frames, is_u8, n, True, self._stage_crops(crops, frames, n))
         logits = self._head_fwd(feat, n, True)
         nv.call("vl_softmax_ce", logits, A["labels"][:b], b, c, parallel.local_grad_scale(b, self.world), A["row_loss"],
                 self.scalars[4:6], A["dlogits"][:b], A["dlogits_bf"][:b], self.c_pad)

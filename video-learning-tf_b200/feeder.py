@@ -1,12 +1,16 @@
 """Batch feeding contract of the hot path (reference: feeder.py:84-141, dataset_.py:386-420,562-613).
 
-The reference's TFRecord reader and per-image Python preprocessing are outside the hot path ("next").
 What the device path depends on is the integer contract, which this module keeps: frames ordered
-video -> clip -> frame, ONE label row per clip, whole videos per batch, `padding` always 0.  Two TF-free sources:
-`synthetic` (seeded uint8 frames, UCF101-shaped) and `npy` (a .npz with `frames` uint8 [N,H,W,3], `labels`,
-`clips_per_video`).
+video -> clip -> frame, ONE label row per clip, whole videos per batch, `padding` always 0.  Sources:
+  tfrecord   the reference's serialized datasets (`<path>.tfrecord` + `<path>.size`, serialize.py:138-151,246-256) read
+             WITHOUT TensorFlow (tfrecord.py); the read-time preprocessing of dataset_.py:481-501 is split: crop
+             offsets and mirror flags are drawn here with the reference's own RNG calls (`choice`, `randrange`), the
+             pixels are cropped / mirrored / mean-subtracted on the device by vl_frames_s2d_crop;
+  synthetic  seeded uint8 frames, UCF101-shaped;   npy   a .npz with `frames` uint8 [N,H,W,3], `labels`, `clips_per_video`.
 """
 import math
+import os
+from random import choice, randrange
 
 import numpy as np
 
@@ -38,9 +42,46 @@ class Dataset(object):
             self.frames = None
             self.rng = rng
             self.shape = (h, w, 3)
+        elif opts.data_format == defs.data_format.tfrecord:
+            from . import tfrecord
+            base = opts.data_path[:-len(".tfrecord")] if str(opts.data_path).endswith(".tfrecord") else opts.data_path
+            self.tfr_path = base + ".tfrecord"
+            if not os.path.exists(self.tfr_path):
+                error("TFRecord file path does not exist: %s" % self.tfr_path)
+            if not os.path.exists(base + ".size"):
+                error("Could not file data size file: %s" % (base + ".size"))
+            meta = tfrecord.read_size_file(base + ".size")
+            if meta["type"] != defs.input_mode.video:
+                error("Specified input mode is [%s] but the size file contains [%s]" % (defs.input_mode.video, meta["type"]))
+            self.num_items = meta["items"]
+            self.clips_per_video = [int(c) for c in meta["cpi"]]
+            if meta["fpc"] != self.fpc:
+                self.fpc = int(meta["fpc"])  # the .size file is authoritative (model.py:56-60)
+            self.frames = None
+            self.labels = None
+            self._tfrecord = tfrecord
+            self._records = None
+            self.verify = getattr(opts, "verify_records", "length")
+            self.imgproc = list(getattr(opts, "imgproc", []) or [])
+            for unsupported in (defs.imgproc.resize, defs.imgproc.raw_resize):
+                if unsupported in self.imgproc:
+                    error("imgproc %s resamples images with scipy.misc.imresize at read time; serialize the frames at "
+                          "the raw / network size instead (resampling is outside the hot path)" % unsupported)
+            self.raw_shape = tuple(getattr(opts, "raw_image_shape", None) or (h, w, 3))
+            self.crop_h = self.crop_w = None
+            if defs.imgproc.rand_crop in self.imgproc:  # dataset_.py:571-577: ranges of admissible offsets
+                self.crop_h = list(range(0, self.raw_shape[0] - h - 1))
+                self.crop_w = list(range(0, self.raw_shape[1] - w - 1))
+            elif defs.imgproc.center_crop in self.imgproc:
+                self.crop_h = int(math.floor((self.raw_shape[0] - h) / 2))
+                self.crop_w = int(math.floor((self.raw_shape[1] - w) / 2))
+            elif tuple(self.raw_shape[:2]) != (h, w):
+                error("Encountered image shape %s but desired shape is %s" % (str(self.raw_shape), str((h, w, 3))))
+            self.net_hw = (h, w)
         else:
-            error("data_format %s needs the reference's TFRecord/raw readers, which are outside the hot path "
-                  "(SURVEY 8f #1); use defs.data_format.synthetic or defs.data_format.npy" % opts.data_format)
+            error("data_format %s reads loose image files with scipy.misc.imread, which is outside the hot path; "
+                  "serialize them (tfrecord) or use defs.data_format.synthetic / npy" % opts.data_format)
+        self.last_crops = None
         if len(self.clips_per_video) != self.num_items:
             error("clips_per_video has %d entries for %d items" % (len(self.clips_per_video), self.num_items))
         self.num_batches = math.ceil(self.num_items / self.batch_size)
@@ -53,9 +94,42 @@ class Dataset(object):
 
     def rewind(self):
         self.batch_index = 0
+        self._records = None
 
     def fast_forward(self, batch_index):
+        """Resume inside an epoch (feeder.py:143-194): skip the records of the batches already consumed."""
         self.batch_index = batch_index
+        if getattr(self, "_tfrecord", None) is not None:
+            self._records = self._tfrecord.read_records(self.tfr_path, self.verify)
+            skip = int(self.clip_offsets[min(batch_index * self.batch_size, self.num_items)]) * self.fpc
+            for _ in range(skip):
+                next(self._records)
+
+    def _next_tfrecord_frames(self, n):
+        """n consecutive frames of the serialization (dataset_.py:171-217) + their crop / mirror draws."""
+        if self._records is None:
+            self._records = self._tfrecord.read_records(self.tfr_path, self.verify)
+        frames = np.empty((n,) + tuple(self.raw_shape), np.uint8)
+        labels, crops = [], np.zeros((n, 3), np.int32)
+        h, w = self.net_hw
+        for i in range(n):
+            try:
+                payload = next(self._records)
+            except StopIteration:
+                error("Encountered unexpected EOF while reading TFRecord example # %d in the batch." % i)
+            image, label = self._tfrecord.deserialize_frame(payload)
+            if image.shape != tuple(self.raw_shape):
+                error("Encountered image shape %s but the dataset declares %s" % (str(image.shape), str(self.raw_shape)))
+            frames[i] = image
+            labels.append(label)
+            # process_image (dataset_.py:481-501): crop first (choice(h) then choice(w)), mirror last
+            if defs.imgproc.rand_crop in self.imgproc:
+                crops[i, 0], crops[i, 1] = choice(self.crop_h), choice(self.crop_w)
+            elif defs.imgproc.center_crop in self.imgproc:
+                crops[i, 0], crops[i, 1] = self.crop_h, self.crop_w
+            if defs.imgproc.rand_mirror in self.imgproc:
+                crops[i, 2] = 0 if randrange(2) else 1
+        return frames, labels, crops
 
     def next_batch(self):
         lo = self.batch_index * self.batch_size
@@ -64,6 +138,14 @@ class Dataset(object):
         cpvs = self.clips_per_video[lo:hi]
         clips = int(sum(cpvs))
         n = clips * self.fpc
+        self.last_crops = None
+        if getattr(self, "_tfrecord", None) is not None:
+            frames, per_frame, self.last_crops = self._next_tfrecord_frames(n)
+            labels, f0 = [], 0
+            for c in cpvs:  # one label row per clip, from the first frame of the video (dataset_.py:400-408)
+                labels.extend([per_frame[f0]] * c)
+                f0 += c * self.fpc
+            return frames, labels_to_one_hot(labels, self.num_classes), cpvs
         if self.frames is not None:
             f0 = int(self.clip_offsets[lo]) * self.fpc
             frames = self.frames[f0:f0 + n]
@@ -89,6 +171,7 @@ class Feeder(object):
         if settings.phase not in self.datasets:
             error("No dataset declared for phase %s" % settings.phase)
         self.main = self.datasets[settings.phase][0]
+        self.last_crops = None
         info("Dataset [%s]: %d items, %d batches of %d, fpc %d" % (
             self.main.opts.name, self.main.num_items, self.main.num_batches, self.main.batch_size, self.main.fpc))
 
@@ -99,6 +182,7 @@ class Feeder(object):
         """(frames uint8 [N,H,W,3], onehot int32 [clips,C], clips-per-video of the batch, num_data, num_labels,
         padding=0) -- feeder.py:84-106 without the placeholder indirection."""
         frames, onehot, cpvs = self.main.next_batch()
+        self.last_crops = self.main.last_crops
         return frames, onehot, cpvs, len(frames), len(onehot), 0
 
     def get_num_batches(self):

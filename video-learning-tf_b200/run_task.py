@@ -34,7 +34,7 @@ def do_train(settings, train, feeder, engine):
             frames, onehot, cpvs, num_data, num_labels, padding = feeder.get_feed_dict()
             print_iter_info(settings, feeder, num_data, num_labels, padding)
             run_batch_count += 1
-            batch_loss, learning_rate, settings.global_step, acc, gnorm = train.step(frames, onehot)
+            batch_loss, learning_rate, settings.global_step, acc, gnorm = train.step(frames, onehot, feeder.last_crops)
             if min_train_loss[0] > batch_loss:
                 min_train_loss = (batch_loss, settings.global_step)
             nats = batch_loss / math.log(settings.num_classes)
@@ -69,7 +69,7 @@ def do_test(settings, val, feeder, engine):
     while feeder.loop():
         frames, onehot, cpvs, num_data, num_labels, padding = feeder.get_feed_dict()
         print_iter_info(settings, feeder, num_data, num_labels, padding)
-        logits = engine.forward(frames)
+        logits = engine.forward(frames, feeder.last_crops)
         val.process_validation_logits(logits, onehot, cpvs, settings.val.clip_fusion_method)
         val.save_validation_logits_chunk()
     val.save_validation_logits_chunk(save_all=True)
@@ -86,6 +86,8 @@ def main(init_file, device="cuda:0"):
     feeder = settings.initialize(init_file)
     cfg = settings.engine_config(feeder.main.fpc)
     mean = feeder.main.opts.mean_image
+    if feeder.main.opts.data_format == defs.data_format.tfrecord and defs.imgproc.sub_mean not in feeder.main.imgproc:
+        mean = None  # dataset_.py:494-495: the mean is subtracted only when imgproc lists sub_mean
     cfg.mean = tuple(mean) if mean is not None else None
     engine = Engine(cfg, max_clips=feeder.max_clips_per_batch(), device=device)
     if settings.should_resume():

@@ -189,6 +189,10 @@ class Settings(object):
             o.data_path = d.get("data_path")
             o.image_shape = tuple(parse_seq(d.get("image_shape", (227, 227, 3))))
             o.mean_image = d.get("mean_image")
+            o.imgproc = [defs.check(x, defs.imgproc) for x in parse_seq(d.get("imgproc") or [])]
+            raw = d.get("raw_image_shape")
+            o.raw_image_shape = tuple(parse_seq(raw)) if raw else None
+            o.verify_records = d.get("verify_records", "length")
             o.num_frames_per_clip = int(d.get("num_frames_per_clip", 16))
             o.clips_per_video = d.get("clips_per_video", 1)
             o.num_items = int(d.get("num_items", 64))
