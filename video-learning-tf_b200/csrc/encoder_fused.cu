@@ -457,7 +457,7 @@ __global__ void __launch_bounds__(256, 3)
 // Instantiated-geometry version: C_ = LPP * 8 * CPL channels, every lane live, CPL independent 16-byte loads per
 // lane in flight.  Same arithmetic as pool_lrn_bwd_kernel2.
 template <int LPP, int CPL, int C_, int H_, int W_>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)
     pool_lrn_bwd_kernel3(const bf16* __restrict__ x, const bf16* __restrict__ dy, const uint8_t* __restrict__ arg,
                          bf16* __restrict__ dx, float* __restrict__ dbias, int n, float alpha, float beta, float bias) {
   constexpr int NE = 8 * CPL;
