@@ -29,6 +29,9 @@ int vl_version(void);
 int vl_device_sm_count(void);
 /* Total number of kernel launches issued through this library since load (bench.py: gpu_launches). */
 int64_t vl_launch_count(void);
+/* cudaMemsetAsync(ptr, 0, bytes) on `stream`: the gradient arena is cleared once per step (tf.gradients starts from
+ * zero; the split-K filter gradients accumulate with red.add). */
+int vl_zero(void* ptr, int64_t bytes, vl_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Tensor-core contraction core (tcgen05.mma + TMEM accumulators + TMA operand staging).

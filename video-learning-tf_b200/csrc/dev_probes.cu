@@ -1,6 +1,6 @@
-// Development probe (not on the product path): per-SM fill rate of TMA tiled vs im2col loads as a function of box
-// rows and ring depth.  One thread per CTA issues `iters` loads into a ring of `stages` slots and waits for slot
-// reuse; the kernel reports elapsed SM cycles per CTA.
+// Development probes (NOT on the product path, not declared in include/vlb200.h): micro-benchmarks that settled design
+// questions on real hardware -- TMA fill rates, the cost of the mbarrier hand-shake and of tcgen05.mma vs tile shape,
+// and whether swizzled operands may start at arbitrary row offsets.  Driven by tests/bringup/{tma_bench,sync_bench,shift_mma}.py.
 #include "common.cuh"
 #include "../../include/vlb200.h"
 

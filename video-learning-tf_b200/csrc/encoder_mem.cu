@@ -743,15 +743,19 @@ extern "C" int vl_maxpool_bwd(const void* dy, const void* argmax, void* dx, cons
 extern "C" int vl_colsum(const void* dy, float* out, int64_t rows, int32_t c, int32_t ld, vl_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   VL_REQUIRE(dy && out && rows > 0 && c > 0 && ld >= c, "vl_colsum: bad arguments");
-  if (c % 8 == 0 && ld % 8 == 0 && c / 8 <= COLSUM_THREADS && (reinterpret_cast<uintptr_t>(dy) & 15) == 0) {
-    const int lanes = COLSUM_THREADS / (c / 8);
-    long long blocks = (long long)vl::num_sms() * 8;
-    long long rpb = (rows + blocks - 1) / blocks;
-    if (rpb < 4LL * lanes) rpb = 4LL * lanes;
-    blocks = (rows + rpb - 1) / rpb;
-    colsum_vec_kernel<<<(int)blocks, COLSUM_THREADS, 0, stream>>>(reinterpret_cast<const bf16*>(dy), out, rows, c, ld,
-                                                                  rpb);
-    VL_LAUNCHED();
+  if (c % 8 == 0 && ld % 8 == 0 && (reinterpret_cast<uintptr_t>(dy) & 15) == 0) {
+    // wide matrices (fc layers: 4096 columns) go through in column blocks of up to 2048
+    for (int c0 = 0; c0 < c; c0 += 2048) {
+      const int cb = c - c0 < 2048 ? c - c0 : 2048;
+      const int lanes = COLSUM_THREADS / (cb / 8);  // cb / 8 <= 256
+      long long blocks = (long long)vl::num_sms() * 8;
+      long long rpb = (rows + blocks - 1) / blocks;
+      if (rpb < 4LL * lanes) rpb = 4LL * lanes;
+      blocks = (rows + rpb - 1) / rpb;
+      colsum_vec_kernel<<<(int)blocks, COLSUM_THREADS, 0, stream>>>(reinterpret_cast<const bf16*>(dy) + c0, out + c0,
+                                                                    rows, cb, ld, rpb);
+      VL_LAUNCHED();
+    }
     return 0;
   }
   int ct = (c + 1) / 2;

@@ -37,3 +37,9 @@ extern "C" const char* vl_last_error(void) { return vl::last_error(); }
 extern "C" int vl_version(void) { return 100; }
 extern "C" int vl_device_sm_count(void) { return vl::num_sms(); }
 extern "C" int64_t vl_launch_count(void) { return vl::g_launches.load(); }
+
+extern "C" int vl_zero(void* ptr, int64_t bytes, vl_stream_t stream_) {
+  VL_REQUIRE(ptr != nullptr && bytes >= 0, "vl_zero: bad arguments");
+  VL_CHECK_CUDA(cudaMemsetAsync(ptr, 0, (size_t)bytes, reinterpret_cast<cudaStream_t>(stream_)));
+  return 0;
+}

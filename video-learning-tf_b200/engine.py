@@ -718,7 +718,7 @@ class Engine(object):
         logits = self._head_fwd(feat, n, True)
         nv.call("vl_softmax_ce", logits, A["labels"][:b], b, c, parallel.local_grad_scale(b, self.world), A["row_loss"],
                 self.scalars[4:6], A["dlogits"][:b], A["dlogits_bf"][:b], self.c_pad)
-        self.grads_ext.zero_()
+        nv.call("vl_zero", self.grads_ext, self.grads_ext.numel() * 4)
         dfeat = self._head_bwd(n)
         self._encoder_bwd(dfeat, n)
         if self.world > 1:
