@@ -656,9 +656,12 @@ extern "C" int vl_lrn_pool_fwd(const void* x, void* y, void* argmax, int32_t n, 
   VL_REQUIRE(radius == 2 && beta == 0.75f, "vl_lrn_pool_fwd: fused path serves depth_radius 2, beta 0.75 (alexnet.py:80-89)");
   const int p = (h - 3) / 2 + 1, q = (w - 3) / 2 + 1;
   const size_t row_bytes = (size_t)w * c * sizeof(bf16);
+  // strip height: small strips -> more CTAs (warps) per SM to hide the load latency, at the price of re-evaluating
+  // the LRN of the rows shared by neighbouring strips
+  const size_t strip_limit = (getenv("VL_LRN_STRIP_KB") ? atoi(getenv("VL_LRN_STRIP_KB")) : 100) * 1024;
   int rows_out = 0;
   for (int r = 1; r <= p; ++r)
-    if ((size_t)(2 * r + 1) * row_bytes <= 100 * 1024) rows_out = r;
+    if ((size_t)(2 * r + 1) * row_bytes <= strip_limit) rows_out = r;
   if (c > 256 || rows_out == 0)
     return vl_lrn_pool_fwd_generic(x, y, argmax, n, h, w, c, radius, alpha, beta, bias, stream_);
   const int strips = (p + rows_out - 1) / rows_out;
