@@ -424,7 +424,7 @@ def _problem(cfg_kwargs, clips, seed=21):
     params = E.init_variables(cfg, seed=seed)
     rng = np.random.default_rng(seed + 1)
     # unit-range pixels keep the sigma=0.05 random init out of gate saturation (see tests/test_oracle.py)
-    frames = rng.uniform(-1, 1, size=(clips * cfg.fpc, 227, 227, 3)).astype(np.float32)
+    frames = rng.uniform(-1, 1, size=(clips * cfg.fpc, cfg.height, cfg.width, 3)).astype(np.float32)
     labels = rng.integers(0, cfg.num_classes, clips)
     onehot = np.zeros((clips, cfg.num_classes), np.int32)
     onehot[np.arange(clips), labels] = 1
@@ -464,6 +464,8 @@ def test_forward_logits_and_labels_vs_oracle(vl, kw):
     (dict(workflow="lrcn", fusion="avg", fpc=4, num_classes=101, lstm_hidden=256, clip_norm=10), "sgd"),
     (dict(workflow="lrcn", fusion="last", fpc=2, num_classes=11, lstm_hidden=64, lstm_layers=2, clip_norm=None), "adam"),
     (dict(workflow="singleframe", fusion="avg", fpc=2, num_classes=101, clip_norm=10), "sgd"),
+    # a non-AlexNet-default input size: the generic (runtime-geometry) LRN / pooling / convolution paths
+    (dict(workflow="lrcn", fusion="avg", fpc=2, num_classes=23, lstm_hidden=256, clip_norm=10, height=131, width=147), "sgd"),
 ])
 def test_train_step_vs_oracle(vl, kw, opt):
     E = vl["E"]
