@@ -141,7 +141,7 @@ def run_reference_arm(args):
         "cpu_baseline": {"value": value, "unit": "clips/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -308,12 +308,34 @@ def run_ours(args):
                      "share_of_step": gemm_ms / ms_step},
         "cpu_baseline": cpu,
     }
-    print(json.dumps(out), flush=True)
+    emit(out)
     if world > 1:
         dist.destroy_process_group()
 
 
+_JSON_FD = None
+
+
+def _reserve_stdout():
+    """stdout must carry exactly ONE JSON line: libraries (NCCL prints its version banner to stdout when NCCL_DEBUG is
+    set on the box) are redirected to stderr, the JSON line is written to the original stdout at the end."""
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, line)
+
+
 def main():
+    _reserve_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
