@@ -94,8 +94,10 @@ __device__ __forceinline__ FTile decode(const FParams& p, int tile) {
 __global__ void __launch_bounds__(NUM_THREADS, 1)
     conv_flat_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                      const __grid_constant__ FParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  // the 1024-byte alignment is applied to the __shared__ array itself so that the compiler keeps the shared address
+  // space (LDS/STS instead of generic LD/ST)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* w_full = reinterpret_cast<uint64_t*>(smem);
   uint64_t* w_empty = w_full + MAX_W_STAGES;
   uint64_t* x_full = w_empty + MAX_W_STAGES;

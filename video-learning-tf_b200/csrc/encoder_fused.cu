@@ -30,6 +30,25 @@ struct alignas(16) Bf16x8 {
   __nv_bfloat162 v[4];
 };
 
+// 16-byte accesses are spelled through uint4: a plain copy of the 4 x bf16x2 struct compiles to four 32-bit LDG/STG
+// (LDS/STS) instructions, i.e. 4x the LSU wavefronts.
+__device__ __forceinline__ Bf16x8 ld8(const void* p) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  Bf16x8 r;
+  r.v[0] = *reinterpret_cast<const __nv_bfloat162*>(&u.x);
+  r.v[1] = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
+  r.v[2] = *reinterpret_cast<const __nv_bfloat162*>(&u.z);
+  r.v[3] = *reinterpret_cast<const __nv_bfloat162*>(&u.w);
+  return r;
+}
+__device__ __forceinline__ void st8(void* p, const Bf16x8& v) {
+  uint4 u;
+  u.x = *reinterpret_cast<const uint32_t*>(&v.v[0]);
+  u.y = *reinterpret_cast<const uint32_t*>(&v.v[1]);
+  u.z = *reinterpret_cast<const uint32_t*>(&v.v[2]);
+  u.w = *reinterpret_cast<const uint32_t*>(&v.v[3]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
 __device__ __forceinline__ void unpack8(const Bf16x8& in, float (&f)[8]) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -125,7 +144,7 @@ __global__ void __launch_bounds__(256)
     frames_s2d_kernel(const void* __restrict__ frames_, const float* __restrict__ mean3, bf16* __restrict__ out, int h,
                       int w, int pad_top, int pad_left, int hb, int wb, int hr, int wr,
                       const int32_t* __restrict__ crops) {
-  extern __shared__ uint8_t smem_raw[];
+  extern __shared__ __align__(16) uint8_t smem_raw[];
   bf16* orow_s = reinterpret_cast<bf16*>(smem_raw);  // [wb][S*S*3]
   constexpr int SEG = S * 3;                          // contiguous source elements per (bx, dy)
   constexpr int CBLK = S * S * 3;
@@ -231,7 +250,7 @@ template <int LPP, int CPL>
 __global__ void __launch_bounds__(512)
     lrn_pool_fwd_kernel2(const bf16* __restrict__ x, bf16* __restrict__ y, uint8_t* __restrict__ arg, int h, int w, int c,
                          int p, int q, int rows_out, int strips, float alpha, float bias) {
-  extern __shared__ uint8_t smem_raw[];
+  extern __shared__ __align__(16) uint8_t smem_raw[];
   bf16* tile = reinterpret_cast<bf16*>(smem_raw);  // [(2*rows_out+1)][w][c]
   constexpr int NE = 8 * CPL;                      // channels per lane; LPP * NE == c (host guarantees it)
   const int strip = blockIdx.x % strips;
@@ -254,7 +273,7 @@ __global__ void __launch_bounds__(512)
     if (live) {
       Bf16x8 in[CPL];
 #pragma unroll
-      for (int k = 0; k < CPL; ++k) in[k] = *reinterpret_cast<const Bf16x8*>(xin + (long long)pix * c + l * NE + 8 * k);
+      for (int k = 0; k < CPL; ++k) in[k] = ld8(xin + (long long)pix * c + l * NE + 8 * k);
 #pragma unroll
       for (int k = 0; k < CPL; ++k) {
         float t8[8];
@@ -279,7 +298,7 @@ __global__ void __launch_bounds__(512)
           const float rs = rsqrt_approx(fmaf(alpha, ssum[8 * k + j], bias));
           o[j] = v[8 * k + j] * (rs * sqrt_approx(rs));
         }
-        *reinterpret_cast<Bf16x8*>(tile + pix * c + l * NE + 8 * k) = pack8(o);
+        st8(tile + pix * c + l * NE + 8 * k, pack8(o));
       }
     }
   }
@@ -304,7 +323,7 @@ __global__ void __launch_bounds__(512)
     for (int r = 0; r < 3; ++r) {
 #pragma unroll
       for (int s2 = 0; s2 < 3; ++s2) {
-        const Bf16x8 v = *reinterpret_cast<const Bf16x8*>(wbase + (r * w + s2) * c);
+        const Bf16x8 v = ld8(wbase + (r * w + s2) * c);
         const uint32_t code2 = (uint32_t)(r * 3 + s2) * 0x00010001u;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -319,7 +338,7 @@ __global__ void __launch_bounds__(512)
     Bf16x8 o;
 #pragma unroll
     for (int i = 0; i < 4; ++i) o.v[i] = best[i];
-    *reinterpret_cast<Bf16x8*>(y + opix * c + ch * 8) = o;
+    st8(y + opix * c + ch * 8, o);
     const uint32_t lo = __byte_perm(bidx[0], bidx[1], 0x6420);
     const uint32_t hi = __byte_perm(bidx[2], bidx[3], 0x6420);
     *reinterpret_cast<uint2*>(arg + opix * c + ch * 8) = make_uint2(lo, hi);
@@ -370,7 +389,7 @@ __global__ void __launch_bounds__(256, 3)
 #pragma unroll
       for (int j = 0; j < 8; ++j) xv[j] = gv[j] = 0.f;
       if (live) {
-        const Bf16x8 xin = *reinterpret_cast<const Bf16x8*>(xrow + ww * c + c0);
+        const Bf16x8 xin = ld8(xrow + ww * c + c0);
         // dn: pooled gradient routed through the argmax codes, accumulated two channels per instruction in bf16
         // (exact for up to two contributions; the unfused path rounds the fp32 sum to bf16 once)
         __nv_bfloat162 g2[4];
@@ -434,7 +453,7 @@ __global__ void __launch_bounds__(256, 3)
           out[j] = xv[j] > 0.f ? g : 0.f;  // ReLU gradient of the producing conv
         }
         const Bf16x8 packed = pack8(out);
-        *reinterpret_cast<Bf16x8*>(dxrow + ww * c + c0) = packed;
+        st8(dxrow + ww * c + c0, packed);
         if (dbias != nullptr) {
           float rb[8];
           unpack8(packed, rb);  // the bias gradient sums the bf16 values that are stored (as vl_colsum would)
@@ -495,7 +514,7 @@ __global__ void __launch_bounds__(128, 4)
       if (live) {
         Bf16x8 xin[CPL];
 #pragma unroll
-        for (int k = 0; k < CPL; ++k) xin[k] = *reinterpret_cast<const Bf16x8*>(xrow + ww * c + c0 + 8 * k);
+        for (int k = 0; k < CPL; ++k) xin[k] = ld8(xrow + ww * c + c0 + 8 * k);
         __nv_bfloat162 g2[4 * CPL];
 #pragma unroll
         for (int i = 0; i < 4 * CPL; ++i) g2[i] = __floats2bfloat162_rn(0.f, 0.f);
@@ -563,7 +582,7 @@ __global__ void __launch_bounds__(128, 4)
             out[j] = xv[e] > 0.f ? g : 0.f;  // ReLU gradient of the producing conv
           }
           const Bf16x8 packed = pack8(out);
-          *reinterpret_cast<Bf16x8*>(dxrow + ww * c + c0 + 8 * k) = packed;
+          st8(dxrow + ww * c + c0 + 8 * k, packed);
           if (dbias != nullptr) {
             float rb[8];
             unpack8(packed, rb);  // the bias gradient sums the bf16 values that are stored (as vl_colsum would)

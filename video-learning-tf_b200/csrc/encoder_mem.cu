@@ -21,6 +21,25 @@ struct alignas(16) Bf16x8 {
   __nv_bfloat162 v[4];
 };
 
+// 16-byte accesses are spelled through uint4: a plain copy of the 4 x bf16x2 struct compiles to four 32-bit LDG/STG
+// (LDS/STS) instructions, i.e. 4x the LSU wavefronts.
+__device__ __forceinline__ Bf16x8 ld8(const void* p) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  Bf16x8 r;
+  r.v[0] = *reinterpret_cast<const __nv_bfloat162*>(&u.x);
+  r.v[1] = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
+  r.v[2] = *reinterpret_cast<const __nv_bfloat162*>(&u.z);
+  r.v[3] = *reinterpret_cast<const __nv_bfloat162*>(&u.w);
+  return r;
+}
+__device__ __forceinline__ void st8(void* p, const Bf16x8& v) {
+  uint4 u;
+  u.x = *reinterpret_cast<const uint32_t*>(&v.v[0]);
+  u.y = *reinterpret_cast<const uint32_t*>(&v.v[1]);
+  u.z = *reinterpret_cast<const uint32_t*>(&v.v[2]);
+  u.w = *reinterpret_cast<const uint32_t*>(&v.v[3]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
 __device__ __forceinline__ void unpack8(const Bf16x8& in, float (&f)[8]) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -47,7 +66,7 @@ __global__ void __launch_bounds__(256)
     conv1_patches_kernel(const void* __restrict__ frames_, const float* __restrict__ mean3, bf16* __restrict__ col,
                          int h, int w, int kh, int kw, int stride, int pad_top, int pad_left, int p, int q, int k_ld,
                          int pitch) {
-  extern __shared__ uint8_t smem_raw[];
+  extern __shared__ __align__(16) uint8_t smem_raw[];
   bf16* rows = reinterpret_cast<bf16*>(smem_raw);                       // [kh][pitch]
   uint16_t* koff = reinterpret_cast<uint16_t*>(rows + kh * pitch);     // [k_ld]
   const int pp = blockIdx.x % p;
@@ -130,7 +149,7 @@ __global__ void lrn_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ y,
     for (int j = 0; j < 16; ++j) v[j] = 0.f;
     {
       float own[8];
-      unpack8(*reinterpret_cast<const Bf16x8*>(xr + c0), own);
+      unpack8(ld8(xr + c0), own);
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[4 + j] = own[j];
     }
@@ -151,7 +170,7 @@ __global__ void lrn_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ y,
       const float s = bias + alpha * acc;
       out[j] = v[4 + j] * pow_neg_beta(s, beta);
     }
-    *reinterpret_cast<Bf16x8*>(y + row * c + c0) = pack8(out);
+    st8(y + row * c + c0, pack8(out));
   }
 }
 
@@ -174,10 +193,10 @@ __global__ void lrn_bwd_kernel(const bf16* __restrict__ x, const bf16* __restric
     for (int j = 0; j < 12; ++j) gv[j] = 0.f;
     {
       float own[8];
-      unpack8(*reinterpret_cast<const Bf16x8*>(xr + c0), own);
+      unpack8(ld8(xr + c0), own);
 #pragma unroll
       for (int j = 0; j < 8; ++j) xv[4 + j] = own[j];
-      unpack8(*reinterpret_cast<const Bf16x8*>(gr + c0), own);
+      unpack8(ld8(gr + c0), own);
 #pragma unroll
       for (int j = 0; j < 8; ++j) gv[2 + j] = own[j];
     }
@@ -213,7 +232,7 @@ __global__ void lrn_bwd_kernel(const bf16* __restrict__ x, const bf16* __restric
       if (relu_mask && !(xv[4 + j] > 0.f)) g = 0.f;
       out[j] = g;
     }
-    *reinterpret_cast<Bf16x8*>(dx + row * c + c0) = pack8(out);
+    st8(dx + row * c + c0, pack8(out));
   }
 }
 
@@ -244,7 +263,7 @@ __global__ void maxpool_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict_
       for (int s = 0; s < 3; ++s) {
         const bf16* src = x + (((long long)nn * h + (pp * 2 + r)) * w + (qq * 2 + s)) * c + c0;
         float v[8];
-        unpack8(*reinterpret_cast<const Bf16x8*>(src), v);
+        unpack8(ld8(src), v);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           if (v[j] > best[j]) {  // strict: the first maximum in (h, w) scan order wins, like TF
@@ -254,7 +273,7 @@ __global__ void maxpool_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict_
         }
       }
     }
-    *reinterpret_cast<Bf16x8*>(y + pix * c + c0) = pack8(best);
+    st8(y + pix * c + c0, pack8(best));
     if (arg != nullptr) {
       uint32_t lo = bi[0] | (bi[1] << 8) | (bi[2] << 16) | (bi[3] << 24);
       uint32_t hi = bi[4] | (bi[5] << 8) | (bi[6] << 16) | (bi[7] << 24);
@@ -289,7 +308,7 @@ __global__ void maxpool_bwd_kernel(const bf16* __restrict__ dy, const uint8_t* _
         const long long opix = ((long long)nn * p + pp) * q + qq;
         const uint2 a = *reinterpret_cast<const uint2*>(arg + opix * c + c0);
         float g[8];
-        unpack8(*reinterpret_cast<const Bf16x8*>(dy + opix * c + c0), g);
+        unpack8(ld8(dy + opix * c + c0), g);
         const uint32_t code = r * 3 + s;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -300,12 +319,12 @@ __global__ void maxpool_bwd_kernel(const bf16* __restrict__ dy, const uint8_t* _
     }
     if (relu_of != nullptr) {
       float m[8];
-      unpack8(*reinterpret_cast<const Bf16x8*>(relu_of + pix * c + c0), m);
+      unpack8(ld8(relu_of + pix * c + c0), m);
 #pragma unroll
       for (int j = 0; j < 8; ++j)
         if (!(m[j] > 0.f)) acc[j] = 0.f;
     }
-    *reinterpret_cast<Bf16x8*>(dx + pix * c + c0) = pack8(acc);
+    st8(dx + pix * c + c0, pack8(acc));
   }
 }
 
@@ -318,7 +337,7 @@ __global__ void maxpool_bwd_kernel(const bf16* __restrict__ dy, const uint8_t* _
 __device__ __forceinline__ void load_window16(const bf16* __restrict__ row, int c0, int c, float (&v)[16]) {
   // channels [c0-4, c0+12) of one pixel, zero outside [0, c)
   float t[8];
-  unpack8(*reinterpret_cast<const Bf16x8*>(row + c0), t);
+  unpack8(ld8(row + c0), t);
 #pragma unroll
   for (int j = 0; j < 8; ++j) v[4 + j] = t[j];
   if (c0 >= 8) {
@@ -381,7 +400,7 @@ __global__ void lrn_pool_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict
         }
       }
     }
-    *reinterpret_cast<Bf16x8*>(y + pix * c + c0) = pack8(best);
+    st8(y + pix * c + c0, pack8(best));
     uint32_t lo = bi[0] | (bi[1] << 8) | (bi[2] << 16) | (bi[3] << 24);
     uint32_t hi = bi[4] | (bi[5] << 8) | (bi[6] << 16) | (bi[7] << 24);
     *reinterpret_cast<uint2*>(arg + pix * c + c0) = make_uint2(lo, hi);
@@ -424,7 +443,7 @@ __global__ void pool_lrn_bwd_kernel(const bf16* __restrict__ x, const bf16* __re
         const uint8_t* ap = arg + opix * c;
         const bf16* gp = dy + opix * c;
         float g[8];
-        unpack8(*reinterpret_cast<const Bf16x8*>(gp + c0), g);
+        unpack8(ld8(gp + c0), g);
         const uint2 a = *reinterpret_cast<const uint2*>(ap + c0);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -476,7 +495,7 @@ __global__ void pool_lrn_bwd_kernel(const bf16* __restrict__ x, const bf16* __re
       out[j] = g;
     }
     const Bf16x8 packed = pack8(out);
-    *reinterpret_cast<Bf16x8*>(dx + pix * c + c0) = packed;
+    st8(dx + pix * c + c0, packed);
     if (dbias != nullptr) {
       float rb[8];
       unpack8(packed, rb);  // the bias gradient sums the bf16 values that are stored (as vl_colsum would)
@@ -518,7 +537,7 @@ __global__ void __launch_bounds__(COLSUM_THREADS)
     for (; r + 3LL * lanes < r1; r += 4LL * lanes) {
       Bf16x8 v[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const Bf16x8*>(base + (r + (long long)u * lanes) * ld);
+      for (int u = 0; u < 4; ++u) v[u] = ld8(base + (r + (long long)u * lanes) * ld);
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         float f[8];
@@ -529,7 +548,7 @@ __global__ void __launch_bounds__(COLSUM_THREADS)
     }
     for (; r < r1; r += lanes) {
       float f[8];
-      unpack8(*reinterpret_cast<const Bf16x8*>(base + r * ld), f);
+      unpack8(ld8(base + r * ld), f);
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[j] += f[j];
     }
@@ -625,7 +644,7 @@ __global__ void cast_bf16_kernel(const float* __restrict__ src, bf16* __restrict
     const float4 a = reinterpret_cast<const float4*>(src)[2 * idx];
     const float4 b = reinterpret_cast<const float4*>(src)[2 * idx + 1];
     float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-    reinterpret_cast<Bf16x8*>(dst)[idx] = pack8(f);
+    st8(reinterpret_cast<Bf16x8*>(dst) + idx, pack8(f));
   }
   if (blockIdx.x == 0 && threadIdx.x == 0)
     for (long long i = n8 << 3; i < n; ++i) dst[i] = __float2bfloat16_rn(src[i]);

@@ -100,9 +100,10 @@ template <int AM, int BMODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
     umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ KParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  // 128B swizzle atoms need 1024B-aligned tiles.
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  // 128B swizzle atoms need 1024B-aligned tiles.  The offset is applied to the __shared__ array itself (not through an
+  // integer round trip) so that the compiler keeps the shared address space: LDS/STS instead of generic LD/ST.
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* tiles = smem + BAR_REGION;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem);
   uint64_t* empty_bar = full_bar + MAX_STAGES;
