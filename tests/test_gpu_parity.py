@@ -305,7 +305,10 @@ def test_fused_lrn_pool_matches_unfused_and_oracle(vl, h, c):
     dn_ref = O.bf16_round(O.maxpool_3x3s2_backward(x.shape, a0.cpu().numpy().astype(np.int64), dy))
     dx_ref = O.lrn_backward(x, dn_ref) * (x > 0)
     assert rel(dx1.float().cpu().numpy(), dx_ref) < 1e-2
-    assert rel(db.cpu().numpy(), dx1.float().cpu().numpy().reshape(-1, c).sum(0)) < 1e-4
+    # the bias gradient sums the fp32 values before their bf16 rounding (closer to the reference's fp32 BiasAddGrad than
+    # the sum of the stored bf16 values): the two differ by the rounding noise of n*h*w terms
+    assert rel(db.cpu().numpy(), dx1.float().cpu().numpy().reshape(-1, c).sum(0)) < 5e-3
+    assert rel(db.cpu().numpy(), dx_ref.reshape(-1, c).sum(0)) < 5e-3
 
 
 def test_segment_pool_bit_exact_vs_numpy(vl):

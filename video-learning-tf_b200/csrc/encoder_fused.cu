@@ -601,6 +601,363 @@ __global__ void __launch_bounds__(128, 4)
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Fourth generation of the fused backward: uniform control flow and a packed pooled-gradient gather.
+//
+// A thread owns NE channels of a 2x2 PIXEL BLOCK (rows 2j, 2j+1 x columns 2b, 2b+1), LPP lanes hold the block's channel
+// axis, a CTA walks (frame, row pair) units.  A 3x3/2 pooling window (p, q) covers rows 2p..2p+2 / columns 2q..2q+2,
+// so the four pixels of a block see a FIXED list of windows and window positions:
+//     (2j  , 2b  ): (j-1,b-1) code 8, (j-1,b) 6, (j,b-1) 2, (j,b) 0
+//     (2j  , 2b+1): (j-1,b) 7, (j,b) 1           (2j+1, 2b  ): (j,b-1) 5, (j,b) 3           (2j+1, 2b+1): (j,b) 4
+// i.e. every lane of every warp runs the same unrolled sequence (the per-pixel loops of the earlier kernels ran 1 or 2
+// iterations depending on the column parity of the lane).  Windows outside the pooled tensor keep a clamped address and
+// a code that never matches.  The gather itself works on bf16 pairs: the argmax byte b of a channel becomes the
+// half-word b << 8 (one PRMT per pair; as bf16 these are distinct finite numbers), HSET2.EQ against the window
+// position yields 1.0 / 0.0 and one HFMA2 accumulates dy — 2 instructions per channel pair and window instead of 3.5.
+// The ReLU mask (x > 0) is applied to the gathered gradient in the packed domain; with dn = 0 every other term of the
+// LRN gradient vanishes too because x = 0 there.
+// ------------------------------------------------------------------------------------------------
+template <int NE>
+__device__ __forceinline__ void load_pairs(const bf16* __restrict__ p, uint32_t (&r)[NE / 2]) {
+  if constexpr (NE % 8 == 0) {
+#pragma unroll
+    for (int k = 0; k < NE / 8; ++k) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(p) + k);
+      r[4 * k] = u.x, r[4 * k + 1] = u.y, r[4 * k + 2] = u.z, r[4 * k + 3] = u.w;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < NE / 4; ++k) {
+      const uint2 u = __ldg(reinterpret_cast<const uint2*>(p) + k);
+      r[2 * k] = u.x, r[2 * k + 1] = u.y;
+    }
+  }
+}
+template <int NE>
+__device__ __forceinline__ void store_pairs(bf16* __restrict__ p, const uint32_t (&r)[NE / 2]) {
+  if constexpr (NE % 8 == 0) {
+#pragma unroll
+    for (int k = 0; k < NE / 8; ++k)
+      reinterpret_cast<uint4*>(p)[k] = make_uint4(r[4 * k], r[4 * k + 1], r[4 * k + 2], r[4 * k + 3]);
+  } else {
+#pragma unroll
+    for (int k = 0; k < NE / 4; ++k) reinterpret_cast<uint2*>(p)[k] = make_uint2(r[2 * k], r[2 * k + 1]);
+  }
+}
+template <int NE>
+__device__ __forceinline__ void load_bytes(const uint8_t* __restrict__ p, uint32_t (&r)[NE / 4]) {
+  if constexpr (NE % 16 == 0) {
+#pragma unroll
+    for (int k = 0; k < NE / 16; ++k) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(p) + k);
+      r[4 * k] = u.x, r[4 * k + 1] = u.y, r[4 * k + 2] = u.z, r[4 * k + 3] = u.w;
+    }
+  } else if constexpr (NE % 8 == 0) {
+#pragma unroll
+    for (int k = 0; k < NE / 8; ++k) {
+      const uint2 u = __ldg(reinterpret_cast<const uint2*>(p) + k);
+      r[2 * k] = u.x, r[2 * k + 1] = u.y;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < NE / 4; ++k) r[k] = __ldg(reinterpret_cast<const uint32_t*>(p) + k);
+  }
+}
+__device__ __forceinline__ uint32_t heq2_one(uint32_t a, uint32_t b) {  // 1.0 / 0.0 per bf16 half
+  uint32_t d;
+  asm("set.eq.bf16x2.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+__device__ __forceinline__ uint32_t hfma2_u(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t d;
+  asm("fma.rn.bf16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+__device__ __forceinline__ uint32_t hgt2_mask_zero(uint32_t a) {  // 0xffff per bf16 half that is > 0
+  uint32_t d;
+  asm("set.gt.u32.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(0u));
+  return d;
+}
+
+// One pixel of the block: NWIN windows (pooled-gradient / argmax pointers already offset to the lane's channels).
+template <int NE, int LPP, int NWIN>
+__device__ __forceinline__ void bwd_pixel4(const bf16* __restrict__ xp, bf16* __restrict__ dxp, bool live,
+                                           const bf16* const (&gp)[4], const uint8_t* const (&ap)[4],
+                                           const uint32_t (&code2)[4], int l, float alpha, float bias, float k2ab,
+                                           float (&bacc)[NE]) {
+  uint32_t xr[NE / 2];
+  if (live) {
+    load_pairs<NE>(xp, xr);
+  } else {
+#pragma unroll
+    for (int i = 0; i < NE / 2; ++i) xr[i] = 0u;
+  }
+  uint32_t dn2[NE / 2];
+#pragma unroll
+  for (int i = 0; i < NE / 2; ++i) dn2[i] = 0u;
+#pragma unroll
+  for (int wi = 0; wi < NWIN; ++wi) {
+    uint32_t g[NE / 2], a[NE / 4];
+    load_pairs<NE>(gp[wi], g);
+    load_bytes<NE>(ap[wi], a);
+#pragma unroll
+    for (int k = 0; k < NE / 4; ++k) {
+      const uint32_t h_lo = __byte_perm(a[k], 0u, 0x1404);  // (b0 << 8, b1 << 8)
+      const uint32_t h_hi = __byte_perm(a[k], 0u, 0x3424);  // (b2 << 8, b3 << 8)
+      dn2[2 * k] = hfma2_u(heq2_one(h_lo, code2[wi]), g[2 * k], dn2[2 * k]);
+      dn2[2 * k + 1] = hfma2_u(heq2_one(h_hi, code2[wi]), g[2 * k + 1], dn2[2 * k + 1]);
+    }
+  }
+  float xv[NE], av[NE];
+#pragma unroll
+  for (int i = 0; i < NE / 2; ++i) {
+    const uint32_t d = dn2[i] & hgt2_mask_zero(xr[i]);  // ReLU gradient of the producing conv
+    xv[2 * i] = __uint_as_float(xr[i] << 16);
+    xv[2 * i + 1] = __uint_as_float(xr[i] & 0xffff0000u);
+    av[2 * i] = __uint_as_float(d << 16);
+    av[2 * i + 1] = __uint_as_float(d & 0xffff0000u);
+  }
+  float sq[NE], ssum[NE];
+#pragma unroll
+  for (int j = 0; j < NE; ++j) sq[j] = xv[j] * xv[j];
+  window5n<LPP, NE>(sq, l, ssum);
+  float tt[NE], tsum[NE];
+#pragma unroll
+  for (int j = 0; j < NE; ++j) {
+    const float rs = rsqrt_approx(fmaf(alpha, ssum[j], bias));  // s^-1/2
+    const float pw = rs * sqrt_approx(rs);                      // s^-3/4
+    av[j] *= pw;                                                // dn * s^-beta
+    tt[j] = av[j] * (xv[j] * (rs * rs));                        // dn * x * s^(-beta-1)
+  }
+  window5n<LPP, NE>(tt, l, tsum);
+  uint32_t o[NE / 2];
+#pragma unroll
+  for (int i = 0; i < NE / 2; ++i) {
+    const float d0 = fmaf(-(k2ab * xv[2 * i]), tsum[2 * i], av[2 * i]);
+    const float d1 = fmaf(-(k2ab * xv[2 * i + 1]), tsum[2 * i + 1], av[2 * i + 1]);
+    bacc[2 * i] += d0;
+    bacc[2 * i + 1] += d1;
+    const __nv_bfloat162 pk = __floats2bfloat162_rn(d0, d1);
+    o[i] = *reinterpret_cast<const uint32_t*>(&pk);
+  }
+  if (live) store_pairs<NE>(dxp, o);
+}
+
+template <int NE, int LPP, int C_, int H_, int W_, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
+    pool_lrn_bwd_kernel4(const bf16* __restrict__ x, const bf16* __restrict__ dy, const uint8_t* __restrict__ arg,
+                         bf16* __restrict__ dx, float* __restrict__ dbias, int n, float alpha, float bias) {
+  constexpr int P = (H_ - 3) / 2 + 1, Q = (W_ - 3) / 2 + 1;
+  constexpr int JP = (H_ + 1) / 2, CP = (W_ + 1) / 2;  // row pairs per frame, column pairs per row
+  static_assert(LPP * NE == C_, "lanes x channels per lane must cover the channel axis exactly");
+  static_assert((THREADS / LPP) >= CP, "a CTA must hold one row of pixel blocks");
+  __shared__ float bsum[C_];
+  const int l = threadIdx.x % LPP;
+  const int b = threadIdx.x / LPP;
+  const int c0 = l * NE;
+  if (dbias != nullptr) {
+    for (int i = threadIdx.x; i < C_; i += THREADS) bsum[i] = 0.f;
+    __syncthreads();
+  }
+  float bacc[NE];
+#pragma unroll
+  for (int j = 0; j < NE; ++j) bacc[j] = 0.f;
+  const float k2ab = 2.0f * alpha * 0.75f;
+  const int col0 = 2 * b, col1 = 2 * b + 1;
+  const bool live0 = col0 < W_, live1 = col1 < W_;
+  // pooled columns of the block: b-1 (window column 2) and b (window columns 0 / 1)
+  const bool qa_ok = b >= 1 && b - 1 < Q, qb_ok = b < Q;
+  const int qa = min(max(b - 1, 0), Q - 1), qb = min(b, Q - 1);
+  constexpr uint32_t DEAD = 0xFF00FF00u;
+#define VL_CODE2(k) ((uint32_t)(k) * 0x01000100u)
+  const int units = n * JP;
+  for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
+    const int nn = unit / JP;
+    const int j = unit - nn * JP;
+    const int row0 = 2 * j, row1 = 2 * j + 1;
+    const bool pa_ok = j >= 1 && j - 1 < P, pb_ok = j < P;  // pooled rows j-1 (window row 2) and j (rows 0 / 1)
+    const int pa = min(max(j - 1, 0), P - 1), pb = min(j, P - 1);
+    const long long pooled = (long long)nn * (P * Q * C_) + c0;
+    const int o_aa = (pa * Q + qa) * C_, o_ab = (pa * Q + qb) * C_, o_ba = (pb * Q + qa) * C_, o_bb = (pb * Q + qb) * C_;
+    const bf16* g_aa = dy + pooled + o_aa;
+    const bf16* g_ab = dy + pooled + o_ab;
+    const bf16* g_ba = dy + pooled + o_ba;
+    const bf16* g_bb = dy + pooled + o_bb;
+    const uint8_t* a_aa = arg + pooled + o_aa;
+    const uint8_t* a_ab = arg + pooled + o_ab;
+    const uint8_t* a_ba = arg + pooled + o_ba;
+    const uint8_t* a_bb = arg + pooled + o_bb;
+    const long long r0 = ((long long)nn * H_ + row0) * (W_ * C_) + c0;
+    {  // (row0, col0): four windows
+      const bf16* const gp[4] = {g_aa, g_ab, g_ba, g_bb};
+      const uint8_t* const ap[4] = {a_aa, a_ab, a_ba, a_bb};
+      const uint32_t cd[4] = {pa_ok && qa_ok ? VL_CODE2(8) : DEAD, pa_ok && qb_ok ? VL_CODE2(6) : DEAD,
+                              pb_ok && qa_ok ? VL_CODE2(2) : DEAD, pb_ok && qb_ok ? VL_CODE2(0) : DEAD};
+      bwd_pixel4<NE, LPP, 4>(x + r0 + col0 * C_, dx + r0 + col0 * C_, live0, gp, ap, cd, l, alpha, bias, k2ab, bacc);
+    }
+    {  // (row0, col1): two windows
+      const bf16* const gp[4] = {g_ab, g_bb, g_bb, g_bb};
+      const uint8_t* const ap[4] = {a_ab, a_bb, a_bb, a_bb};
+      const uint32_t cd[4] = {pa_ok && qb_ok ? VL_CODE2(7) : DEAD, pb_ok && qb_ok ? VL_CODE2(1) : DEAD, DEAD, DEAD};
+      bwd_pixel4<NE, LPP, 2>(x + r0 + col1 * C_, dx + r0 + col1 * C_, live1, gp, ap, cd, l, alpha, bias, k2ab, bacc);
+    }
+    if (row1 < H_) {  // uniform per CTA
+      const long long r1 = r0 + (W_ * C_);
+      {  // (row1, col0): two windows
+        const bf16* const gp[4] = {g_ba, g_bb, g_bb, g_bb};
+        const uint8_t* const ap[4] = {a_ba, a_bb, a_bb, a_bb};
+        const uint32_t cd[4] = {pb_ok && qa_ok ? VL_CODE2(5) : DEAD, pb_ok && qb_ok ? VL_CODE2(3) : DEAD, DEAD, DEAD};
+        bwd_pixel4<NE, LPP, 2>(x + r1 + col0 * C_, dx + r1 + col0 * C_, live0, gp, ap, cd, l, alpha, bias, k2ab, bacc);
+      }
+      {  // (row1, col1): one window
+        const bf16* const gp[4] = {g_bb, g_bb, g_bb, g_bb};
+        const uint8_t* const ap[4] = {a_bb, a_bb, a_bb, a_bb};
+        const uint32_t cd[4] = {pb_ok && qb_ok ? VL_CODE2(4) : DEAD, DEAD, DEAD, DEAD};
+        bwd_pixel4<NE, LPP, 1>(x + r1 + col1 * C_, dx + r1 + col1 * C_, live1, gp, ap, cd, l, alpha, bias, k2ab, bacc);
+      }
+    }
+  }
+#undef VL_CODE2
+  if (dbias != nullptr) {
+    // dead lanes (blocks beyond the last column pair) accumulated exact zeros: x = 0 -> dn masked -> dx = 0
+#pragma unroll
+    for (int j = 0; j < NE; ++j) atomicAdd(&bsum[c0 + j], bacc[j]);
+    __syncthreads();
+    for (int i = threadIdx.x; i < C_; i += THREADS) atomicAdd(dbias + i, bsum[i]);
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Third generation of the fused forward: a CTA streams the input rows of one (frame, segment of pooled rows) through a
+// ring of five row slots in shared memory.  Iteration p normalises input rows 2p+1 and 2p+2 (row 2p is left over from
+// iteration p-1), one barrier, then pools output row p from rows 2p..2p+2; the rows of iteration p+1 land in the two
+// slots last read by iteration p-1, so one barrier per iteration is enough.  Every input row of a segment is
+// normalised exactly once (the strip kernel re-evaluated 1 row in 9), the geometry is a compile-time constant (no
+// index divisions), the x rows of the next iteration are fetched into registers before the pooling step, and with
+// 55-72 KB per CTA three to four CTAs per SM interleave their MUFU-heavy and ALU-heavy steps.
+// ------------------------------------------------------------------------------------------------
+template <int NE, int LPP, int C_, int H_, int W_, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
+    lrn_pool_fwd_kernel3(const bf16* __restrict__ x, bf16* __restrict__ y, uint8_t* __restrict__ arg, int n, int seg_rows,
+                         int segs, float alpha, float bias) {
+  constexpr int P = (H_ - 3) / 2 + 1, Q = (W_ - 3) / 2 + 1;
+  constexpr int RING = 5;
+  constexpr int ROW = W_ * C_;                       // elements per image row
+  constexpr int GROUPS = THREADS / LPP;              // pixels normalised per pass
+  constexpr int PASSES = (2 * W_ + GROUPS - 1) / GROUPS;  // passes over a pair of rows
+  constexpr int CPR = C_ / 8;                        // 16-byte chunks per pixel
+  constexpr int POOL_TASKS = Q * CPR;
+  static_assert(LPP * NE == C_ && NE % 8 == 0, "lanes x channels per lane must cover the channel axis exactly");
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  bf16* ring = reinterpret_cast<bf16*>(smem_raw);  // [RING][W][C]
+  const int l = threadIdx.x % LPP;
+  const int grp = threadIdx.x / LPP;
+  const int units = n * segs;
+  for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
+    const int nn = unit / segs;
+    const int sg = unit - nn * segs;
+    const int p0 = sg * seg_rows;
+    const int p1 = min(P, p0 + seg_rows);
+    const bf16* ximg = x + (long long)nn * (H_ * ROW) + l * NE;
+    // normalise `cnt` consecutive input rows starting at row `r0` from registers `xr` into ring slots starting at `s0`
+    uint32_t xr[PASSES][NE / 2];
+    auto fetch = [&](int r0, int cnt) {
+#pragma unroll
+      for (int ps = 0; ps < PASSES; ++ps) {
+        const int pix = ps * GROUPS + grp;
+        if (pix < cnt * W_) {
+          load_pairs<NE>(ximg + (long long)r0 * ROW + pix * C_, xr[ps]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < NE / 2; ++i) xr[ps][i] = 0u;
+        }
+      }
+    };
+    auto normalise = [&](int s0, int cnt) {
+#pragma unroll
+      for (int ps = 0; ps < PASSES; ++ps) {
+        const int pix = ps * GROUPS + grp;
+        float v[NE], sq[NE], ssum[NE];
+#pragma unroll
+        for (int i = 0; i < NE / 2; ++i) {
+          v[2 * i] = __uint_as_float(xr[ps][i] << 16);
+          v[2 * i + 1] = __uint_as_float(xr[ps][i] & 0xffff0000u);
+        }
+#pragma unroll
+        for (int j = 0; j < NE; ++j) sq[j] = v[j] * v[j];
+        window5n<LPP, NE>(sq, l, ssum);
+        uint32_t o[NE / 2];
+#pragma unroll
+        for (int i = 0; i < NE / 2; ++i) {
+          const float r0s = rsqrt_approx(fmaf(alpha, ssum[2 * i], bias));
+          const float r1s = rsqrt_approx(fmaf(alpha, ssum[2 * i + 1], bias));
+          const __nv_bfloat162 pk =
+              __floats2bfloat162_rn(v[2 * i] * (r0s * sqrt_approx(r0s)), v[2 * i + 1] * (r1s * sqrt_approx(r1s)));
+          o[i] = *reinterpret_cast<const uint32_t*>(&pk);
+        }
+        if (pix < cnt * W_) {
+          const int rr = pix >= W_ ? 1 : 0;  // which of the (up to) two rows
+          int slot = s0 + rr;
+          if (slot >= RING) slot -= RING;
+          store_pairs<NE>(ring + slot * ROW + (pix - rr * W_) * C_ + l * NE, o);
+        }
+      }
+    };
+    __syncthreads();  // the previous unit's pooling reads are finished
+    int slot_top = 0;  // ring slot of input row 2p
+    fetch(2 * p0, 1);
+    normalise(0, 1);
+    fetch(2 * p0 + 1, 2);
+    for (int p = p0; p < p1; ++p) {
+      int s1 = slot_top + 1;
+      if (s1 >= RING) s1 -= RING;
+      normalise(s1, 2);  // rows 2p+1, 2p+2
+      if (p + 1 < p1) fetch(2 * p + 3, 2);
+      __syncthreads();
+      int s2 = s1 + 1;
+      if (s2 >= RING) s2 -= RING;
+      const bf16* rows3[3] = {ring + slot_top * ROW, ring + s1 * ROW, ring + s2 * ROW};
+      for (int t = threadIdx.x; t < POOL_TASKS; t += THREADS) {
+        const int ch = t % CPR;
+        const int qq = t / CPR;
+        uint32_t best[4], bidx[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          best[i] = 0xFF80FF80u;  // (-inf, -inf)
+          bidx[i] = 0;
+        }
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          const bf16* rp = rows3[r] + (2 * qq) * C_ + ch * 8;
+#pragma unroll
+          for (int s2c = 0; s2c < 3; ++s2c) {
+            const uint4 vv = *reinterpret_cast<const uint4*>(rp + s2c * C_);
+            const uint32_t v4[4] = {vv.x, vv.y, vv.z, vv.w};
+            const uint32_t code2 = (uint32_t)(r * 3 + s2c) * 0x00010001u;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              // strict >: the first maximum in (h, w) scan order wins, like TF
+              uint32_t m, mx;
+              asm("set.gt.u32.bf16x2 %0, %1, %2;" : "=r"(m) : "r"(v4[i]), "r"(best[i]));
+              asm("max.bf16x2 %0, %1, %2;" : "=r"(mx) : "r"(best[i]), "r"(v4[i]));
+              best[i] = mx;
+              bidx[i] = (bidx[i] & ~m) | (code2 & m);
+            }
+          }
+        }
+        const long long opix = ((long long)nn * P + p) * Q + qq;
+        *reinterpret_cast<uint4*>(y + opix * C_ + ch * 8) = make_uint4(best[0], best[1], best[2], best[3]);
+        const uint32_t lo = __byte_perm(bidx[0], bidx[1], 0x6420);
+        const uint32_t hi = __byte_perm(bidx[2], bidx[3], 0x6420);
+        *reinterpret_cast<uint2*>(arg + opix * C_ + ch * 8) = make_uint2(lo, hi);
+      }
+      slot_top = s2;
+    }
+  }
+}
+
 }  // namespace
 
 #define VL_LAUNCHED()                  \
@@ -681,6 +1038,46 @@ extern "C" int vl_lrn_pool_fwd(const void* x, void* y, void* argmax, int32_t n, 
   int rows_out = 0;
   for (int r = 1; r <= p; ++r)
     if ((size_t)(2 * r + 1) * row_bytes <= strip_limit) rows_out = r;
+  // third generation (row ring, compile-time geometry): the two AlexNet instances
+  if (!getenv("VL_LRN_FWD_V2") && ((c == 96 && h == 57 && w == 57) || (c == 256 && h == 28 && w == 28))) {
+    const int ring_bytes = 5 * (int)row_bytes;
+    const int per_sm_smem = (227 * 1024) / (ring_bytes + 1024);
+    const int per_sm = per_sm_smem < 3 ? per_sm_smem : 3;  // 80 registers x 256 threads: three CTAs per SM
+    const long long resident = (long long)vl::num_sms() * per_sm;
+    // segments per frame: balance the waves against the one re-normalised row per extra segment
+    int best_segs = 1;
+    double best_eff = 0.0;
+    for (int sgs = 1; sgs <= 4; ++sgs) {
+      const int sr = (p + sgs - 1) / sgs;
+      const int real = (p + sr - 1) / sr;
+      const long long units = (long long)n * real;
+      const long long waves = (units + resident - 1) / resident;
+      const double eff = (double)units / (double)(waves * resident) * (2.0 * p + 1) / (2.0 * p + real);
+      if (eff > best_eff + 1e-9) best_eff = eff, best_segs = real;
+    }
+    const int seg_rows = (p + best_segs - 1) / best_segs;
+    const long long units = (long long)n * best_segs;
+    const int g = (int)(units < resident ? units : resident);
+#define VL_FWD3_LAUNCH(NE_, LPP_, C__, H__, W__, T_, MB_)                                                                 \
+  do {                                                                                                                \
+    static bool attr = false;                                                                                         \
+    if (!attr) {                                                                                                      \
+      VL_CHECK_CUDA(cudaFuncSetAttribute(lrn_pool_fwd_kernel3<NE_, LPP_, C__, H__, W__, T_, MB_>,                          \
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, ring_bytes));                   \
+      attr = true;                                                                                                    \
+    }                                                                                                                 \
+    lrn_pool_fwd_kernel3<NE_, LPP_, C__, H__, W__, T_, MB_><<<g, T_, ring_bytes, stream>>>(                                \
+        reinterpret_cast<const bf16*>(x), reinterpret_cast<bf16*>(y), reinterpret_cast<uint8_t*>(argmax), n, seg_rows, \
+        best_segs, alpha, bias);                                                                                      \
+  } while (0)
+    if (c == 96)
+      VL_FWD3_LAUNCH(24, 4, 96, 57, 57, 256, 3);
+    else
+      VL_FWD3_LAUNCH(16, 16, 256, 28, 28, 256, 3);
+#undef VL_FWD3_LAUNCH
+    VL_LAUNCHED();
+    return 0;
+  }
   if (c > 256 || rows_out == 0)
     return vl_lrn_pool_fwd_generic(x, y, argmax, n, h, w, c, radius, alpha, beta, bias, stream_);
   const int strips = (p + rows_out - 1) / rows_out;
@@ -735,6 +1132,40 @@ extern "C" int vl_pool_lrn_bwd(const void* x, const void* dy, const void* argmax
   // for a co-resident contraction CTA of another stream
   const int per_sm = getenv("VL_LRN_BWD_CTAS") ? atoi(getenv("VL_LRN_BWD_CTAS")) : 4;
   const long long blocks3 = (long long)n * h < (long long)vl::num_sms() * per_sm ? (long long)n * h : (long long)vl::num_sms() * per_sm;
+  // fourth generation (2x2 pixel blocks, uniform control flow): the two AlexNet geometries, beta = 0.75
+  const int v4 = getenv("VL_LRN_BWD_V4") ? atoi(getenv("VL_LRN_BWD_V4")) : 2;
+  if (v4 && beta == 0.75f && c == 96 && h == 57 && w == 57) {
+    const long long units = (long long)n * 29;
+    if (v4 == 2) {
+      const long long g = units < (long long)vl::num_sms() * 4 ? units : (long long)vl::num_sms() * 4;
+      pool_lrn_bwd_kernel4<12, 8, 96, 57, 57, 256, 2><<<(int)g, 256, 0, stream>>>(
+          reinterpret_cast<const bf16*>(x), reinterpret_cast<const bf16*>(dy), reinterpret_cast<const uint8_t*>(argmax),
+          reinterpret_cast<bf16*>(dx), dbias, n, alpha, bias);
+    } else {
+      const long long g = units < (long long)vl::num_sms() * 8 ? units : (long long)vl::num_sms() * 8;
+      pool_lrn_bwd_kernel4<24, 4, 96, 57, 57, 128, 4><<<(int)g, 128, 0, stream>>>(
+          reinterpret_cast<const bf16*>(x), reinterpret_cast<const bf16*>(dy), reinterpret_cast<const uint8_t*>(argmax),
+          reinterpret_cast<bf16*>(dx), dbias, n, alpha, bias);
+    }
+    VL_LAUNCHED();
+    return 0;
+  }
+  if (v4 && beta == 0.75f && c == 256 && h == 28 && w == 28) {
+    const long long units = (long long)n * 14;
+    if (v4 == 2) {
+      const long long g = units < (long long)vl::num_sms() * 4 ? units : (long long)vl::num_sms() * 4;
+      pool_lrn_bwd_kernel4<8, 32, 256, 28, 28, 448, 1><<<(int)g, 448, 0, stream>>>(
+          reinterpret_cast<const bf16*>(x), reinterpret_cast<const bf16*>(dy), reinterpret_cast<const uint8_t*>(argmax),
+          reinterpret_cast<bf16*>(dx), dbias, n, alpha, bias);
+    } else {
+      const long long g = units < (long long)vl::num_sms() * 6 ? units : (long long)vl::num_sms() * 6;
+      pool_lrn_bwd_kernel4<16, 16, 256, 28, 28, 224, 2><<<(int)g, 224, 0, stream>>>(
+          reinterpret_cast<const bf16*>(x), reinterpret_cast<const bf16*>(dy), reinterpret_cast<const uint8_t*>(argmax),
+          reinterpret_cast<bf16*>(dx), dbias, n, alpha, bias);
+    }
+    VL_LAUNCHED();
+    return 0;
+  }
   if (c == 96 && h == 57 && w == 57 && !getenv("VL_LRN_BWD_V2"))  // conv1 block of the 227x227 AlexNet
     pool_lrn_bwd_kernel3<4, 3, 96, 57, 57><<<(int)blocks3, 128, 0, stream>>>(
         reinterpret_cast<const bf16*>(x), reinterpret_cast<const bf16*>(dy), reinterpret_cast<const uint8_t*>(argmax),
