@@ -248,6 +248,7 @@ def run_ours(args):
     peak_tf, peak_hbm, peak_src = measured_peaks()
     # every rank runs this extra step (the train step all-reduces); rank 0's events are the ones reported
     spans = []
+    labels = []
     orig, orig_flat = nv.gemm, nv.conv_flat
 
     def timed_call(fn):
@@ -257,6 +258,12 @@ def run_ours(args):
             fn(*a, **k)
             e.record()
             spans.append((s, e))
+            d = a[0]
+            if hasattr(d, "m"):
+                labels.append("gemm a%d b%d m=%d n=%d k=%d g=%d%s" % (d.a_mode, d.b_mode, d.m, d.n, d.k, d.groups,
+                                                                     " d2s" if d.d2s_c else ""))
+            else:
+                labels.append("conv_flat %dx%dx%d k%dx%d cout_g=%d g=%d" % (d.h, d.w, d.c, d.kh, d.kw, d.cout_g, d.groups))
         return wrapper
     nv.gemm, nv.conv_flat = timed_call(orig), timed_call(orig_flat)
     eng.set_serial(True)  # one stream: each launch is timed alone (co-running kernels would stretch the spans)
@@ -267,6 +274,9 @@ def run_ours(args):
         nv.gemm, nv.conv_flat = orig, orig_flat
         eng.set_serial(False)
     gemm_ms = sum(s.elapsed_time(e) for s, e in spans)
+    if rank == 0:  # per-launch list of the contraction kernels (stderr: stdout carries exactly one JSON line)
+        for (s_, e_), lab in zip(spans, labels):
+            sys.stderr.write("contraction %8.1f us  %s\n" % (s_.elapsed_time(e_) * 1e3, lab))
     n_gemm = len(spans)
     barrier()
 

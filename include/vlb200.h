@@ -85,6 +85,11 @@ typedef struct vl_gemm_desc {
   int32_t msub;          /* 128-row sub-tiles per CTA tile: 0 = choose, 1, or 2 (needs 2*block_n <= 256)   */
   int32_t block_n;       /* 0 = choose; else multiple of 16 in [16,256]                             */
   int32_t mask_ld;       /* row pitch of relu_mask                                                  */
+  /* depth-to-space epilogue (d2s_c > 0; data gradient of a stride-1 convolution issued as a stride-(sh,sw)
+   * forward convolution over dy, see vl_pack_dgrad_d2s): row (n,Y,X) of the p x q grid, column (dy,dx,ch) of
+   * group g -> C[n][sh*Y+dy][sw*X+dx][g*c_goff + ch] of an NHWC tensor [n][d2s_h][d2s_w][c_ld]; rows / columns
+   * beyond d2s_h / d2s_w are dropped.  d2s_c % 16 == 0. */
+  int32_t d2s_sh, d2s_sw, d2s_c, d2s_h, d2s_w;
   vl_conv_geom conv;     /* used when a_mode is an im2col mode                                      */
 } vl_gemm_desc;
 
@@ -116,6 +121,15 @@ int vl_conv_flat(const vl_conv_flat_desc* desc, const void* x, const void* w_kma
  * cout_g rounded up to 64; src = HWIO fp32 as 2-D [taps*cin_g][groups*cout_g]. */
 int vl_pack_dgrad_kmajor(const float* src, void* dst, int32_t taps, int32_t cin_g, int32_t cout_g, int32_t groups,
                          vl_stream_t stream);
+/* K-major filter of the depth-to-space data gradient of a stride-1 convolution (conv2: 5x5, 48 -> 128 per group).
+ * din[sh*Y+dy][sw*X+dx][c] = sum over the (kh+sh-1) x (kw+sw-1) taps (ty,tx) of a stride-(sh,sw) walk over dout and over
+ * the cout_g channels k of  dout[sh*Y-(kh-1-pad_top)+ty][sw*X-(kw-1-pad_left)+tx][k] * W[kh-1+dy-ty][kw-1+dx-tx][c][k]
+ * (zero where the filter index leaves [0,kh) x [0,kw)), so that one 128 x (sh*sw*cin_g) x 16 UMMA tile does the work of
+ * sh*sw narrow (N = cin_g) tiles.  src = HWIO fp32 [kh][kw][cin_g][groups*cout_g];
+ * dst = bf16 [groups*sh*sw*cin_g][(kh+sh-1)*(kw+sw-1)*kpad], kpad = cout_g rounded up to 64,
+ * row = g*sh*sw*cin_g + (dy*sw+dx)*cin_g + c, column = (ty*(kw+sw-1)+tx)*kpad + k. */
+int vl_pack_dgrad_d2s(const float* src, void* dst, int32_t kh, int32_t kw, int32_t cin_g, int32_t cout_g, int32_t groups,
+                      int32_t sh, int32_t sw, vl_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Memory-bound kernels of the AlexNet encoder (HBM roofline).

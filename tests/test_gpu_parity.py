@@ -130,6 +130,41 @@ def test_tap_shifted_conv_fwd_dgrad_vs_oracle(vl, name, n, h, cin, cout, k, grou
     assert rel(dx.float().cpu().numpy(), dx_ref) < BF16_TOL
 
 
+@pytest.mark.parametrize("name,n,h,cin,cout,k,groups,sh,sw", [
+    ("conv2 2x2", 3, 28, 96, 256, 5, 2, 2, 2), ("conv2 1x2", 2, 28, 96, 256, 5, 2, 1, 2),
+    ("odd extent", 2, 9, 32, 64, 3, 1, 2, 2), ("conv5 2x1", 2, 13, 384, 256, 3, 2, 2, 1)])
+def test_depth_to_space_dgrad_vs_oracle(vl, name, n, h, cin, cout, k, groups, sh, sw):
+    """Data gradient of a stride-1 convolution as a stride-(sh,sw) forward convolution over dy with a depth-to-space
+    epilogue (vl_pack_dgrad_d2s + vl_gemm d2s_*): same result as conv2d_backprop_input, also where h % sh != 0."""
+    nv, K = vl["nv"], vl["K"]
+    rng = np.random.default_rng(23)
+    x = bf16_round(rng.standard_normal((n, h, h, cin)))
+    w = bf16_round(rng.standard_normal((k, k, cin // groups, cout)) * 0.05)
+    dy = bf16_round(rng.standard_normal((n, h, h, cout)))
+    dx_ref, _, _ = O.conv2d_same_backward(x, w, dy, 1, groups)
+    spec = K.ConvSpec(h, h, cin, cout, k, k, 1, groups)
+    rows, cols = K.d2s_filter_shape(spec, sh, sw)
+    wd = torch.empty(rows, cols, dtype=torch.bfloat16, device="cuda")
+    nv.call("vl_pack_dgrad_d2s", dev(w), wd, k, k, spec.cin_g, spec.cout_g, groups, sh, sw)
+    # the packed operand against its definition (include/vlb200.h)
+    kpad = -(-spec.cout_g // 64) * 64
+    ref = np.zeros((groups, sh, sw, spec.cin_g, k + sh - 1, k + sw - 1, kpad), np.float32)
+    for g in range(groups):
+        for dyy in range(sh):
+            for dxx in range(sw):
+                for ty in range(k + sh - 1):
+                    for tx in range(k + sw - 1):
+                        r, q = k - 1 + dyy - ty, k - 1 + dxx - tx
+                        if 0 <= r < k and 0 <= q < k:
+                            ref[g, dyy, dxx, :, ty, tx, :spec.cout_g] = w[r, q, :, g * spec.cout_g:(g + 1) * spec.cout_g]
+    assert np.array_equal(wd.float().cpu().numpy(), ref.reshape(rows, cols))
+    dx = torch.full((n, h, h, cin), float("nan"), dtype=torch.bfloat16, device="cuda")
+    K.conv_dgrad_d2s(spec, dev(dy, torch.bfloat16), wd, dx, sh=sh, sw=sw)
+    got = dx.float().cpu().numpy()
+    assert np.isfinite(got).all()  # every output element is written exactly once
+    assert rel(got, dx_ref) < BF16_TOL
+
+
 def test_conv1_space_to_depth_path_vs_oracle(vl):
     """conv1 (11x11 stride 4 SAME, alexnet.py:60-77) as space-to-depth + 3x3 VALID im2col-TMA convolution."""
     nv, K, E = vl["nv"], vl["K"], vl["E"]

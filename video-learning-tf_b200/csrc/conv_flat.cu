@@ -400,6 +400,33 @@ __global__ void pack_dgrad_kmajor_kernel(const float* __restrict__ src, bf16* __
   }
 }
 
+
+// K-major filter of the depth-to-space data gradient (include/vlb200.h: vl_pack_dgrad_d2s):
+// dst[g*sh*sw*cin_g + (dy*sw+dx)*cin_g + c][(ty*kw2+tx)*kpad + k] = src[kh-1+dy-ty][kw-1+dx-tx][c][g*cout_g + k]
+// (0 outside the filter or for k >= cout_g); consecutive threads walk k, i.e. the contiguous axis of both tensors.
+__global__ void pack_dgrad_d2s_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int kh, int kw, int cin_g,
+                                      int cout_g, int groups, int sh, int sw, int kpad, long long total) {
+  const int kh2 = kh + sh - 1, kw2 = kw + sw - 1;
+  const int ld = kh2 * kw2 * kpad;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int row = (int)(idx / ld);
+    const int col = (int)(idx - (long long)row * ld);
+    const int tap = col / kpad, k = col - tap * kpad;
+    const int ty = tap / kw2, tx = tap - ty * kw2;
+    const int per_g = sh * sw * cin_g;
+    const int g = row / per_g;
+    const int rr = row - g * per_g;
+    const int seg = rr / cin_g, c = rr - seg * cin_g;
+    const int dy = seg / sw, dx = seg - dy * sw;
+    const int r = kh - 1 + dy - ty, q = kw - 1 + dx - tx;
+    float v = 0.f;
+    if (k < cout_g && r >= 0 && r < kh && q >= 0 && q < kw)
+      v = src[(((long long)r * kw + q) * cin_g + c) * (groups * cout_g) + g * cout_g + k];
+    dst[idx] = __float2bfloat16_rn(v);
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -556,6 +583,22 @@ extern "C" int vl_pack_dgrad_kmajor(const float* src, void* dst, int32_t taps, i
   const long long total = (long long)groups * cin_g * taps * kpad;
   pack_dgrad_kmajor_kernel<<<(int)((total + 255) / 256), 256, 0, stream>>>(src, reinterpret_cast<bf16*>(dst), taps,
                                                                            cin_g, cout_g, groups, kpad, total);
+  vl::g_launches.fetch_add(1);
+  VL_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int vl_pack_dgrad_d2s(const float* src, void* dst, int32_t kh, int32_t kw, int32_t cin_g, int32_t cout_g,
+                                 int32_t groups, int32_t sh, int32_t sw, vl_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  VL_REQUIRE(src && dst && kh > 0 && kw > 0 && cin_g > 0 && cout_g > 0 && groups > 0 && sh >= 1 && sw >= 1,
+             "vl_pack_dgrad_d2s: bad arguments");
+  const int kpad = ((cout_g + 63) / 64) * 64;
+  const long long total = (long long)groups * sh * sw * cin_g * (kh + sh - 1) * (kw + sw - 1) * kpad;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 65535LL * 16) blocks = 65535LL * 16;
+  pack_dgrad_d2s_kernel<<<(int)blocks, 256, 0, stream>>>(src, reinterpret_cast<bf16*>(dst), kh, kw, cin_g, cout_g, groups,
+                                                         sh, sw, kpad, total);
   vl::g_launches.fetch_add(1);
   VL_CHECK_CUDA(cudaGetLastError());
   return 0;

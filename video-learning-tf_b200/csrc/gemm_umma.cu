@@ -60,6 +60,8 @@ struct KParams {
   int taps, cchunks, kw, flip;
   int P, Q, PQ, stride_h, stride_w, lower_h, lower_w, cin_g;
   FastDiv fd_nblk, fd_mblk, fd_groups, fd_cchunks, fd_kw, fd_PQ, fd_Q;
+  int d2s_sh, d2s_sw, d2s_c, d2s_h, d2s_w;  // depth-to-space epilogue (d2s_c > 0), see vl_gemm_desc
+  FastDiv fd_d2s_c, fd_d2s_sw;
   void* C;
   int c_ld, c_dtype, c_atomic, relu;
   const float* bias;
@@ -401,6 +403,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
           row_ok = grow < p.M;
         }
         const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + acc * ACC_STRIDE_COLS + sub * BN;
+        // depth-to-space epilogue: row (n, Y, X) -> base pixel (sh*Y, sw*X) of the NHWC output
+        long long d2s_base = 0;
+        int d2s_y = 0, d2s_x = 0;
+        if (p.d2s_c > 0 && row_ok) {
+          int nn, rem, yy, xx;
+          fd_divmod((int)grow, p.fd_PQ, nn, rem);
+          fd_divmod(rem, p.fd_Q, yy, xx);
+          d2s_y = yy * p.d2s_sh;
+          d2s_x = xx * p.d2s_sw;
+          d2s_base = (((long long)nn * p.d2s_h + d2s_y) * p.d2s_w + d2s_x) * p.c_ld + t.g * p.c_goff;
+        }
 
         auto process = [&](const uint32_t (&v)[16], int c0) {
           if (!row_ok || (p.dbg & 8)) return;
@@ -459,7 +472,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
                 if (j < ncols && !(__bfloat162float(mrow[j]) > 0.0f)) f[j] = 0.0f;
             }
           }
-          const long long off = grow * p.c_ld + gcol0 + c0;
+          long long off = grow * p.c_ld + gcol0 + c0;
+          if (p.d2s_c > 0) {
+            int seg, within, ddy, ddx;
+            fd_divmod(n0 + c0, p.fd_d2s_c, seg, within);
+            fd_divmod(seg, p.fd_d2s_sw, ddy, ddx);
+            if (d2s_y + ddy >= p.d2s_h || d2s_x + ddx >= p.d2s_w) return;
+            off = d2s_base + (long long)(ddy * p.d2s_w + ddx) * p.c_ld + within;
+          }
           if (p.c_dtype == VL_DT_BF16) {
             bf16* out = reinterpret_cast<bf16*>(p.C) + off;
             if (vec_ok && ncols == 16) {
@@ -744,6 +764,22 @@ extern "C" int vl_gemm(const vl_gemm_desc* d, const void* a, const void* b, void
   p.fd_kw = make_fastdiv(p.kw);
   p.fd_PQ = make_fastdiv(p.PQ);
   p.fd_Q = make_fastdiv(p.Q);
+  p.d2s_c = d->d2s_c;
+  if (p.d2s_c > 0) {
+    VL_REQUIRE(d->a_mode == VL_A_IM2COL_K && d->b_mode == VL_B_TILED_K && !d->c_atomic && bias == nullptr &&
+                   relu_mask == nullptr,
+               "vl_gemm: the depth-to-space epilogue serves plain im2col convolutions only");
+    VL_REQUIRE(d->d2s_c % 16 == 0 && d->d2s_sh >= 1 && d->d2s_sw >= 1 && d->n == d->d2s_sh * d->d2s_sw * d->d2s_c,
+               "vl_gemm: depth-to-space needs n == sh*sw*c and c %% 16 == 0 (n=%d sh=%d sw=%d c=%d)", d->n, d->d2s_sh,
+               d->d2s_sw, d->d2s_c);
+    VL_REQUIRE(d->d2s_h > 0 && d->d2s_w > 0 && d->c_goff % 8 == 0, "vl_gemm: bad depth-to-space output extent");
+    p.d2s_sh = d->d2s_sh;
+    p.d2s_sw = d->d2s_sw;
+    p.d2s_h = d->d2s_h;
+    p.d2s_w = d->d2s_w;
+    p.fd_d2s_c = make_fastdiv(p.d2s_c);
+    p.fd_d2s_sw = make_fastdiv(p.d2s_sw);
+  }
 
   {
     const char* e = getenv("VL_GEMM_DBG");

@@ -229,6 +229,9 @@ class Engine(object):
             s = sp[name]
             sh[name] = torch.zeros(s.taps * s.cin_g, s.cout, dtype=BF16, device=dev)  # HWIO as 2D (data gradient)
             sh[name + "_fwd"] = torch.zeros(s.cout, s.k_packed, dtype=BF16, device=dev)  # K-major, taps padded to 64
+        # conv2's data gradient runs as a stride-2 forward convolution over dy with a depth-to-space epilogue
+        # (kernels.conv_dgrad_d2s): N = 2*2*48 = 192 columns per UMMA instead of 48
+        sh["conv2_d2s"] = torch.zeros(*K.d2s_filter_shape(sp["conv2"], 2, 2), dtype=BF16, device=dev)
         sh["fc6"] = torch.zeros(sp["flat"], 4096, dtype=BF16, device=dev)
         names = dict(self.var_shapes)
         if "dcnn/fc7W" in names:
@@ -257,6 +260,9 @@ class Engine(object):
             nv.call("vl_cast_f32_to_bf16", w, sh[name], w.numel())
             nv.call("vl_pack_bf16_t", w, s.taps * s.cin_g, s.cout, sh[name + "_fwd"], s.k_packed, s.cin_g,
                     s.cchunks * 64)
+        s2 = sp["conv2"]
+        nv.call("vl_pack_dgrad_d2s", self.var("dcnn/conv2W"), sh["conv2_d2s"], s2.kh, s2.kw, s2.cin_g, s2.cout_g,
+                s2.groups, 2, 2)
         for name in ("fc6", "fc7"):
             if name in sh:
                 w = self.var("dcnn/%sW" % name)
@@ -666,7 +672,7 @@ class Engine(object):
                 ev = torch.cuda.Event()
                 ev.record(st)
                 da2_ready.append(ev)
-                K.conv_dgrad(s2, G["da2"][lo:hi], self.sh["conv2"], G["dp1"][lo:hi])
+                K.conv_dgrad_d2s(s2, G["da2"][lo:hi], self.sh["conv2_d2s"], G["dp1"][lo:hi], sh=2, sw=2)
                 nv.call("vl_pool_lrn_bwd", A["a1"][lo:hi], G["dp1"][lo:hi], A["arg1"][lo:hi], G["da1"][lo:hi],
                         self.var("dcnn/conv1b", self.grads), m, s1.p, s1.q, 96, LRN["radius"], LRN["alpha"],
                         LRN["beta"], LRN["bias"])

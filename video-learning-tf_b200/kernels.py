@@ -197,6 +197,48 @@ def conv_dgrad_flat(spec, dy, w_dgrad_kmajor, dx):
     return dx
 
 
+def d2s_filter_shape(spec, sh, sw):
+    """Shape of the vl_pack_dgrad_d2s operand of `spec`: [groups*sh*sw*cin_g, (kh+sh-1)*(kw+sw-1)*roundup64(cout_g)]."""
+    kpad = -(-spec.cout_g // 64) * 64
+    return spec.groups * sh * sw * spec.cin_g, (spec.kh + sh - 1) * (spec.kw + sw - 1) * kpad
+
+
+def conv_dgrad_d2s(spec, dy, w_d2s, dx, sh=2, sw=2, block_n=0, msub=0):
+    """dx = conv2d_backprop_input(dy, W) of a stride-1 convolution with a NARROW cin_g (conv2: 48), issued as a
+    stride-(sh,sw) forward convolution over dy that produces the sh*sw sub-positions of every output block at once
+    (N = sh*sw*cin_g columns per UMMA instead of cin_g; the epilogue scatters them back, depth-to-space).
+    w_d2s = vl_pack_dgrad_d2s(W) (see include/vlb200.h)."""
+    assert spec.stride == 1 and dx.dtype == BF16 and spec.cin_g % 16 == 0
+    n = dy.shape[0]
+    kh2, kw2 = spec.kh + sh - 1, spec.kw + sw - 1
+    kpad = -(-spec.cout_g // 64) * 64
+    py, qx = -(-spec.h // sh), -(-spec.w // sw)
+    d = nv.GemmDesc()
+    d.m, d.n, d.k, d.groups = n * py * qx, sh * sw * spec.cin_g, kh2 * kw2 * kpad, spec.groups
+    d.a_mode, d.b_mode = nv.A_IM2COL_K, nv.B_TILED_K
+    d.a_goff, d.b_goff, d.c_goff = spec.cout_g, 0, spec.cin_g
+    d.b_row_goff = sh * sw * spec.cin_g
+    d.b_tap_inner = kpad
+    d.b_ld = kh2 * kw2 * kpad
+    d.c_ld = spec.cin
+    d.c_dtype = nv.DT_BF16
+    d.split_k = 1
+    d.block_n = block_n
+    d.msub = msub
+    d.d2s_sh, d.d2s_sw, d.d2s_c, d.d2s_h, d.d2s_w = sh, sw, spec.cin_g, spec.h, spec.w
+    g = nv.ConvGeom()
+    g.n, g.h, g.w, g.c = n, spec.p, spec.q, spec.cout
+    g.kh, g.kw = kh2, kw2
+    g.stride_h, g.stride_w = sh, sw
+    g.pad_top, g.pad_left = spec.kh - 1 - spec.pad_top, spec.kw - 1 - spec.pad_left
+    g.p, g.q = py, qx
+    g.cin_g = spec.cout_g
+    g.flip_taps = 0
+    d.conv = g
+    nv.gemm(d, dy, w_d2s, dx, None, None)
+    return dx
+
+
 def conv_dgrad(spec, dy, w_hwio, dx, relu_mask=None, block_n=0, msub=0):
     """dx[N,H,W,Cin] = conv2d_backprop_input(dy[N,P,Q,Cout], W); w_hwio = bf16 [taps*cin_g, Cout] (HWIO as 2D)."""
     n = dy.shape[0]
