@@ -53,7 +53,34 @@ class ClockSampler(threading.Thread):
         self.stop_flag = False
         self.proc = None
 
+    def run_nvml(self):
+        """In-process NVML polling (same counters as the nvidia-smi query, without a second process taking the driver's
+        locks every 100 ms next to the timed region).  Returns False when NVML is not usable."""
+        try:
+            import pynvml as N
+            N.nvmlInit()
+            h = N.nvmlDeviceGetHandleByIndex(self.index)
+            mx = N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM)
+            get_reasons = getattr(N, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                N.nvmlDeviceGetCurrentClocksThrottleReasons
+            bits = [(0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"),
+                    (0x4, "sw_power_cap")]
+            N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)
+        except Exception:
+            return False
+        while not self.stop_flag:
+            try:
+                sm = N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)
+                r = int(get_reasons(h))
+                self.samples.append([str(sm), str(mx), "0"] + ["Active" if r & b else "Not Active" for b, _ in bits])
+            except Exception:
+                pass
+            time.sleep(0.02)
+        return True
+
     def run(self):
+        if os.environ.get("VL_BENCH_CLOCKS", "nvml") == "nvml" and self.run_nvml():
+            return
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")

@@ -277,6 +277,11 @@ int vl_clip_scalars(const float* sqnorms, int32_t num_vars, float clip_norm, flo
                     vl_stream_t stream);
 int vl_sgd_update(float* params, const float* grads, int64_t n, float lr, const float* scalars,
                   float grad_prescale, vl_stream_t stream);
+/* vl_sgd_update that also stores the bf16 operand copy of up to 4 arena ranges [seg_begin[k], seg_end[k]) (HOST arrays,
+ * float4 aligned) into seg_dst[k] (device, same layout as the master: fc / LSTM kernels), saving the separate cast. */
+int vl_sgd_update_shadow(float* params, const float* grads, int64_t n, float lr, const float* scalars,
+                         float grad_prescale, int32_t num_segs, const int64_t* seg_begin, const int64_t* seg_end,
+                         void* const* seg_dst, vl_stream_t stream);
 int vl_adam_update(float* params, const float* grads, float* m, float* v, int64_t n, float lr, float beta1,
                    float beta2, float eps, int32_t step, const float* scalars, float grad_prescale,
                    vl_stream_t stream);

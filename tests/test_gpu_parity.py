@@ -427,6 +427,16 @@ def test_optimizer_kernels_vs_oracle(vl):
     got = wd.cpu().numpy()
     for i, s in enumerate(sizes):
         assert rel(got[offs[i]:offs[i] + s], p_sgd[str(i)]) < 1e-5
+    # the fused variant: identical weights, and the bf16 operand copies of two ranges written in the same pass
+    import ctypes
+    wd2 = dev(w)
+    segs = [(offs[1], offs[1] + (sizes[1] // 4) * 4), (offs[3], offs[3] + (sizes[3] // 4) * 4)]
+    shadows = [torch.full((e - b,), float("nan"), dtype=torch.bfloat16, device="cuda") for b, e in segs]
+    nv.call("vl_sgd_update_shadow", wd2, gd, n, 0.01, scal, 1.0, 2, (ctypes.c_int64 * 2)(*[b for b, _ in segs]),
+            (ctypes.c_int64 * 2)(*[e for _, e in segs]), (ctypes.c_void_p * 2)(*[t.data_ptr() for t in shadows]))
+    assert torch.equal(wd2, wd)
+    for (b, e), t in zip(segs, shadows):
+        assert torch.equal(t, wd[b:e].to(torch.bfloat16))
     # Adam, three steps
     wd = dev(w)
     m = torch.zeros(n, device="cuda")

@@ -415,7 +415,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
           d2s_base = (((long long)nn * p.d2s_h + d2s_y) * p.d2s_w + d2s_x) * p.c_ld + t.g * p.c_goff;
         }
 
-        auto process = [&](const uint32_t (&v)[16], int c0) {
+        // ReLU-gradient mask of a 16-column chunk, fetched two chunks ahead of its use (the row-strided 32-byte
+        // reads of the epilogue threads are latency bound when issued at the point of use)
+        const bool mask_vec = p.mask != nullptr && row_ok && vec_ok && !(p.dbg & 8);
+        auto fetch_mask = [&](int c0, uint4 (&m)[2]) {
+          if (mask_vec && c0 < BN && n0 + c0 + 16 <= p.N) {
+            const bf16* mrow = p.mask + grow * p.mask_ld + gcol0 + c0;
+            m[0] = __ldg(reinterpret_cast<const uint4*>(mrow));
+            m[1] = __ldg(reinterpret_cast<const uint4*>(mrow + 8));
+          }
+        };
+        auto process = [&](const uint32_t (&v)[16], int c0, const uint4 (&mpre)[2]) {
           if (!row_ok || (p.dbg & 8)) return;
           if (BMODE == VL_B_IM2COL_MN) {
             // filter gradient with the filter taps on the N side: C[(tap, ci)][g * c_goff + row]; consecutive lanes
@@ -454,11 +464,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 #pragma unroll
             for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.0f);
           }
-          if (p.mask != nullptr) {
+          // bf16 vector path: the mask is applied to the packed pairs below (one HSET2 + one LOP3 per pair)
+          const bool mask_packed = p.mask != nullptr && vec_ok && ncols == 16 && p.c_dtype == VL_DT_BF16;
+          if (p.mask != nullptr && !mask_packed) {
             const bf16* mrow = p.mask + grow * p.mask_ld + gcol0 + c0;
             if (vec_ok && ncols == 16) {
-              uint4 m0v = *reinterpret_cast<const uint4*>(mrow);
-              uint4 m1v = *reinterpret_cast<const uint4*>(mrow + 8);
+              uint4 m0v = mpre[0];
+              uint4 m1v = mpre[1];
               const bf16* mv0 = reinterpret_cast<const bf16*>(&m0v);
               const bf16* mv1 = reinterpret_cast<const bf16*>(&m1v);
 #pragma unroll
@@ -488,6 +500,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
               for (int j = 0; j < 8; ++j) {
                 __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
                 w[j] = *reinterpret_cast<uint32_t*>(&h);
+              }
+              if (mask_packed) {
+                const uint32_t mw[8] = {mpre[0].x, mpre[0].y, mpre[0].z, mpre[0].w,
+                                        mpre[1].x, mpre[1].y, mpre[1].z, mpre[1].w};
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  uint32_t keep;  // 0xffff per half where mask > 0 (tf ReluGrad)
+                  asm("set.gt.u32.bf16x2 %0, %1, %2;" : "=r"(keep) : "r"(mw[j]), "r"(0u));
+                  w[j] &= keep;
+                }
               }
               *reinterpret_cast<uint4*>(out) = make_uint4(w[0], w[1], w[2], w[3]);
               *reinterpret_cast<uint4*>(out + 8) = make_uint4(w[4], w[5], w[6], w[7]);
@@ -524,17 +546,24 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 
         // software pipelined TMEM drain: the load of chunk i+1 is in flight while chunk i is processed
         uint32_t va[16], vb[16];
+        uint4 ma[2], mb[2], na[2], nb[2];
+        ma[0] = ma[1] = mb[0] = mb[1] = na[0] = na[1] = nb[0] = nb[1] = make_uint4(0, 0, 0, 0);
+        fetch_mask(0, ma);
+        fetch_mask(16, mb);
         tmem_ld_x16(taddr, va);
         for (int c0 = 0; c0 < BN; c0 += 32) {
+          fetch_mask(c0 + 32, na);
+          fetch_mask(c0 + 48, nb);
           tmem_ld_wait();
           const bool has_b = c0 + 16 < BN;
           if (has_b) tmem_ld_x16(taddr + c0 + 16, vb);
-          process(va, c0);
+          process(va, c0, ma);
           if (has_b) {
             tmem_ld_wait();
             if (c0 + 32 < BN) tmem_ld_x16(taddr + c0 + 32, va);
-            process(vb, c0 + 16);
+            process(vb, c0 + 16, mb);
           }
+          ma[0] = na[0], ma[1] = na[1], mb[0] = nb[0], mb[1] = nb[1];
         }
       }
       tc_fence_before();

@@ -2,6 +2,7 @@
 // per-variable squared norms -> global-norm clip scale (kept on device) -> SGD / Adam apply.
 // HBM-bound: SGD reads w,g and writes w (12 B/param); Adam reads w,g,m,v and writes w,m,v (28 B/param).
 #include "common.cuh"
+#include <cstring>
 #include "../../include/vlb200.h"
 
 #include <atomic>
@@ -68,6 +69,42 @@ __global__ void sgd_kernel(float* __restrict__ w, const float* __restrict__ g, l
     wv.z -= s * gv.z;
     wv.w -= s * gv.w;
     reinterpret_cast<float4*>(w)[idx] = wv;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    for (long long i = n4 << 2; i < n; ++i) w[i] -= s * g[i];
+}
+
+// SGD step that also refreshes the bf16 tensor-core operand ("shadow") of up to 4 arena ranges whose shadow has the
+// layout of the master (fc6 / fc7 / LSTM kernels = 97 % of the parameters): the updated weights are rounded and
+// stored while they are in registers instead of being re-read by a cast kernel.  Ranges are float4 aligned.
+struct ShadowSegs {
+  long long begin4[4], end4[4];  // [begin, end) in float4 units
+  __nv_bfloat16* dst[4];
+  int n;
+};
+__global__ void sgd_shadow_kernel(float* __restrict__ w, const float* __restrict__ g, long long n, float lr,
+                                  const float* __restrict__ scalars, float prescale, const ShadowSegs segs) {
+  const float s = lr * prescale * (scalars ? scalars[1] : 1.0f);
+  const long long n4 = n >> 2;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n4;
+       idx += (long long)gridDim.x * blockDim.x) {
+    float4 wv = reinterpret_cast<float4*>(w)[idx];
+    const float4 gv = reinterpret_cast<const float4*>(g)[idx];
+    wv.x -= s * gv.x;
+    wv.y -= s * gv.y;
+    wv.z -= s * gv.z;
+    wv.w -= s * gv.w;
+    reinterpret_cast<float4*>(w)[idx] = wv;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (k < segs.n && idx >= segs.begin4[k] && idx < segs.end4[k]) {
+        const __nv_bfloat162 lo = __floats2bfloat162_rn(wv.x, wv.y), hi = __floats2bfloat162_rn(wv.z, wv.w);
+        uint2 o;
+        o.x = *reinterpret_cast<const uint32_t*>(&lo);
+        o.y = *reinterpret_cast<const uint32_t*>(&hi);
+        reinterpret_cast<uint2*>(segs.dst[k])[idx - segs.begin4[k]] = o;
+      }
+    }
   }
   if (blockIdx.x == 0 && threadIdx.x == 0)
     for (long long i = n4 << 2; i < n; ++i) w[i] -= s * g[i];
@@ -141,6 +178,27 @@ extern "C" int vl_adam_update(float* params, const float* grads, float* m, float
   const double lr_t = (double)lr * sqrt(1.0 - pow((double)beta2, step)) / (1.0 - pow((double)beta1, step));
   adam_kernel<<<sweep_grid(n, 256), 256, 0, stream>>>(params, grads, m, v, n, (float)lr_t, beta1, beta2, eps, scalars,
                                                       grad_prescale);
+  VL_LAUNCHED();
+  return 0;
+}
+
+extern "C" int vl_sgd_update_shadow(float* params, const float* grads, int64_t n, float lr, const float* scalars,
+                                    float grad_prescale, int32_t num_segs, const int64_t* seg_begin,
+                                    const int64_t* seg_end, void* const* seg_dst, vl_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  VL_REQUIRE(params && grads && n > 0 && num_segs >= 0 && num_segs <= 4, "vl_sgd_update_shadow: bad arguments");
+  ShadowSegs segs;
+  memset(&segs, 0, sizeof(segs));
+  segs.n = num_segs;
+  for (int k = 0; k < num_segs; ++k) {
+    VL_REQUIRE(seg_begin[k] % 4 == 0 && seg_end[k] % 4 == 0 && seg_begin[k] <= seg_end[k] && seg_end[k] <= (n & ~3LL) &&
+                   (reinterpret_cast<uintptr_t>(seg_dst[k]) & 7) == 0,
+               "vl_sgd_update_shadow: range %d must be float4 aligned inside the arena, its shadow 8-byte aligned", k);
+    segs.begin4[k] = seg_begin[k] / 4;
+    segs.end4[k] = seg_end[k] / 4;
+    segs.dst[k] = reinterpret_cast<__nv_bfloat16*>(seg_dst[k]);
+  }
+  sgd_shadow_kernel<<<sweep_grid(n / 4 + 1, 256), 256, 0, stream>>>(params, grads, n, lr, scalars, grad_prescale, segs);
   VL_LAUNCHED();
   return 0;
 }

@@ -248,8 +248,24 @@ class Engine(object):
                 sh["output_fc"] = torch.zeros(cfg.lstm_hidden, self.c_pad, dtype=BF16, device=dev)
         self.sh = sh
 
-    def refresh_shadows(self):
-        """fp32 master -> bf16 tensor-core operands (after load and after every optimiser step)."""
+    def _plain_shadow_segments(self):
+        """(begin, end, shadow) of the variables whose bf16 operand copy has the master's layout (fc6, fc7 and the LSTM
+        kernels): vl_sgd_update_shadow writes them while the updated weights are in registers."""
+        segs = []
+        for name, key in (("dcnn/fc6W", "fc6"), ("dcnn/fc7W", "fc7")):
+            if key in self.sh and name in self.var_off:
+                segs.append((self.var_off[name], self.var_off[name] + self.sh[key].numel(), self.sh[key]))
+        if self.cfg.workflow == "lrcn":
+            for layer in range(self.cfg.lstm_layers):
+                name = "rnn/multi_rnn_cell/cell_%d/basic_lstm_cell/kernel" % layer
+                t = self.sh["lstm%d" % layer]
+                segs.append((self.var_off[name], self.var_off[name] + t.numel(), t))
+        segs = [sg for sg in segs if sg[0] % 4 == 0 and sg[1] % 4 == 0]
+        return segs[:4] if len(segs) <= 4 else None
+
+    def refresh_shadows(self, plain_done=False):
+        """fp32 master -> bf16 tensor-core operands (after load and after every optimiser step).  plain_done: the
+        same-layout copies (fc6, fc7, LSTM kernels) were already written by vl_sgd_update_shadow."""
         sh, sp = self.sh, self.sp
         s1 = sp["conv1"]
         nv.call("vl_s2d_pack_filter", self.var("dcnn/conv1W"), sh["conv1_fwd"], s1.kh, s1.kw, 3, 96, s1.stride,
@@ -264,7 +280,7 @@ class Engine(object):
         nv.call("vl_pack_dgrad_d2s", self.var("dcnn/conv2W"), sh["conv2_d2s"], s2.kh, s2.kw, s2.cin_g, s2.cout_g,
                 s2.groups, 2, 2)
         for name in ("fc6", "fc7"):
-            if name in sh:
+            if name in sh and not plain_done:
                 w = self.var("dcnn/%sW" % name)
                 nv.call("vl_cast_f32_to_bf16", w, sh[name], w.numel())
         if "fc8" in sh:
@@ -274,7 +290,8 @@ class Engine(object):
             hdim = self.cfg.lstm_hidden
             for layer in range(self.cfg.lstm_layers):
                 kern = self.var("rnn/multi_rnn_cell/cell_%d/basic_lstm_cell/kernel" % layer)
-                nv.call("vl_cast_f32_to_bf16", kern, sh["lstm%d" % layer], kern.numel())
+                if not plain_done:
+                    nv.call("vl_cast_f32_to_bf16", kern, sh["lstm%d" % layer], kern.numel())
                 d_in = kern.shape[0] - hdim
                 nv.call("vl_transpose_f32", kern[d_in:], sh["lstm%d_wht" % layer], hdim, 4 * hdim)
             if "output_fc" in sh:
@@ -555,6 +572,25 @@ class Engine(object):
         want = max(1, (2 * nv.lib().vl_device_sm_count()) // max(tiles, 1))
         return int(max(1, min(want, kb // 4 if kb >= 8 else 1)))
 
+    def _zero_grads(self, n):
+        """Zero the gradient arena where the backward pass ACCUMULATES (split-K red.add filter gradients, atomically
+        summed bias gradients).  The fc6 / fc7 filter gradients (89 % of the arena) are plain stores whenever their
+        GEMM runs unsplit, which is the case at every batch size that fills the tile grid: they are skipped."""
+        skip = []
+        for name in ("dcnn/fc6W", "dcnn/fc7W"):
+            if name in self.var_off:
+                rows, cols = self.var2d(name).shape
+                if self._split_k(rows, cols, n) == 1:
+                    skip.append((self.var_off[name], self.var_off[name] + rows * cols))
+        lo = 0
+        total = self.grads_ext.numel()
+        for b, e in sorted(skip):
+            if b > lo:
+                nv.call("vl_zero", self.grads_ext[lo:b], (b - lo) * 4)
+            lo = e
+        if total > lo:
+            nv.call("vl_zero", self.grads_ext[lo:], (total - lo) * 4)
+
     def _dense_bwd(self, x, dy, wname, bname, n_valid=None):
         """Filter / bias gradient of y = x @ W + b into the gradient arena."""
         dw = self.var2d(wname, self.grads)
@@ -724,7 +760,7 @@ class Engine(object):
         logits = self._head_fwd(feat, n, True)
         nv.call("vl_softmax_ce", logits, A["labels"][:b], b, c, parallel.local_grad_scale(b, self.world), A["row_loss"],
                 self.scalars[4:6], A["dlogits"][:b], A["dlogits_bf"][:b], self.c_pad)
-        nv.call("vl_zero", self.grads_ext, self.grads_ext.numel() * 4)
+        self._zero_grads(n)
         dfeat = self._head_bwd(n)
         self._encoder_bwd(dfeat, n)
         if self.world > 1:
@@ -734,13 +770,25 @@ class Engine(object):
         clip = float(cfg.clip_norm) if cfg.clip_norm else 0.0
         nv.call("vl_clip_scalars", self.sqnorms, len(self.var_shapes), clip, 1.0, self.scalars)
         if apply_update:
+            fused = False
             if cfg.optimizer == "sgd":
-                nv.call("vl_sgd_update", self.params, self.grads, self.arena_n, float(lr), self.scalars, 1.0)
+                segs = self._plain_shadow_segments()
+                if segs:
+                    import ctypes
+                    k = len(segs)
+                    begin = (ctypes.c_int64 * k)(*[b for b, _, _ in segs])
+                    end = (ctypes.c_int64 * k)(*[e for _, e, _ in segs])
+                    dst = (ctypes.c_void_p * k)(*[t.data_ptr() for _, _, t in segs])
+                    nv.call("vl_sgd_update_shadow", self.params, self.grads, self.arena_n, float(lr), self.scalars, 1.0,
+                            k, begin, end, dst)
+                    fused = True
+                else:
+                    nv.call("vl_sgd_update", self.params, self.grads, self.arena_n, float(lr), self.scalars, 1.0)
             else:
                 self.adam_t += 1
                 nv.call("vl_adam_update", self.params, self.grads, self.adam_m, self.adam_v, self.arena_n, float(lr),
                         0.9, 0.999, 1e-8, self.adam_t, self.scalars, 1.0)
-            self.refresh_shadows()
+            self.refresh_shadows(plain_done=fused)
             self.global_step += 1
         self._last_clips = b
         return self.read_step_scalars(lr)
