@@ -280,7 +280,7 @@ def conv_wgrad(spec, x, dy, dw, split_k=0, block_n=0, msub=0):
     return dw
 
 
-def conv_wgrad_t(spec, x, dy, dw, split_k=0, block_n=0):
+def conv_wgrad_t(spec, x, dy, dw, split_k=0, block_n=0, a_ld=0):
     """Same contract as conv_wgrad with the operands swapped: output channels (dy^T) on the M side, the (tap, channel
     chunk) axis of im2col(x)^T on the N side.  Every UMMA is 128 x block_n x 16 with block_n = 192 / 256 instead of
     a narrow cout-wide one, and the split-K red.adds of a warp coalesce."""
@@ -290,7 +290,7 @@ def conv_wgrad_t(spec, x, dy, dw, split_k=0, block_n=0):
     d.m, d.n, d.k, d.groups = spec.cout_g, chunks * 64, n * spec.p * spec.q, spec.groups
     d.a_mode, d.b_mode = nv.A_TILED_MN, nv.B_IM2COL_MN
     d.a_goff, d.b_goff, d.c_goff = spec.cout_g, spec.cin_g, spec.cout_g
-    d.a_ld = spec.cout
+    d.a_ld = a_ld or spec.cout  # row pitch of dy (elements); > cout when the tensor is stored channel-padded
     d.c_ld = spec.cout
     d.c_dtype = nv.DT_F32
     d.c_atomic = 1
