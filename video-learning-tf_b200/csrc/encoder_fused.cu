@@ -1131,7 +1131,10 @@ extern "C" int vl_lrn_pool_fwd(const void* x, void* y, void* argmax, int32_t n, 
   if (!getenv("VL_LRN_FWD_V2") && ((c == 96 && h == 57 && w == 57) || (c == 256 && h == 28 && w == 28))) {
     const int ring_bytes = 5 * (int)row_bytes;
     const int per_sm_smem = (227 * 1024) / (ring_bytes + 1024);
-    const int per_sm = per_sm_smem < 3 ? per_sm_smem : 3;  // 80 registers x 256 threads: three CTAs per SM
+    // 80 registers x 256 threads: three CTAs per SM; VL_LRN_FWD_CTAS=4 selects the 64-register build of the 96-channel
+    // instance (four CTAs per SM, a few spills)
+    const int want_mb = (c == 96 && getenv("VL_LRN_FWD_CTAS") && atoi(getenv("VL_LRN_FWD_CTAS")) == 4) ? 4 : 3;
+    const int per_sm = per_sm_smem < want_mb ? per_sm_smem : want_mb;
     const long long resident = (long long)vl::num_sms() * per_sm;
     // segments per frame: balance the waves against the one re-normalised row per extra segment
     int best_segs = 1;
@@ -1159,7 +1162,9 @@ extern "C" int vl_lrn_pool_fwd(const void* x, void* y, void* argmax, int32_t n, 
         reinterpret_cast<const bf16*>(x), reinterpret_cast<bf16*>(y), reinterpret_cast<uint8_t*>(argmax), n, seg_rows, \
         best_segs, alpha, bias);                                                                                      \
   } while (0)
-    if (c == 96)
+    if (c == 96 && want_mb == 4)
+      VL_FWD3_LAUNCH(24, 4, 96, 57, 57, 256, 4);
+    else if (c == 96)
       VL_FWD3_LAUNCH(24, 4, 96, 57, 57, 256, 3);
     else
       VL_FWD3_LAUNCH(16, 16, 256, 28, 28, 256, 3);
@@ -1225,7 +1230,12 @@ extern "C" int vl_pool_lrn_bwd(const void* x, const void* dy, const void* argmax
   const int v4 = getenv("VL_LRN_BWD_V4") ? atoi(getenv("VL_LRN_BWD_V4")) : 2;
   if (v4 && beta == 0.75f && c == 96 && h == 57 && w == 57) {
     const long long units = (long long)n * 29;
-    if (v4 == 2) {
+    if (v4 == 3) {  // 80 registers (a few spills), three CTAs per SM
+      const long long g = units < (long long)vl::num_sms() * 6 ? units : (long long)vl::num_sms() * 6;
+      pool_lrn_bwd_kernel4<12, 8, 96, 57, 57, 256, 3><<<(int)g, 256, 0, stream>>>(
+          reinterpret_cast<const bf16*>(x), reinterpret_cast<const bf16*>(dy), reinterpret_cast<const uint8_t*>(argmax),
+          reinterpret_cast<bf16*>(dx), dbias, n, alpha, bias);
+    } else if (v4 == 2) {
       const long long g = units < (long long)vl::num_sms() * 4 ? units : (long long)vl::num_sms() * 4;
       pool_lrn_bwd_kernel4<12, 8, 96, 57, 57, 256, 2><<<(int)g, 256, 0, stream>>>(
           reinterpret_cast<const bf16*>(x), reinterpret_cast<const bf16*>(dy), reinterpret_cast<const uint8_t*>(argmax),
@@ -1241,7 +1251,12 @@ extern "C" int vl_pool_lrn_bwd(const void* x, const void* dy, const void* argmax
   }
   if (v4 && beta == 0.75f && c == 256 && h == 28 && w == 28) {
     const long long units = (long long)n * 14;
-    if (v4 == 2) {
+    if (v4 >= 2) {  // 72 registers: two CTAs of 448 threads per SM (243 us against 293 us with one CTA, 128 registers)
+      const long long g = units < (long long)vl::num_sms() * 4 ? units : (long long)vl::num_sms() * 4;
+      pool_lrn_bwd_kernel4<8, 32, 256, 28, 28, 448, 2><<<(int)g, 448, 0, stream>>>(
+          reinterpret_cast<const bf16*>(x), reinterpret_cast<const bf16*>(dy), reinterpret_cast<const uint8_t*>(argmax),
+          reinterpret_cast<bf16*>(dx), dbias, n, alpha, bias);
+    } else if (v4 == 4) {
       const long long g = units < (long long)vl::num_sms() * 4 ? units : (long long)vl::num_sms() * 4;
       pool_lrn_bwd_kernel4<8, 32, 256, 28, 28, 448, 1><<<(int)g, 448, 0, stream>>>(
           reinterpret_cast<const bf16*>(x), reinterpret_cast<const bf16*>(dy), reinterpret_cast<const uint8_t*>(argmax),

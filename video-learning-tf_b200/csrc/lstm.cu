@@ -207,10 +207,11 @@ constexpr int CL = 8;          // CTAs per cluster
 constexpr int CH = 256;        // hidden size served by the cluster kernels
 constexpr int CU = CH / CL;    // hidden units per CTA (32)
 constexpr int CN = 4 * CU;     // gate columns per CTA (128)
-constexpr int CCB = 8;         // clips per cluster
+// CCB = clips per cluster (template parameter: 8 by default, 4 as a measured alternative)
 constexpr int WP = CN + 1;     // padded pitch of the weight slice
 constexpr int LSTM_CL_THREADS = 256;
 
+template <int CCB>
 struct ClusterSmem {
   float w[CH * WP];            // w[k][g*CU+u] = kernel[D+k][g*CH + rank*CU + u]
   float h[2][CH][CCB];         // h_{t-1} of the 8 clips, k-major, double buffered (fwd) / recv partials (bwd)
@@ -225,12 +226,13 @@ __device__ __forceinline__ void load_w_slice(float* w, const float* __restrict__
   }
 }
 
+template <int CCB>
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(LSTM_CL_THREADS, 1)
     lstm_fwd_cluster_kernel(const float* __restrict__ gx, const float* __restrict__ w_h, float* __restrict__ acts,
                             float* __restrict__ cs, float* __restrict__ h_seq, bf16* __restrict__ h_seq_bf16,
                             bf16* __restrict__ h_prev_bf16, int batch, int t_len, float forget_bias) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  ClusterSmem& S = *reinterpret_cast<ClusterSmem*>(smem_raw);
+  ClusterSmem<CCB>& S = *reinterpret_cast<ClusterSmem<CCB>*>(smem_raw);
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
   const int b0 = (blockIdx.x / CL) * CCB;
@@ -243,8 +245,9 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(LSTM_CL_THREADS, 1)
   // cell role: unit u, clip cb
   const int u = tid & (CU - 1);
   const int cb = tid >> 5;
+  const bool cell = cb < CCB;  // CCB = 4: the upper half of the CTA only takes part in the matmul role
   const int b = b0 + cb;
-  const bool live = b < batch;
+  const bool live = cell && b < batch;
   const int junit = rank * CU + u;
   float c = 0.f;
   float gxr[4] = {0.f, 0.f, 0.f, 0.f};
@@ -271,25 +274,25 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(LSTM_CL_THREADS, 1)
 #pragma unroll 4
       for (int k = 0; k < CH / 2; ++k) {
         const float wv = wk[k * WP];
-        const float4 h0 = *reinterpret_cast<const float4*>(hk + k * CCB);
-        const float4 h1 = *reinterpret_cast<const float4*>(hk + k * CCB + 4);
-        acc[0] = fmaf(h0.x, wv, acc[0]);
-        acc[1] = fmaf(h0.y, wv, acc[1]);
-        acc[2] = fmaf(h0.z, wv, acc[2]);
-        acc[3] = fmaf(h0.w, wv, acc[3]);
-        acc[4] = fmaf(h1.x, wv, acc[4]);
-        acc[5] = fmaf(h1.y, wv, acc[5]);
-        acc[6] = fmaf(h1.z, wv, acc[6]);
-        acc[7] = fmaf(h1.w, wv, acc[7]);
+#pragma unroll
+        for (int v = 0; v < CCB / 4; ++v) {
+          const float4 h4 = *reinterpret_cast<const float4*>(hk + k * CCB + 4 * v);
+          acc[4 * v] = fmaf(h4.x, wv, acc[4 * v]);
+          acc[4 * v + 1] = fmaf(h4.y, wv, acc[4 * v + 1]);
+          acc[4 * v + 2] = fmaf(h4.z, wv, acc[4 * v + 2]);
+          acc[4 * v + 3] = fmaf(h4.w, wv, acc[4 * v + 3]);
+        }
       }
       float4* dst = reinterpret_cast<float4*>(&S.part[khalf][col][0]);
-      dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-      dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
-      __syncthreads();
 #pragma unroll
-      for (int q = 0; q < 4; ++q) pre[q] += S.part[0][q * CU + u][cb] + S.part[1][q * CU + u][cb];
+      for (int v = 0; v < CCB / 4; ++v) dst[v] = make_float4(acc[4 * v], acc[4 * v + 1], acc[4 * v + 2], acc[4 * v + 3]);
+      __syncthreads();
+      if (cell) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) pre[q] += S.part[0][q * CU + u][cb] + S.part[1][q * CU + u][cb];
+      }
     }
-    const float hprev = S.h[cur][junit][cb];
+    const float hprev = cell ? S.h[cur][junit][cb] : 0.f;
     const float si = sigmoidf_(pre[0]);
     const float tj = tanhf(pre[1]);
     const float sf = sigmoidf_(pre[2] + forget_bias);
@@ -297,10 +300,12 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(LSTM_CL_THREADS, 1)
     c = c * sf + si * tj;
     const float h = tanhf(c) * so;
     // publish h_t[junit][cb] to every CTA of the cluster (next step's operand)
+    if (cell) {
 #pragma unroll
-    for (int r = 0; r < CL; ++r) {
-      float* remote = cluster.map_shared_rank(&S.h[cur ^ 1][0][0], r);
-      remote[junit * CCB + cb] = h;
+      for (int r = 0; r < CL; ++r) {
+        float* remote = cluster.map_shared_rank(&S.h[cur ^ 1][0][0], r);
+        remote[junit * CCB + cb] = h;
+      }
     }
     if (live) {
       const long long row = (long long)b * t_len + t;
@@ -320,12 +325,13 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(LSTM_CL_THREADS, 1)
   }
 }
 
+template <int CCB>
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(LSTM_CL_THREADS, 1)
     lstm_bwd_cluster_kernel(const float* __restrict__ dh_seq, const float* __restrict__ acts,
                             const float* __restrict__ cs, const float* __restrict__ w_h, bf16* __restrict__ dg,
                             int batch, int t_len) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  ClusterSmem& S = *reinterpret_cast<ClusterSmem*>(smem_raw);
+  ClusterSmem<CCB>& S = *reinterpret_cast<ClusterSmem<CCB>*>(smem_raw);
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
   const int b0 = (blockIdx.x / CL) * CCB;
@@ -335,8 +341,9 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(LSTM_CL_THREADS, 1)
   for (int idx = tid; idx < 2 * CH * CCB; idx += LSTM_CL_THREADS) (&S.h[0][0][0])[idx] = 0.f;
   const int u = tid & (CU - 1);
   const int cb = tid >> 5;
+  const bool cell = cb < CCB;
   const int b = b0 + cb;
-  const bool live = b < batch;
+  const bool live = cell && b < batch;
   const int junit = rank * CU + u;
   float dc_next = 0.f;
   cluster.sync();
@@ -344,7 +351,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(LSTM_CL_THREADS, 1)
     const int par = t & 1;
     // dh_next = sum over source CTAs of the partials they sent for my units (zero at t = T-1)
     float dh = 0.f;
-    {
+    if (cell) {
       const float* recv = &S.h[par ^ 1][0][0];
 #pragma unroll
       for (int src = 0; src < CL; ++src) dh += recv[(src * CU + u) * CCB + cb];
@@ -370,10 +377,12 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(LSTM_CL_THREADS, 1)
       out[2 * CH] = __float2bfloat16_rn(d_f);
       out[3 * CH] = __float2bfloat16_rn(d_o);
     }
-    S.part[0][u][cb] = d_i;
-    S.part[0][CU + u][cb] = d_j;
-    S.part[0][2 * CU + u][cb] = d_f;
-    S.part[0][3 * CU + u][cb] = d_o;
+    if (cell) {
+      S.part[0][u][cb] = d_i;
+      S.part[0][CU + u][cb] = d_j;
+      S.part[0][2 * CU + u][cb] = d_f;
+      S.part[0][3 * CU + u][cb] = d_o;
+    }
     __syncthreads();
     if (t > 0) {
       // partial dh_{t-1}[k][cb] over my 128 gate columns, thread = k
@@ -385,21 +394,20 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(LSTM_CL_THREADS, 1)
 #pragma unroll 4
       for (int n = 0; n < CN; ++n) {
         const float wv = wr[n];
-        const float4 g0 = *reinterpret_cast<const float4*>(&S.part[0][n][0]);
-        const float4 g1 = *reinterpret_cast<const float4*>(&S.part[0][n][4]);
-        acc[0] = fmaf(g0.x, wv, acc[0]);
-        acc[1] = fmaf(g0.y, wv, acc[1]);
-        acc[2] = fmaf(g0.z, wv, acc[2]);
-        acc[3] = fmaf(g0.w, wv, acc[3]);
-        acc[4] = fmaf(g1.x, wv, acc[4]);
-        acc[5] = fmaf(g1.y, wv, acc[5]);
-        acc[6] = fmaf(g1.z, wv, acc[6]);
-        acc[7] = fmaf(g1.w, wv, acc[7]);
+#pragma unroll
+        for (int v = 0; v < CCB / 4; ++v) {
+          const float4 g4 = *reinterpret_cast<const float4*>(&S.part[0][n][4 * v]);
+          acc[4 * v] = fmaf(g4.x, wv, acc[4 * v]);
+          acc[4 * v + 1] = fmaf(g4.y, wv, acc[4 * v + 1]);
+          acc[4 * v + 2] = fmaf(g4.z, wv, acc[4 * v + 2]);
+          acc[4 * v + 3] = fmaf(g4.w, wv, acc[4 * v + 3]);
+        }
       }
       // send to the CTA that owns unit k: recv[par][my rank][k % CU][cb]
       float* remote = cluster.map_shared_rank(&S.h[par][0][0], k / CU) + (rank * CU + (k % CU)) * CCB;
-      reinterpret_cast<float4*>(remote)[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-      reinterpret_cast<float4*>(remote)[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+#pragma unroll
+      for (int v = 0; v < CCB / 4; ++v)
+        reinterpret_cast<float4*>(remote)[v] = make_float4(acc[4 * v], acc[4 * v + 1], acc[4 * v + 2], acc[4 * v + 3]);
     }
     cluster.sync();
   }
@@ -407,20 +415,28 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(LSTM_CL_THREADS, 1)
 
 }  // namespace
 
-extern "C" int vl_lstm_fwd_cluster(const float* gx, const float* w_h, float* acts, float* cs, float* h_seq,
-                                   void* h_seq_bf16, void* h_prev_bf16, int32_t batch, int32_t t_len, int32_t hidden,
-                                   float forget_bias, vl_stream_t stream_) {
-  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  VL_REQUIRE(gx && w_h && batch > 0 && t_len > 0, "vl_lstm_fwd_cluster: bad arguments");
-  VL_REQUIRE(hidden == CH, "vl_lstm_fwd_cluster: the resident-weight kernel serves hidden == %d", CH);
+// clips per cluster: 8.  Four clips per cluster (16 clusters for 64 clips) halve the FMA work per step but measured
+// SLOWER (forward 149 us against 117 us, backward 95 against 69): the recurrence is bound by the per-step cluster
+// barrier / DSMEM exchange, not by arithmetic, and 16 clusters of 8 CTAs are not all co-resident.  VL_LSTM_CCB=4 selects it.
+static int lstm_clips_per_cluster(int batch) {
+  (void)batch;
+  const char* e = getenv("VL_LSTM_CCB");
+  if (e && (atoi(e) == 4 || atoi(e) == 8)) return atoi(e);
+  return 8;
+}
+
+template <int CCB>
+static int launch_lstm_fwd_cluster(const float* gx, const float* w_h, float* acts, float* cs, float* h_seq,
+                                   void* h_seq_bf16, void* h_prev_bf16, int32_t batch, int32_t t_len,
+                                   float forget_bias, cudaStream_t stream) {
   static bool attr = false;
   if (!attr) {
-    VL_CHECK_CUDA(cudaFuncSetAttribute(lstm_fwd_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)sizeof(ClusterSmem)));
+    VL_CHECK_CUDA(cudaFuncSetAttribute(lstm_fwd_cluster_kernel<CCB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)sizeof(ClusterSmem<CCB>)));
     attr = true;
   }
   const int clusters = (batch + CCB - 1) / CCB;
-  lstm_fwd_cluster_kernel<<<clusters * CL, LSTM_CL_THREADS, sizeof(ClusterSmem), stream>>>(
+  lstm_fwd_cluster_kernel<CCB><<<clusters * CL, LSTM_CL_THREADS, sizeof(ClusterSmem<CCB>), stream>>>(
       gx, w_h, acts, cs, h_seq, reinterpret_cast<bf16*>(h_seq_bf16), reinterpret_cast<bf16*>(h_prev_bf16), batch, t_len,
       forget_bias);
   vl::g_launches.fetch_add(1);
@@ -428,21 +444,40 @@ extern "C" int vl_lstm_fwd_cluster(const float* gx, const float* w_h, float* act
   return 0;
 }
 
+template <int CCB>
+static int launch_lstm_bwd_cluster(const float* dh_seq, const float* acts, const float* cs, const float* w_h, void* dg,
+                                   int32_t batch, int32_t t_len, cudaStream_t stream) {
+  static bool attr = false;
+  if (!attr) {
+    VL_CHECK_CUDA(cudaFuncSetAttribute(lstm_bwd_cluster_kernel<CCB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)sizeof(ClusterSmem<CCB>)));
+    attr = true;
+  }
+  const int clusters = (batch + CCB - 1) / CCB;
+  lstm_bwd_cluster_kernel<CCB><<<clusters * CL, LSTM_CL_THREADS, sizeof(ClusterSmem<CCB>), stream>>>(
+      dh_seq, acts, cs, w_h, reinterpret_cast<bf16*>(dg), batch, t_len);
+  vl::g_launches.fetch_add(1);
+  VL_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int vl_lstm_fwd_cluster(const float* gx, const float* w_h, float* acts, float* cs, float* h_seq,
+                                   void* h_seq_bf16, void* h_prev_bf16, int32_t batch, int32_t t_len, int32_t hidden,
+                                   float forget_bias, vl_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  VL_REQUIRE(gx && w_h && batch > 0 && t_len > 0, "vl_lstm_fwd_cluster: bad arguments");
+  VL_REQUIRE(hidden == CH, "vl_lstm_fwd_cluster: the resident-weight kernel serves hidden == %d", CH);
+  if (lstm_clips_per_cluster(batch) == 4)
+    return launch_lstm_fwd_cluster<4>(gx, w_h, acts, cs, h_seq, h_seq_bf16, h_prev_bf16, batch, t_len, forget_bias, stream);
+  return launch_lstm_fwd_cluster<8>(gx, w_h, acts, cs, h_seq, h_seq_bf16, h_prev_bf16, batch, t_len, forget_bias, stream);
+}
+
 extern "C" int vl_lstm_bwd_cluster(const float* dh_seq, const float* acts, const float* cs, const float* w_h, void* dg,
                                    int32_t batch, int32_t t_len, int32_t hidden, vl_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   VL_REQUIRE(dh_seq && acts && cs && w_h && dg && batch > 0 && t_len > 0, "vl_lstm_bwd_cluster: bad arguments");
   VL_REQUIRE(hidden == CH, "vl_lstm_bwd_cluster: the resident-weight kernel serves hidden == %d", CH);
-  static bool attr = false;
-  if (!attr) {
-    VL_CHECK_CUDA(cudaFuncSetAttribute(lstm_bwd_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)sizeof(ClusterSmem)));
-    attr = true;
-  }
-  const int clusters = (batch + CCB - 1) / CCB;
-  lstm_bwd_cluster_kernel<<<clusters * CL, LSTM_CL_THREADS, sizeof(ClusterSmem), stream>>>(
-      dh_seq, acts, cs, w_h, reinterpret_cast<bf16*>(dg), batch, t_len);
-  vl::g_launches.fetch_add(1);
-  VL_CHECK_CUDA(cudaGetLastError());
-  return 0;
+  if (lstm_clips_per_cluster(batch) == 4)
+    return launch_lstm_bwd_cluster<4>(dh_seq, acts, cs, w_h, dg, batch, t_len, stream);
+  return launch_lstm_bwd_cluster<8>(dh_seq, acts, cs, w_h, dg, batch, t_len, stream);
 }
