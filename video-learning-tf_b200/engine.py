@@ -9,6 +9,7 @@ hand-written kernels (csrc/) through the C-ABI.  PyTorch provides device memory,
 NCCL process group; it performs no arithmetic of the model.
 """
 import math
+import os
 
 import numpy as np
 import torch
@@ -176,6 +177,12 @@ class Engine(object):
             self.adam_v = torch.zeros(off, dtype=F32, device=self.dev)
         self._side = torch.cuda.Stream(device=self.dev)  # filter gradients (off the backward critical path)
         self._side2 = torch.cuda.Stream(device=self.dev)  # second half-batch chain of the conv1/conv2 backward
+        # read-back of the step scalars: they are final after vl_clip_scalars, so the host copy waits on an event recorded
+        # there (not on the optimiser update / operand refresh that follow) and the next step is enqueued while the
+        # tail of this one still runs - the device never idles between steps
+        self._rb_stream = torch.cuda.Stream(device=self.dev)
+        self._scalars_host = torch.zeros(8, dtype=F32).pin_memory()
+        self._scalars_ready = None
         self._streams = (self._side, self._side2)
         self._alloc_shadows()
         self._alloc_activations()
@@ -769,6 +776,9 @@ class Engine(object):
         nv.call("vl_grad_sqnorms", self.grads, self.arena_n, self.seg_offsets, len(self.var_shapes), self.sqnorms)
         clip = float(cfg.clip_norm) if cfg.clip_norm else 0.0
         nv.call("vl_clip_scalars", self.sqnorms, len(self.var_shapes), clip, 1.0, self.scalars)
+        if os.environ.get("VL_EARLY_READ", "1") != "0":
+            self._scalars_ready = torch.cuda.Event()
+            self._scalars_ready.record()
         if apply_update:
             fused = False
             if cfg.optimizer == "sgd":
@@ -795,7 +805,15 @@ class Engine(object):
 
     def read_step_scalars(self, lr):
         """Device -> host read of the step results (the only synchronisation point of a step)."""
-        s = self.scalars.cpu().numpy()
+        if self._scalars_ready is not None:
+            self._rb_stream.wait_event(self._scalars_ready)
+            with torch.cuda.stream(self._rb_stream):
+                self._scalars_host.copy_(self.scalars, non_blocking=True)
+            self._rb_stream.synchronize()
+            self._scalars_ready = None
+            s = self._scalars_host.numpy().copy()
+        else:
+            s = self.scalars.cpu().numpy()
         b = self._last_clips
         loss = float(s[4]) / self.world
         acc = float(s[5]) / (b * self.world)
