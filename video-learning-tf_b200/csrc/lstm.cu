@@ -413,6 +413,261 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(LSTM_CL_THREADS, 1)
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Wide variants (1024 threads per CTA, 8 clips per cluster).  The 256-thread kernels above spend a step in a
+// 128-iteration dependent FMA loop with two warps per scheduler (7.3 us per step, latency bound); here the
+// contraction axis is split eight ways (forward: K = 256 -> 8 x 32) / four ways (backward: 128 gate columns -> 4 x 32),
+// the partial sums meet in shared memory, and eight warps per scheduler hide the LDS / FMA latency.
+// ------------------------------------------------------------------------------------------------
+constexpr int WIDE_T = 1024;
+constexpr int WCB = 8;                 // clips per cluster
+constexpr int KPARTS = WIDE_T / CN;    // 8 K slices of 32 (forward)
+constexpr int NPARTS = WIDE_T / CH;    // 4 column slices of 32 (backward)
+
+struct WideSmem {
+  float w[CH * WP];
+  float h[2][CH][WCB];
+  float part[KPARTS * CN * WCB];       // fwd: [KPARTS][CN][WCB]; bwd: [NPARTS][CH][WCB] (same size)
+  float dg[CN][WCB];                   // bwd: gate gradients of this step
+};
+
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(WIDE_T, 1)
+    lstm_fwd_cluster_wide_kernel(const float* __restrict__ gx, const float* __restrict__ w_h, float* __restrict__ acts,
+                                 float* __restrict__ cs, float* __restrict__ h_seq, bf16* __restrict__ h_seq_bf16,
+                                 bf16* __restrict__ h_prev_bf16, int batch, int t_len, float forget_bias) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  WideSmem& S = *reinterpret_cast<WideSmem*>(smem_raw);
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int b0 = (blockIdx.x / CL) * WCB;
+  const int tid = threadIdx.x;
+  for (int idx = tid; idx < CH * CN; idx += WIDE_T) {
+    const int k = idx / CN, col = idx - k * CN;
+    const int g = col / CU, u = col - g * CU;
+    S.w[k * WP + col] = w_h[(long long)k * (4 * CH) + g * CH + rank * CU + u];
+  }
+  for (int idx = tid; idx < CH * WCB; idx += WIDE_T) (&S.h[0][0][0])[idx] = 0.f;
+  const int col = tid & (CN - 1);
+  const int kp = tid >> 7;
+  const bool cell = tid < CU * WCB;  // first 256 threads: unit u of clip cb
+  const int u = tid & (CU - 1);
+  const int cb = (tid >> 5) & (WCB - 1);
+  const int b = b0 + cb;
+  const bool live = cell && b < batch;
+  const int junit = rank * CU + u;
+  float c = 0.f;
+  float gxr[4] = {0.f, 0.f, 0.f, 0.f};
+  if (live) {
+    const float* g = gx + ((long long)b * t_len) * (4 * CH) + junit;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) gxr[q] = g[q * CH];
+  }
+  cluster.sync();
+  for (int t = 0; t < t_len; ++t) {
+    const int cur = t & 1;
+    float pre[4] = {gxr[0], gxr[1], gxr[2], gxr[3]};
+    if (live && t + 1 < t_len) {
+      const float* g = gx + ((long long)b * t_len + t + 1) * (4 * CH) + junit;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) gxr[q] = g[q * CH];
+    }
+    if (t > 0) {
+      float acc[WCB];
+#pragma unroll
+      for (int i = 0; i < WCB; ++i) acc[i] = 0.f;
+      constexpr int KS = CH / KPARTS;
+      const float* hk = &S.h[cur][kp * KS][0];
+      const float* wk = S.w + kp * KS * WP + col;
+#pragma unroll 8
+      for (int k = 0; k < KS; ++k) {
+        const float wv = wk[k * WP];
+        const float4 h0 = *reinterpret_cast<const float4*>(hk + k * WCB);
+        const float4 h1 = *reinterpret_cast<const float4*>(hk + k * WCB + 4);
+        acc[0] = fmaf(h0.x, wv, acc[0]);
+        acc[1] = fmaf(h0.y, wv, acc[1]);
+        acc[2] = fmaf(h0.z, wv, acc[2]);
+        acc[3] = fmaf(h0.w, wv, acc[3]);
+        acc[4] = fmaf(h1.x, wv, acc[4]);
+        acc[5] = fmaf(h1.y, wv, acc[5]);
+        acc[6] = fmaf(h1.z, wv, acc[6]);
+        acc[7] = fmaf(h1.w, wv, acc[7]);
+      }
+      float4* dst = reinterpret_cast<float4*>(S.part + (kp * CN + col) * WCB);
+      dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+      __syncthreads();
+      if (cell) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float sum = 0.f;
+#pragma unroll
+          for (int pp = 0; pp < KPARTS; ++pp) sum += S.part[(pp * CN + q * CU + u) * WCB + cb];
+          pre[q] += sum;
+        }
+      }
+    }
+    float hprev = 0.f, si = 0.f, tj = 0.f, sf = 0.f, so = 0.f, h = 0.f;
+    float* hstage = &S.dg[0][0];  // [CU][WCB]: this CTA's slice of h_t, laid out like the remote h[.][rank*CU + u][cb]
+    if (cell) {
+      hprev = S.h[cur][junit][cb];
+      si = sigmoidf_(pre[0]);
+      tj = tanhf(pre[1]);
+      sf = sigmoidf_(pre[2] + forget_bias);
+      so = sigmoidf_(pre[3]);
+      c = c * sf + si * tj;
+      h = tanhf(c) * so;
+      hstage[u * WCB + cb] = h;
+    }
+    __syncthreads();
+    // publish h_t to every CTA of the cluster: 8 destinations x 64 float4 (one 16-byte DSMEM store per thread of the
+    // lower half; 2048 scalar remote stores per step were the dominant cost of the 256-thread kernel)
+    if (tid < CL * (CU * WCB / 4)) {
+      const int r = tid / (CU * WCB / 4), i = tid % (CU * WCB / 4);
+      float* remote = cluster.map_shared_rank(&S.h[cur ^ 1][0][0], r) + rank * (CU * WCB);
+      reinterpret_cast<float4*>(remote)[i] = reinterpret_cast<const float4*>(hstage)[i];
+    }
+    // arrive (release) NOW: only the DSMEM publication above has to be visible cluster-wide.  The global stores of
+    // this step follow the arrive, so the barrier does not wait for their acknowledgement.
+    cluster.barrier_arrive();
+    if (cell) {
+      if (live) {
+        const long long row = (long long)b * t_len + t;
+        if (acts != nullptr) {
+          float* a = acts + row * (4 * CH) + junit;
+          a[0] = si;
+          a[CH] = tj;
+          a[2 * CH] = sf;
+          a[3 * CH] = so;
+        }
+        if (cs != nullptr) cs[row * CH + junit] = c;
+        if (h_seq != nullptr) h_seq[row * CH + junit] = h;
+        if (h_seq_bf16 != nullptr) h_seq_bf16[row * CH + junit] = __float2bfloat16_rn(h);
+        if (h_prev_bf16 != nullptr) h_prev_bf16[row * CH + junit] = __float2bfloat16_rn(hprev);
+      }
+    }
+    cluster.barrier_wait();  // h_t visible cluster-wide; also orders the reuse of S.part and S.h[cur]
+  }
+}
+
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(WIDE_T, 1)
+    lstm_bwd_cluster_wide_kernel(const float* __restrict__ dh_seq, const float* __restrict__ acts,
+                                 const float* __restrict__ cs, const float* __restrict__ w_h, bf16* __restrict__ dg,
+                                 int batch, int t_len) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  WideSmem& S = *reinterpret_cast<WideSmem*>(smem_raw);
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int b0 = (blockIdx.x / CL) * WCB;
+  const int tid = threadIdx.x;
+  for (int idx = tid; idx < CH * CN; idx += WIDE_T) {
+    const int k = idx / CN, col = idx - k * CN;
+    const int g = col / CU, u = col - g * CU;
+    S.w[k * WP + col] = w_h[(long long)k * (4 * CH) + g * CH + rank * CU + u];
+  }
+  for (int idx = tid; idx < 2 * CH * WCB; idx += WIDE_T) (&S.h[0][0][0])[idx] = 0.f;
+  const bool cell = tid < CU * WCB;
+  const int u = tid & (CU - 1);
+  const int cb = (tid >> 5) & (WCB - 1);
+  const int b = b0 + cb;
+  const bool live = cell && b < batch;
+  const int junit = rank * CU + u;
+  const int kk = tid & (CH - 1);  // matmul role: hidden unit k, column slice np
+  const int np = tid >> 8;
+  float dc_next = 0.f;
+  // operands of a step (gate activations, cell states, incoming dh) are fetched one step ahead of their use
+  float nx[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  auto fetch = [&](int t) {
+    if (live && t >= 0) {
+      const long long row = (long long)b * t_len + t;
+      const float* a = acts + row * (4 * CH) + junit;
+      nx[0] = a[0], nx[1] = a[CH], nx[2] = a[2 * CH], nx[3] = a[3 * CH];
+      nx[4] = cs[row * CH + junit];
+      nx[5] = t > 0 ? cs[(row - 1) * CH + junit] : 0.f;
+      nx[6] = dh_seq[row * CH + junit];
+    }
+  };
+  fetch(t_len - 1);
+  cluster.sync();
+  for (int t = t_len - 1; t >= 0; --t) {
+    const int par = t & 1;
+    float d_i = 0.f, d_j = 0.f, d_f = 0.f, d_o = 0.f;
+    if (cell) {
+      float dh = 0.f;
+      const float* recv = &S.h[par ^ 1][0][0];
+#pragma unroll
+      for (int src = 0; src < CL; ++src) dh += recv[(src * CU + u) * WCB + cb];
+      if (live) {
+        const float si = nx[0], tj = nx[1], sf = nx[2], so = nx[3];
+        const float ct = nx[4];
+        const float cprev = nx[5];
+        const float tc = tanhf(ct);
+        dh += nx[6];
+        d_o = dh * tc * so * (1.f - so);
+        const float dc = dh * so * (1.f - tc * tc) + dc_next;
+        d_i = dc * tj * si * (1.f - si);
+        d_j = dc * si * (1.f - tj * tj);
+        d_f = dc * cprev * sf * (1.f - sf);
+        dc_next = dc * sf;
+      }
+      fetch(t - 1);
+      S.dg[u][cb] = d_i;
+      S.dg[CU + u][cb] = d_j;
+      S.dg[2 * CU + u][cb] = d_f;
+      S.dg[3 * CU + u][cb] = d_o;
+    }
+    __syncthreads();
+    if (t > 0) {
+      float acc[WCB];
+#pragma unroll
+      for (int i = 0; i < WCB; ++i) acc[i] = 0.f;
+      constexpr int NS = CN / NPARTS;
+      const float* wr = S.w + kk * WP + np * NS;
+#pragma unroll 8
+      for (int n = 0; n < NS; ++n) {
+        const float wv = wr[n];
+        const float4 g0 = *reinterpret_cast<const float4*>(&S.dg[np * NS + n][0]);
+        const float4 g1 = *reinterpret_cast<const float4*>(&S.dg[np * NS + n][4]);
+        acc[0] = fmaf(g0.x, wv, acc[0]);
+        acc[1] = fmaf(g0.y, wv, acc[1]);
+        acc[2] = fmaf(g0.z, wv, acc[2]);
+        acc[3] = fmaf(g0.w, wv, acc[3]);
+        acc[4] = fmaf(g1.x, wv, acc[4]);
+        acc[5] = fmaf(g1.y, wv, acc[5]);
+        acc[6] = fmaf(g1.z, wv, acc[6]);
+        acc[7] = fmaf(g1.w, wv, acc[7]);
+      }
+      float4* dst = reinterpret_cast<float4*>(S.part + (np * CH + kk) * WCB);
+      dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+      __syncthreads();
+      if (tid < CH) {
+        // dh_{t-1}[k][.] partial over my 128 gate columns -> the CTA that owns unit k: recv[par][my rank][k % CU][cb]
+        float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
+#pragma unroll
+        for (int pp = 0; pp < NPARTS; ++pp) {
+          const float4 a0 = *reinterpret_cast<const float4*>(S.part + (pp * CH + tid) * WCB);
+          const float4 a1 = *reinterpret_cast<const float4*>(S.part + (pp * CH + tid) * WCB + 4);
+          s0.x += a0.x, s0.y += a0.y, s0.z += a0.z, s0.w += a0.w;
+          s1.x += a1.x, s1.y += a1.y, s1.z += a1.z, s1.w += a1.w;
+        }
+        float* remote = cluster.map_shared_rank(&S.h[par][0][0], tid / CU) + (rank * CU + (tid % CU)) * WCB;
+        reinterpret_cast<float4*>(remote)[0] = s0;
+        reinterpret_cast<float4*>(remote)[1] = s1;
+      }
+    }
+    cluster.barrier_arrive();  // release covers the DSMEM partials; the global stores below are not waited for
+    if (live) {
+      bf16* out = dg + ((long long)b * t_len + t) * (4 * CH) + junit;
+      out[0] = __float2bfloat16_rn(d_i);
+      out[CH] = __float2bfloat16_rn(d_j);
+      out[2 * CH] = __float2bfloat16_rn(d_f);
+      out[3 * CH] = __float2bfloat16_rn(d_o);
+    }
+    cluster.barrier_wait();
+  }
+}
+
 }  // namespace
 
 // clips per cluster: 8.  Four clips per cluster (16 clusters for 64 clips) halve the FMA work per step but measured
@@ -467,6 +722,21 @@ extern "C" int vl_lstm_fwd_cluster(const float* gx, const float* w_h, float* act
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   VL_REQUIRE(gx && w_h && batch > 0 && t_len > 0, "vl_lstm_fwd_cluster: bad arguments");
   VL_REQUIRE(hidden == CH, "vl_lstm_fwd_cluster: the resident-weight kernel serves hidden == %d", CH);
+  if (!(getenv("VL_LSTM_WIDE") && atoi(getenv("VL_LSTM_WIDE")) == 0) && !getenv("VL_LSTM_CCB")) {
+    static bool attr = false;
+    if (!attr) {
+      VL_CHECK_CUDA(cudaFuncSetAttribute(lstm_fwd_cluster_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)sizeof(WideSmem)));
+      attr = true;
+    }
+    const int clusters = (batch + WCB - 1) / WCB;
+    lstm_fwd_cluster_wide_kernel<<<clusters * CL, WIDE_T, sizeof(WideSmem), stream>>>(
+        gx, w_h, acts, cs, h_seq, reinterpret_cast<bf16*>(h_seq_bf16), reinterpret_cast<bf16*>(h_prev_bf16), batch, t_len,
+        forget_bias);
+    vl::g_launches.fetch_add(1);
+    VL_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
   if (lstm_clips_per_cluster(batch) == 4)
     return launch_lstm_fwd_cluster<4>(gx, w_h, acts, cs, h_seq, h_seq_bf16, h_prev_bf16, batch, t_len, forget_bias, stream);
   return launch_lstm_fwd_cluster<8>(gx, w_h, acts, cs, h_seq, h_seq_bf16, h_prev_bf16, batch, t_len, forget_bias, stream);
@@ -477,6 +747,20 @@ extern "C" int vl_lstm_bwd_cluster(const float* dh_seq, const float* acts, const
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   VL_REQUIRE(dh_seq && acts && cs && w_h && dg && batch > 0 && t_len > 0, "vl_lstm_bwd_cluster: bad arguments");
   VL_REQUIRE(hidden == CH, "vl_lstm_bwd_cluster: the resident-weight kernel serves hidden == %d", CH);
+  if (!(getenv("VL_LSTM_WIDE") && atoi(getenv("VL_LSTM_WIDE")) == 0) && !getenv("VL_LSTM_CCB")) {
+    static bool attr = false;
+    if (!attr) {
+      VL_CHECK_CUDA(cudaFuncSetAttribute(lstm_bwd_cluster_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)sizeof(WideSmem)));
+      attr = true;
+    }
+    const int clusters = (batch + WCB - 1) / WCB;
+    lstm_bwd_cluster_wide_kernel<<<clusters * CL, WIDE_T, sizeof(WideSmem), stream>>>(
+        dh_seq, acts, cs, w_h, reinterpret_cast<bf16*>(dg), batch, t_len);
+    vl::g_launches.fetch_add(1);
+    VL_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
   if (lstm_clips_per_cluster(batch) == 4)
     return launch_lstm_bwd_cluster<4>(dh_seq, acts, cs, w_h, dg, batch, t_len, stream);
   return launch_lstm_bwd_cluster<8>(dh_seq, acts, cs, w_h, dg, batch, t_len, stream);
