@@ -21,6 +21,7 @@
 
 #include <atomic>
 #include <cstdlib>
+#include <cstring>
 
 namespace vl {
 extern std::atomic<long long> g_launches;
@@ -68,7 +69,19 @@ struct FParams {
   const float* bias;
   uint32_t idesc;
   int dbg;
+  int tma_store;                       // 1: the epilogue leaves through TMA tensor stores (tmY)
+  int direct;                          // 1: the epilogue stores 2-byte elements straight from registers (default)
 };
+
+// 16 positions x 128 channels of the epilogue stage -> out[n][h][w .. w+15][c .. c+127]; elements outside the tensor
+// (channels beyond c_ld, columns outside [0, Wo), rows beyond Ho) are clipped by the TMA unit.
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, uint32_t src, int32_t c0, int32_t c1, int32_t c2,
+                                             int32_t c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               :
+               : "l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
 
 __device__ __forceinline__ void tma_load_4d_u32(uint32_t dst, const CUtensorMap* m, uint32_t bar, int32_t c0, int32_t c1,
                                                 int32_t c2, int32_t c3) {
@@ -93,7 +106,7 @@ __device__ __forceinline__ FTile decode(const FParams& p, int tile) {
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
     conv_flat_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
-                     const __grid_constant__ FParams p) {
+                     const __grid_constant__ CUtensorMap tmY, const __grid_constant__ FParams p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   // the 1024-byte alignment is applied to the __shared__ array itself so that the compiler keeps the shared address
   // space (LDS/STS instead of generic LD/ST)
@@ -322,6 +335,35 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
       }
       // one 16-position chunk: registers -> stage[buf] -> global (static register indexing: no local memory)
       auto emit = [&](const uint32_t(&v)[16], int buf) {
+        if (p.direct) {
+          // Direct epilogue: lane = channel, so the 32 lanes of a warp write 64 contiguous bytes per position; no
+          // shared-memory transposition, no barrier between the four warps of a group - every epilogue warp runs on
+          // its own, and the short-K layers (conv1: 27 UMMAs per tile) are bound by exactly this code.
+          if (m_ok && !(p.dbg & 8)) {
+            int col = col_c, row = row_c;
+            int off = (row_c * p.Wo + col_c) * p.c_ld + m_local;  // tile-local element offset (fits 32 bits)
+            const int wrap_fix = (p.Wo - p.Wp) * p.c_ld;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float f = __uint_as_float(v[j]) + bv;
+              if (p.relu) f = fmaxf(f, 0.f);
+              if (col < p.Wo && row < rows_here) obase[off] = __float2bfloat16_rn(f);
+              ++col;
+              off += p.c_ld;
+              if (col == p.Wp) {
+                col = 0;
+                ++row;
+                off += wrap_fix;
+              }
+            }
+          }
+          col_c += 16 * EPI_GROUPS;
+          while (col_c >= p.Wp) {
+            col_c -= p.Wp;
+            ++row_c;
+          }
+          return;
+        }
         bf16* sb = stage + buf * (16 * 128);
         if (m_ok) {
 #pragma unroll
@@ -330,6 +372,28 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
             if (p.relu) f = fmaxf(f, 0.f);
             sb[j * 128 + m_local] = __float2bfloat16_rn(f);
           }
+        }
+        if (p.tma_store) {
+          // the stage leaves through the TMA unit: no per-thread addressing, junk columns / channels clipped by the
+          // tensor map.  Thread 0 of the group first waits until the store issued two chunks ago (same buffer as the
+          // NEXT chunk) has read its data, so that passing this barrier also frees that buffer.
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          if (etid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory");
+          if (etid == 0 && !(p.dbg & 8)) {
+            const uint32_t src = smem_u32(sb);
+            const int cch = t.g * p.c_goff + t.m_blk * 128;
+            if (row_c < rows_here && !(p.dbg & 32)) tma_store_4d(&tmY, src, cch, col_c, orow0 + row_c, t.img);
+            if (col_c + 16 > p.Wp && row_c + 1 < rows_here && !(p.dbg & 16))
+              tma_store_4d(&tmY, src, cch, col_c - p.Wp, orow0 + row_c + 1, t.img);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+          col_c += 16 * EPI_GROUPS;
+          while (col_c >= p.Wp) {
+            col_c -= p.Wp;
+            ++row_c;
+          }
+          return;
         }
         asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory");
         if (!(p.dbg & 8)) {
@@ -375,6 +439,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     }
   }
 
+  if (p.tma_store && warp >= 2 && ((threadIdx.x - 64) & 127) == 0)
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // the stage must outlive the last stores
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -510,7 +576,17 @@ extern "C" int vl_conv_flat(const vl_conv_flat_desc* d, const void* x, const voi
   p.x_box_bytes = box_rows * p.Wp * 128;
   p.x_stage_bytes = ((p.x_box_bytes + 1023) / 1024) * 1024;
   p.x_stages = MAX_X_STAGES;
-  const int STAGE_BYTES = EPI_GROUPS * 2 * 16 * 128 * 2;  // epilogue transposition stages (per group, double buffered)
+  // Epilogue modes.  Default: 16 positions x 128 channels are transposed through a shared-memory stage and leave
+  // through ONE TMA tensor store per chunk when the padded row width is a multiple of 16 (conv2: chunks never straddle
+  // rows; a store with a negative start column faults), else through per-thread 16-byte stores.  Measured at 1024
+  // frames (conv1 / conv2 forward, us): no epilogue at all 277 / 380, stage + 16-byte stores 377 / 424, stage + TMA
+  // store 342 (second store of straddling chunks skipped, i.e. incomplete) / 414, VL_FLAT_EPI=direct (2-byte stores
+  // straight from registers, lane = channel) 536 / 416: the 64-byte partial-line writes of the direct form are what
+  // the transposition avoids, and conv1 is bound by its main loop (277 us against a 163 us UMMA floor) before
+  // anything else.
+  const char* epi_env = getenv("VL_FLAT_EPI");
+  p.direct = (epi_env && !strcmp(epi_env, "direct")) ? 1 : 0;
+  const int STAGE_BYTES = p.direct ? 0 : EPI_GROUPS * 2 * 16 * 128 * 2;  // transposition stages (per group, double buffered)
   const int w_avail = SMEM_LIMIT - 1024 - BAR_REGION - STAGE_BYTES - 1024 - p.x_stages * p.x_stage_bytes;
   // filter box: only the rows that exist (8-row swizzle atoms); the UMMA reads 128 rows, the surplus lanes are
   // never stored
@@ -541,7 +617,28 @@ extern "C" int vl_conv_flat(const vl_conv_flat_desc* d, const void* x, const voi
   // instruction descriptor: D=f32, A=B=bf16 K-major, N>>3 at bit 17, M>>4 at bit 24
   p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.npos >> 3) << 17) | ((128u >> 4) << 24);
 
-  CUtensorMap tmX, tmW;
+  CUtensorMap tmX, tmW, tmY;
+  // epilogue through TMA stores: a 128-channel box must not spill into the channels of another group / m-block
+  // (a 16-position chunk may touch at most two output rows: Wp >= 16)
+  // (TMA stores fault on a negative start coordinate, measured: chunks must not straddle rows -> Wp % 16 == 0)
+  p.tma_store = ((d->cout_g % 128 == 0) || d->groups == 1) && (d->c_ld % 8 == 0) && p.Wp % 16 == 0 &&
+                        ((reinterpret_cast<uintptr_t>(out) & 15) == 0) && !p.direct && !(epi_env && !strcmp(epi_env, "stage"))
+                    ? 1
+                    : 0;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)d->c_ld, (cuuint64_t)p.Wo, (cuuint64_t)p.Ho, (cuuint64_t)d->n};
+    cuuint64_t strides[3] = {(cuuint64_t)d->c_ld * 2, (cuuint64_t)d->c_ld * p.Wo * 2,
+                             (cuuint64_t)d->c_ld * p.Wo * p.Ho * 2};
+    cuuint32_t box[4] = {128, 16, 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = g_encode(&tmY, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, out, dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      p.tma_store = 0;  // e.g. an exotic pitch: the per-thread store path serves it
+      memset(&tmY, 0, sizeof(tmY));
+    }
+  }
   {
     cuuint64_t dims[4] = {(cuuint64_t)d->c, (cuuint64_t)d->w, (cuuint64_t)d->h, (cuuint64_t)d->n};
     cuuint64_t strides[3] = {(cuuint64_t)d->c * 2, (cuuint64_t)d->c * d->w * 2, (cuuint64_t)d->c * d->w * d->h * 2};
@@ -569,7 +666,7 @@ extern "C" int vl_conv_flat(const vl_conv_flat_desc* d, const void* x, const voi
     attr_set = true;
   }
   const int grid = p.total_tiles < vl::num_sms() ? p.total_tiles : vl::num_sms();
-  conv_flat_kernel<<<grid, NUM_THREADS, smem_bytes, stream>>>(tmX, tmW, p);
+  conv_flat_kernel<<<grid, NUM_THREADS, smem_bytes, stream>>>(tmX, tmW, tmY, p);
   vl::g_launches.fetch_add(1);
   VL_CHECK_CUDA(cudaGetLastError());
   return 0;
