@@ -156,6 +156,16 @@ int vl_frames_s2d(const void* frames, int32_t is_u8, const float* mean3, void* o
 int vl_frames_s2d_crop(const void* frames, int32_t is_u8, const float* mean3, void* out, int32_t n, int32_t hr,
                        int32_t wr, const int32_t* crops, int32_t h, int32_t w, int32_t s, int32_t pad_top,
                        int32_t pad_left, int32_t hb, int32_t wb, vl_stream_t stream);
+/* Read-time resampling of the reference (dataset_.py:238,484,491; serialize.py:425): scipy.misc.imresize(image, shape)
+ * with its default bilinear filter = Pillow's 8-bit ImagingResample: horizontal pass, then vertical pass, each rounded
+ * to uint8, 22-bit fixed-point coefficients.  in: uint8 [n][h_in][w_in][channels] -> out: uint8 [n][h_out][w_out][channels]
+ * (bit-exact against PIL).  bounds_* = DEVICE int32 [out][2] (first input index, tap count), coeffs_* = DEVICE int32
+ * [out][ksize_*], computed by the host exactly as Pillow's precompute_coeffs (resize.py: pil_bilinear_coeffs); an axis
+ * whose size does not change needs none.  tmp = uint8 [n][h_in][w_out][channels] scratch when both axes change. */
+int vl_resize_bilinear_u8(const void* in, void* out, void* tmp, int32_t n, int32_t h_in, int32_t w_in, int32_t h_out,
+                          int32_t w_out, int32_t channels, const int32_t* bounds_w, const int32_t* coeffs_w,
+                          int32_t ksize_w, const int32_t* bounds_h, const int32_t* coeffs_h, int32_t ksize_h,
+                          vl_stream_t stream);
 /* Filter of that convolution: HWIO fp32 [kh][kw][cin][cout] -> bf16 [taps][chunk][cout] (chunk >= s*s*cin rows per
  * tap, zero padded), and the inverse scatter of its filter gradient dws[taps*s*s*cin][cout] -> HWIO dw. */
 int vl_s2d_pack_filter(const float* src, void* dst, int32_t kh, int32_t kw, int32_t cin, int32_t cout, int32_t s,

@@ -234,6 +234,34 @@ def test_staging_with_crop_and_mirror_bit_exact(vl):
     assert np.array_equal(xs.float().cpu().numpy(), bf16_round(ref))
 
 
+def test_resize_bilinear_bit_exact_against_pil_golden(vl):
+    """vl_resize_bilinear_u8 (csrc/resize.cu) == PIL.Image.resize(BILINEAR) on the golden vectors, also batched."""
+    import importlib
+    import os
+    P = importlib.import_module("video-learning-tf_b200.resize")
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "resize_bilinear_golden.npz"))
+    rz = P.DeviceResizer("cuda")
+    i = 0
+    while "in_%d" % i in g:
+        src, ref = g["in_%d" % i], g["out_%d" % i]
+        batch = np.stack([src, src[::-1].copy(), src])
+        out = rz.resize(dev(batch), ref.shape[0], ref.shape[1]).cpu().numpy()
+        assert out.dtype == np.uint8 and np.array_equal(out[0], ref) and np.array_equal(out[2], ref), i
+        assert np.array_equal(out[1], O_resize(src[::-1].copy(), ref.shape[0], ref.shape[1])), i
+        i += 1
+    assert i >= 6
+    # one axis only (the other pass is skipped), and the identity
+    src = g["in_0"]
+    for (oh, ow) in ((src.shape[0], 29), (19, src.shape[1]), src.shape[:2]):
+        out = rz.resize(dev(src[None]), oh, ow).cpu().numpy()[0]
+        assert np.array_equal(out, O_resize(src, oh, ow)), (oh, ow)
+
+
+def O_resize(img, oh, ow):
+    from oracle import resize_pil as R
+    return R.imresize_bilinear(img, oh, ow)
+
+
 @pytest.mark.parametrize("c", [96, 256])
 def test_lrn_fwd_bwd_vs_oracle(vl, c):
     nv = vl["nv"]

@@ -121,3 +121,58 @@ def test_run_task_on_a_serialized_tfrecord_dataset(tmp_path):
                     - np.array(mean, np.float32) for i, (y, x, m) in enumerate(ds.last_crops)])
     ref = eng.forward(pre)  # fp32 feed of already-preprocessed frames (feeder.py:97-100 contract)
     assert np.array_equal(got, ref)
+
+
+def test_raw_resize_on_the_device_equals_pil_then_crop(tmp_path):
+    """imgproc raw_resize + center_crop (dataset_.py:481-491): frames serialized at 120x160 are resampled to
+    raw_image_shape on the device with Pillow's bilinear (bit-exact: the oracle restatement is pinned on PIL's own
+    outputs) and then cropped; the engine's logits equal its logits on frames preprocessed on the host."""
+    import torch
+    import vlb200  # noqa: F401
+    from oracle import resize_pil as R
+    from vlb200 import run_task, tfrecord
+    from vlb200.defs import defs
+    from vlb200.engine import Engine, EngineConfig
+    from vlb200.feeder import Dataset
+
+    rng = np.random.default_rng(6)
+    cpv, fpc, stored, raw_shape = [1, 1, 2], 2, (120, 160, 3), (240, 250, 3)
+    base = str(tmp_path / "small_frames")
+    with open(base + ".tfrecord", "wb") as f:
+        for v, c in enumerate(cpv):
+            for _ in range(c * fpc):
+                tfrecord.write_record(f, tfrecord.serialize_frame(rng.integers(0, 256, size=stored, dtype=np.uint8), [v]))
+    tfrecord.write_size_file(base + ".size", cpv, fpc)
+
+    opts = types.SimpleNamespace(name="t", data_format=defs.data_format.tfrecord, data_path=base, image_shape=(227, 227, 3),
+                                 num_frames_per_clip=fpc, imgproc=[defs.imgproc.raw_resize, defs.imgproc.center_crop],
+                                 raw_image_shape=raw_shape, verify_records="full", mean_image=None)
+    ds = Dataset(opts, batch_size=4, num_classes=101, epochs=1, save_freq_per_epoch=1)
+    assert ds.resize_to == (240, 250)
+    frames, onehot, _ = ds.next_batch()
+    assert frames.shape == (8, 120, 160, 3) and frames.dtype == np.uint8  # still at the serialized size on the host
+    mean = (99.197148, 105.293620, 109.503945)
+    cfg = EngineConfig(workflow="lrcn", fusion="avg", fpc=fpc, num_classes=101, lstm_hidden=256, mean=mean)
+    eng = Engine(cfg, max_clips=4)
+    eng.set_read_resize(ds.resize_to)
+    got = eng.forward(frames, ds.last_crops)
+    resized = R.imresize_bilinear(frames, 240, 250)
+    y0, x0 = ds.last_crops[0, 0], ds.last_crops[0, 1]
+    assert (y0, x0) == ((240 - 227) // 2, (250 - 227) // 2)
+    pre = resized[:, y0:y0 + 227, x0:x0 + 227].astype(np.float32) - np.array(mean, np.float32)
+    eng.set_read_resize(None)
+    ref = eng.forward(pre)
+    assert np.array_equal(got, ref)
+
+    # and the whole workflow runs with imgproc resize (no crop): frames resampled straight to the network input
+    def mutate(run):
+        run["data"] = {"ucf": {"data_format": "defs.data_format.tfrecord", "data_path": base,
+                               "image_shape": "(227, 227, 3)",
+                               "imgproc": ["defs.imgproc.resize", "defs.imgproc.sub_mean"],
+                               "mean_image": [99.197148, 105.293620, 109.503945], "num_frames_per_clip": fpc,
+                               "phase": "defs.phase.train", "tag": "defs.dataset_tag.main"}}
+        run["train"]["batch_size"] = 2
+        run["train"]["epochs"] = 1
+    run_task.main(_cfg("config2_lrcn_train.yml", tmp_path, mutate))
+    names = [l.strip() for l in open(tmp_path / "run" / "checkpoints" / "checkpoint") if l.strip()]
+    assert names and names[-1].endswith("gs_2.graph-2")

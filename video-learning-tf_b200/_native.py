@@ -98,6 +98,7 @@ def _declare(L):
         "vl_softmax_ce": [vp, vp, i32, i32, f32, vp, vp, vp, vp, i32, vp],
         "vl_grad_sqnorms": [vp, i64, vp, i32, vp, vp],
         "vl_clip_scalars": [vp, i32, f32, f32, vp, vp],
+        "vl_resize_bilinear_u8": [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, i32, vp, vp, i32, vp],
         "vl_sgd_update": [vp, vp, i64, f32, vp, f32, vp],
         "vl_sgd_update_shadow": [vp, vp, i64, f32, vp, f32, i32, vp, vp, vp, vp],
         "vl_adam_update": [vp, vp, vp, vp, i64, f32, f32, f32, f32, i32, vp, f32, vp],
@@ -114,7 +115,7 @@ EXPORTS = ["vl_last_error", "vl_version", "vl_device_sm_count", "vl_launch_count
            "vl_lstm_fwd_cluster", "vl_lstm_bwd_cluster", "vl_frames_s2d", "vl_frames_s2d_crop", "vl_pack_bf16_t", "vl_s2d_pack_filter", "vl_s2d_unpack_grad",
            "vl_lrn_pool_fwd_generic", "vl_pool_lrn_bwd_generic", "vl_segment_pool_fwd",
            "vl_segment_pool_bwd", "vl_dropout_mask", "vl_mul", "vl_softmax_ce", "vl_grad_sqnorms",
-           "vl_clip_scalars", "vl_sgd_update", "vl_sgd_update_shadow", "vl_adam_update"]
+           "vl_clip_scalars", "vl_resize_bilinear_u8", "vl_sgd_update", "vl_sgd_update_shadow", "vl_adam_update"]
 
 
 def check(status):

@@ -180,6 +180,8 @@ class Engine(object):
         # read-back of the step scalars: they are final after vl_clip_scalars, so the host copy waits on an event recorded
         # there (not on the optimiser update / operand refresh that follow) and the next step is enqueued while the
         # tail of this one still runs - the device never idles between steps
+        self.read_resize = None
+        self._resizer = None
         self._rb_stream = torch.cuda.Stream(device=self.dev)
         self._scalars_host = torch.zeros(8, dtype=F32).pin_memory()
         self._scalars_ready = None
@@ -428,7 +430,19 @@ class Engine(object):
             dst = self._frame_buffer(frames.shape[1:3], frames.dtype)
             dst[:n].copy_(frames, non_blocking=True)
             frames = dst[:n]
+        if self.read_resize is not None and frames.dtype == torch.uint8 and \
+                tuple(int(x) for x in frames.shape[1:3]) != tuple(self.read_resize):
+            # imgproc raw_resize / resize of the reference (dataset_.py:481-491): scipy.misc.imresize at read time
+            if self._resizer is None:
+                from .resize import DeviceResizer
+                self._resizer = DeviceResizer(self.dev)
+            frames = self._resizer.resize(frames, int(self.read_resize[0]), int(self.read_resize[1]))
         return frames, frames.dtype == torch.uint8, n
+
+    def set_read_resize(self, hw):
+        """Resample uint8 frames to (h, w) on the device before crop / staging (None: frames arrive at their final
+        stored size).  Mirrors `imresize(image, raw_image_shape)` / `imresize(image, desired_image_shape)`."""
+        self.read_resize = None if hw is None else (int(hw[0]), int(hw[1]))
 
     def _stage_crops(self, crops, frames, n):
         """Per-frame (y0, x0, mirror) int32 triples on the device; None when the frames already have the input shape."""

@@ -63,11 +63,23 @@ class Dataset(object):
             self._records = None
             self.verify = getattr(opts, "verify_records", "length")
             self.imgproc = list(getattr(opts, "imgproc", []) or [])
-            for unsupported in (defs.imgproc.resize, defs.imgproc.raw_resize):
-                if unsupported in self.imgproc:
-                    error("imgproc %s resamples images with scipy.misc.imresize at read time; serialize the frames at "
-                          "the raw / network size instead (resampling is outside the hot path)" % unsupported)
             self.raw_shape = tuple(getattr(opts, "raw_image_shape", None) or (h, w, 3))
+            # imgproc raw_resize / resize (dataset_.py:481-491): scipy.misc.imresize at read time.  The frames stay at
+            # their serialized size on the host; the engine resamples them on the device (Engine.set_read_resize,
+            # csrc/resize.cu: Pillow's bilinear, bit-exact) before the crop / staging kernel.
+            self.resize_to = None
+            if defs.imgproc.raw_resize in self.imgproc:
+                if getattr(opts, "raw_image_shape", None) is None:
+                    error("imgproc raw_resize needs raw_image_shape")
+                self.resize_to = tuple(self.raw_shape[:2])
+            has_crop = defs.imgproc.rand_crop in self.imgproc or defs.imgproc.center_crop in self.imgproc
+            if defs.imgproc.resize in self.imgproc and not has_crop:  # dataset_.py:486-491: crop wins over resize
+                if self.resize_to is not None:
+                    error("imgproc raw_resize followed by resize resamples every frame twice; serialize the frames at "
+                          "raw_image_shape or drop one of the two")
+                self.resize_to = (h, w)
+                self.raw_shape = (h, w, 3)
+            self.stored_shape = None  # serialized frame shape, read from the first record when a resize is active
             self.crop_h = self.crop_w = None
             if defs.imgproc.rand_crop in self.imgproc:  # dataset_.py:571-577: ranges of admissible offsets
                 self.crop_h = list(range(0, self.raw_shape[0] - h - 1))
@@ -82,6 +94,8 @@ class Dataset(object):
             error("data_format %s reads loose image files with scipy.misc.imread, which is outside the hot path; "
                   "serialize them (tfrecord) or use defs.data_format.synthetic / npy" % opts.data_format)
         self.last_crops = None
+        if not hasattr(self, "resize_to"):
+            self.resize_to = None
         if len(self.clips_per_video) != self.num_items:
             error("clips_per_video has %d entries for %d items" % (len(self.clips_per_video), self.num_items))
         self.num_batches = math.ceil(self.num_items / self.batch_size)
@@ -109,7 +123,7 @@ class Dataset(object):
         """n consecutive frames of the serialization (dataset_.py:171-217) + their crop / mirror draws."""
         if self._records is None:
             self._records = self._tfrecord.read_records(self.tfr_path, self.verify)
-        frames = np.empty((n,) + tuple(self.raw_shape), np.uint8)
+        frames = None if self.resize_to is not None else np.empty((n,) + tuple(self.raw_shape), np.uint8)
         labels, crops = [], np.zeros((n, 3), np.int32)
         h, w = self.net_hw
         for i in range(n):
@@ -118,7 +132,14 @@ class Dataset(object):
             except StopIteration:
                 error("Encountered unexpected EOF while reading TFRecord example # %d in the batch." % i)
             image, label = self._tfrecord.deserialize_frame(payload)
-            if image.shape != tuple(self.raw_shape):
+            if self.resize_to is not None:
+                if frames is None:  # frames keep their serialized size; the device resamples them
+                    self.stored_shape = tuple(image.shape)
+                    frames = np.empty((n,) + self.stored_shape, np.uint8)
+                if image.shape != self.stored_shape:
+                    error("Encountered image shape %s after %s: one batch must hold frames of one serialized size" % (
+                        str(image.shape), str(self.stored_shape)))
+            elif image.shape != tuple(self.raw_shape):
                 error("Encountered image shape %s but the dataset declares %s" % (str(image.shape), str(self.raw_shape)))
             frames[i] = image
             labels.append(label)

@@ -90,6 +90,7 @@ def main(init_file, device="cuda:0"):
         mean = None  # dataset_.py:494-495: the mean is subtracted only when imgproc lists sub_mean
     cfg.mean = tuple(mean) if mean is not None else None
     engine = Engine(cfg, max_clips=feeder.max_clips_per_batch(), device=device)
+    engine.set_read_resize(getattr(feeder.main, "resize_to", None))  # imgproc raw_resize / resize on the device
     if settings.should_resume():
         prefix = checkpoint.resolve(settings.run_folder, settings.resume_file)
         batch_index, epoch_index, gstep = checkpoint.restore(engine, prefix, is_validation=not settings.train)
