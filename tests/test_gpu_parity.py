@@ -647,3 +647,51 @@ def _oracle_backward_on_device_state(eng, cfg, params, frames, onehot, mask):
                      feat_shape=feat.shape)
         grads = O.lrcn_backward(params, cache, dlogits, q)
     return grads, float(O.global_norm(grads))
+
+
+def test_full_size_properties_config2(vl):
+    """BASELINE.json configs[1] at its FULL size (64 clips x 16 frames per GPU), where the oracle would take minutes:
+    size-independent properties of the path.
+      (1) batch independence: the first 8 clips of the 64-clip forward == the 8-clip forward, bit for bit
+          (every frame / clip is processed by the same tile arithmetic whatever its neighbours are);
+      (2) permutation: reversing the clip order reverses the logits rows bit for bit, and the mean loss of the train
+          step is unchanged up to the order of the final sums;
+      (3) clip -> video fusion of the 64 rows on the device == numpy on the host (val.py:158-167), labels bit exact;
+      (4) loss / accuracy read back from the step equal the softmax cross-entropy of the device logits."""
+    E, nv = vl["E"], vl["nv"]
+    clips, fpc, c = 64, 16, 101
+    cfg = E.EngineConfig(workflow="lrcn", fusion="avg", fpc=fpc, num_classes=c, lstm_hidden=256, clip_norm=10,
+                         dropout_keep_prob=0.0, optimizer="sgd", mean=(99.197148, 105.293620, 109.503945))
+    eng = E.Engine(cfg, max_clips=clips, params=E.init_variables(cfg, seed=3))
+    g = torch.Generator(device="cuda").manual_seed(5)
+    frames = torch.randint(0, 256, (clips * fpc, 227, 227, 3), dtype=torch.uint8, device="cuda", generator=g)
+    labels = np.random.default_rng(6).integers(0, c, clips)
+    onehot = np.zeros((clips, c), np.int32)
+    onehot[np.arange(clips), labels] = 1
+    full = eng.forward(frames)
+    assert full.shape == (clips, c) and np.isfinite(full).all()
+    # (1)
+    part = eng.forward(frames[:8 * fpc].contiguous())
+    assert np.array_equal(part, full[:8])
+    # (2) forward
+    rev_frames = frames.view(clips, fpc, 227, 227, 3).flip(0).reshape(clips * fpc, 227, 227, 3).contiguous()
+    rev = eng.forward(rev_frames)
+    assert np.array_equal(rev[::-1], full)
+    # (3) videos of 1..7 clips
+    cpv = [3, 1, 7, 5, 2, 6, 4, 1, 7, 3, 5, 2, 6, 4, 7, 1]
+    assert sum(cpv) == clips
+    seg = np.concatenate([[0], np.cumsum(cpv)]).astype(np.int32)
+    y = torch.empty(len(cpv), c, device="cuda")
+    nv.call("vl_segment_pool_fwd", dev(full), dev(seg), 0, len(cpv), c, 0, y, None)
+    ref = np.stack([np.mean(full[seg[i]:seg[i + 1]], axis=0) for i in range(len(cpv))]).astype(np.float32)
+    assert np.array_equal(y.cpu().numpy(), ref) and np.array_equal(y.cpu().numpy().argmax(1), ref.argmax(1))
+    # (4) + (2) train step (no update: the weights stay those of the forward passes above)
+    loss, _, _, acc, gnorm = eng.train_step(frames, onehot, 1e-3, apply_update=False)
+    z = full.astype(np.float64)
+    lse = np.log(np.exp(z - z.max(1, keepdims=True)).sum(1)) + z.max(1)
+    ce = float(np.mean(lse - z[np.arange(clips), labels]))
+    assert abs(loss - ce) < 1e-4 * max(1.0, abs(ce))
+    assert acc == float(np.mean(full.argmax(1) == labels))
+    loss_rev, _, _, acc_rev, gnorm_rev = eng.train_step(rev_frames, onehot[::-1].copy(), 1e-3, apply_update=False)
+    assert abs(loss_rev - loss) < 1e-5 * max(1.0, abs(loss)) and acc_rev == acc
+    assert abs(gnorm_rev - gnorm) < 2e-2 * gnorm  # split-K atomics / bf16 partial sums: order-dependent rounding only
