@@ -208,75 +208,170 @@ __global__ void __launch_bounds__(256)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
     frames_s2d_fast_kernel(const uint8_t* __restrict__ frames, const float* __restrict__ mean3, bf16* __restrict__ out,
-                           int h, int w, int pad_top, int pad_left, int hb, int wb, long long total_bytes) {
+                           int h, int w, int pad_top, int pad_left, int hb, int wb, long long total_bytes, int n_units) {
   constexpr int S = 4, SEG = 12, CBLK = 48, ROWS = 2;
   extern __shared__ __align__(16) uint8_t smem_raw[];
   bf16* orow_s = reinterpret_cast<bf16*>(smem_raw);  // [ROWS][wb][48]
   const int pairs = (hb + ROWS - 1) / ROWS;
-  const int by0 = (blockIdx.x % pairs) * ROWS;
-  const int nn = blockIdx.x / pairs;
-  const int nrows = min(ROWS, hb - by0);
   float m[3] = {0.f, 0.f, 0.f};
   if (mean3 != nullptr) {
     m[0] = mean3[0];
     m[1] = mean3[1];
     m[2] = mean3[2];
   }
-  const int items = nrows * S * wb;
-  const long long frame_off = (long long)nn * h * w * 3;
   const int row_bytes = w * 3;
-  for (int it = threadIdx.x; it < items; it += blockDim.x) {
-    const int bx = it % wb;
-    const int t = it / wb;
-    const int dy = t % S;
-    const int br = t / S;
-    const int y = (by0 + br) * S - pad_top + dy;
-    const int xb = bx * SEG - pad_left * 3;  // first source byte of the segment inside the frame row
-    uint32_t o[6] = {0u, 0u, 0u, 0u, 0u, 0u};
-    if (y >= 0 && y < h && xb + SEG > 0 && xb < row_bytes) {
-      // absolute addresses: the frames pointer itself may be unaligned (a slice of a batch)
-      const uintptr_t lo = reinterpret_cast<uintptr_t>(frames), hi = lo + (uintptr_t)total_bytes;
-      const uintptr_t a = lo + (uintptr_t)(frame_off + (long long)y * row_bytes + xb);  // may precede lo when xb < 0
-      const uintptr_t a4 = a & ~(uintptr_t)3;
-      uint32_t wd[4];
+  // persistent CTAs walk the (frame, block-row pair) units: 60 k one-shot CTAs of ~470 items each were bound by their
+  // launch / drain overhead, not by the 500 MB they move
+  // thread -> (block column bx = tid & 63, image row dy = tid >> 6 of the block row): no index divisions; 59 of 64
+  // lanes carry data for wb = 59
+  const int bx = threadIdx.x & 63, dy = threadIdx.x >> 6;
+  const int xb = bx * SEG - pad_left * 3;  // first source byte of the segment inside the frame row
+  const bool seg_any = bx < wb && xb + SEG > 0 && xb < row_bytes;
+  const bool seg_full = xb >= 0 && xb + SEG <= row_bytes;  // no padding byte inside the segment (all but the edges)
+  const uintptr_t lo = reinterpret_cast<uintptr_t>(frames), hi = lo + (uintptr_t)total_bytes;
+  for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+    const int nn = unit / pairs;
+    const int by0 = (unit - nn * pairs) * ROWS;
+    const int nrows = min(ROWS, hb - by0);
+    const long long frame_off = (long long)nn * h * w * 3;
+    if (bx < wb) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const uintptr_t p = a4 + 4 * k;
-        if (p >= lo && p + 4 <= hi) {
-          wd[k] = __ldg(reinterpret_cast<const uint32_t*>(p));
-        } else {  // first / last word of the whole tensor: byte loads
-          wd[k] = 0u;
-          for (int j = 0; j < 4; ++j)
-            if (p + j >= lo && p + j < hi) wd[k] |= (uint32_t)__ldg(reinterpret_cast<const uint8_t*>(p + j)) << (8 * j);
+      for (int br = 0; br < ROWS; ++br) {
+        if (br >= nrows) break;
+        const int y = (by0 + br) * S - pad_top + dy;
+        uint32_t o[6] = {0u, 0u, 0u, 0u, 0u, 0u};
+        if (seg_any && y >= 0 && y < h) {
+          // absolute addresses: the frames pointer itself may be unaligned (a slice of a batch)
+          const uintptr_t a = lo + (uintptr_t)(frame_off + (long long)y * row_bytes + xb);  // may precede lo (xb < 0)
+          const uintptr_t a4 = a & ~(uintptr_t)3;
+          uint32_t wd[4];
+          if (a4 >= lo && a4 + 16 <= hi) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) wd[k] = __ldg(reinterpret_cast<const uint32_t*>(a4) + k);
+          } else {  // first / last bytes of the whole tensor
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              wd[k] = 0u;
+              for (int j = 0; j < 4; ++j) {
+                const uintptr_t pb = a4 + 4 * k + j;
+                if (pb >= lo && pb < hi) wd[k] |= (uint32_t)__ldg(reinterpret_cast<const uint8_t*>(pb)) << (8 * j);
+              }
+            }
+          }
+          const uint32_t sh = (uint32_t)(a - a4) * 8u;
+          const uint32_t b3[3] = {__funnelshift_r(wd[0], wd[1], sh), __funnelshift_r(wd[1], wd[2], sh),
+                                  __funnelshift_r(wd[2], wd[3], sh)};
+          float v[12];
+#pragma unroll
+          for (int e = 0; e < 12; ++e) {
+            // 0x4B0000bb = 2^23 + b exactly; channel of element e is e % 3 (segments start on a pixel boundary)
+            const uint32_t bits = __byte_perm(b3[e >> 2], 0x4B000000u, 0x7440u | (uint32_t)(e & 3));
+            v[e] = (__uint_as_float(bits) - 8388608.0f) - m[e % 3];
+          }
+          if (!seg_full) {  // bytes left of the frame row (xb < 0) or beyond it are padding
+#pragma unroll
+            for (int e = 0; e < 12; ++e)
+              if (xb + e < 0 || xb + e >= row_bytes) v[e] = 0.f;
+          }
+#pragma unroll
+          for (int i = 0; i < 6; ++i) {
+            const __nv_bfloat162 pk = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+            o[i] = *reinterpret_cast<const uint32_t*>(&pk);
+          }
+        }
+        uint2* dst = reinterpret_cast<uint2*>(orow_s + (br * wb + bx) * CBLK + dy * SEG);
+        dst[0] = make_uint2(o[0], o[1]);
+        dst[1] = make_uint2(o[2], o[3]);
+        dst[2] = make_uint2(o[4], o[5]);
+      }
+    }
+    __syncthreads();
+    uint4* dstg = reinterpret_cast<uint4*>(out + ((long long)nn * hb + by0) * wb * CBLK);
+    const int nvec = nrows * wb * CBLK / 8;
+    for (int i = threadIdx.x; i < nvec; i += blockDim.x) dstg[i] = reinterpret_cast<const uint4*>(orow_s)[i];
+  __syncthreads();  // the stage is rewritten by the next unit
+  }
+}
+
+// Register-only form of the fast staging: a thread owns one output block (frame, by, bx) = 4 image rows x 12 source
+// bytes -> 48 contiguous bf16 (96 bytes); no shared memory and no barriers (the staged form spent its time waiting on
+// two __syncthreads per 11 KB of output).  Loads of a warp walk 32 x 12 contiguous bytes of each of the four rows,
+// stores cover 32 x 96 contiguous bytes.
+__global__ void __launch_bounds__(128)
+    frames_s2d_direct_kernel(const uint8_t* __restrict__ frames, const float* __restrict__ mean3, bf16* __restrict__ out,
+                             int h, int w, int pad_top, int pad_left, int hb, int wb, long long total_bytes,
+                             int n_rows /* n * hb */) {
+  constexpr int S = 4, SEG = 12, CBLK = 48;
+  float m[3] = {0.f, 0.f, 0.f};
+  if (mean3 != nullptr) {
+    m[0] = mean3[0];
+    m[1] = mean3[1];
+    m[2] = mean3[2];
+  }
+  const int row_bytes = w * 3;
+  const int bx = threadIdx.x & 63;           // 64 block columns per half CTA (wb <= 64), two block rows per CTA
+  const int half = threadIdx.x >> 6;
+  const int xb = bx * SEG - pad_left * 3;
+  const bool seg_any = bx < wb && xb + SEG > 0 && xb < row_bytes;
+  const bool seg_full = xb >= 0 && xb + SEG <= row_bytes;
+  const uintptr_t lo = reinterpret_cast<uintptr_t>(frames), hi = lo + (uintptr_t)total_bytes;
+  for (int rowi = blockIdx.x * 2 + half; rowi < n_rows; rowi += gridDim.x * 2) {
+    if (bx >= wb) continue;
+    const int nn = rowi / hb;
+    const int by = rowi - nn * hb;
+    const long long frame_off = (long long)nn * h * w * 3;
+    uint32_t wd[S][4];
+    bool ok[S];
+#pragma unroll
+    for (int dy = 0; dy < S; ++dy) {
+      const int y = by * S - pad_top + dy;
+      ok[dy] = seg_any && y >= 0 && y < h;
+      wd[dy][0] = wd[dy][1] = wd[dy][2] = wd[dy][3] = 0u;
+      if (ok[dy]) {
+        const uintptr_t a = lo + (uintptr_t)(frame_off + (long long)y * row_bytes + xb);
+        const uintptr_t a4 = a & ~(uintptr_t)3;
+        if (a4 >= lo && a4 + 16 <= hi) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) wd[dy][k] = __ldg(reinterpret_cast<const uint32_t*>(a4) + k);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            for (int j = 0; j < 4; ++j) {
+              const uintptr_t pb = a4 + 4 * k + j;
+              if (pb >= lo && pb < hi) wd[dy][k] |= (uint32_t)__ldg(reinterpret_cast<const uint8_t*>(pb)) << (8 * j);
+            }
         }
       }
-      const uint32_t sh = (uint32_t)(a - a4) * 8u;
-      const uint32_t b3[3] = {__funnelshift_r(wd[0], wd[1], sh), __funnelshift_r(wd[1], wd[2], sh),
-                              __funnelshift_r(wd[2], wd[3], sh)};
+    }
+    uint32_t o[24];
+#pragma unroll
+    for (int dy = 0; dy < S; ++dy) {
+      const int y = by * S - pad_top + dy;
+      const uintptr_t a = lo + (uintptr_t)(frame_off + (long long)y * row_bytes + xb);
+      const uint32_t sh = (uint32_t)(a & 3) * 8u;
+      const uint32_t b3[3] = {__funnelshift_r(wd[dy][0], wd[dy][1], sh), __funnelshift_r(wd[dy][1], wd[dy][2], sh),
+                              __funnelshift_r(wd[dy][2], wd[dy][3], sh)};
       float v[12];
 #pragma unroll
       for (int e = 0; e < 12; ++e) {
-        // 0x4B0000bb = 2^23 + b exactly; channel of element e is e % 3 (segments start on a pixel boundary)
         const uint32_t bits = __byte_perm(b3[e >> 2], 0x4B000000u, 0x7440u | (uint32_t)(e & 3));
         v[e] = (__uint_as_float(bits) - 8388608.0f) - m[e % 3];
-        const int xs = xb + e;  // bytes left of the frame row (xb < 0) or beyond it are padding
-        if (xs < 0 || xs >= row_bytes) v[e] = 0.f;
+      }
+      if (!seg_full) {
+#pragma unroll
+        for (int e = 0; e < 12; ++e)
+          if (xb + e < 0 || xb + e >= row_bytes) v[e] = 0.f;
       }
 #pragma unroll
       for (int i = 0; i < 6; ++i) {
         const __nv_bfloat162 pk = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-        o[i] = *reinterpret_cast<const uint32_t*>(&pk);
+        o[dy * 6 + i] = ok[dy] ? *reinterpret_cast<const uint32_t*>(&pk) : 0u;
       }
     }
-    uint2* dst = reinterpret_cast<uint2*>(orow_s + (br * wb + bx) * CBLK + dy * SEG);
-    dst[0] = make_uint2(o[0], o[1]);
-    dst[1] = make_uint2(o[2], o[3]);
-    dst[2] = make_uint2(o[4], o[5]);
+    uint4* dst = reinterpret_cast<uint4*>(out + ((long long)rowi * wb + bx) * CBLK);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) dst[k] = make_uint4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
   }
-  __syncthreads();
-  uint4* dstg = reinterpret_cast<uint4*>(out + ((long long)nn * hb + by0) * wb * CBLK);
-  const int nvec = nrows * wb * CBLK / 8;
-  for (int i = threadIdx.x; i < nvec; i += blockDim.x) dstg[i] = reinterpret_cast<const uint4*>(orow_s)[i];
 }
 
 // dst[(tr*kb+ts)*chunk + (dy*s+dx)*cin + c][o] = src[s*tr+dy][s*ts+dx][c][o] (0 when outside the kh x kw filter or
@@ -1060,10 +1155,24 @@ extern "C" int vl_frames_s2d_crop(const void* frames, int32_t is_u8, const float
   const size_t smem = (size_t)wb * s * s * 3 * sizeof(bf16);
   VL_REQUIRE(smem <= 48 * 1024, "vl_frames_s2d: image row too wide (%zu bytes of shared memory)", smem);
   if (is_u8 && crops == nullptr && pad_left % 4 == 0 && pad_top >= 0 && !getenv("VL_S2D_SLOW")) {
+    if (wb <= 64 && !(getenv("VL_S2D_MODE") && atoi(getenv("VL_S2D_MODE")) == 1)) {
+      const int n_rows = n * hb;
+      const int per_sm_d = getenv("VL_S2D_CTAS") ? atoi(getenv("VL_S2D_CTAS")) : 16;
+      const int want = (n_rows + 1) / 2;
+      const int grid_d = want < vl::num_sms() * per_sm_d ? want : vl::num_sms() * per_sm_d;
+      frames_s2d_direct_kernel<<<grid_d, 128, 0, stream>>>(reinterpret_cast<const uint8_t*>(frames), mean3,
+                                                          reinterpret_cast<bf16*>(out), h, w, pad_top, pad_left, hb, wb,
+                                                          (long long)n * h * w * 3, n_rows);
+      VL_LAUNCHED();
+      return 0;
+    }
     const int pairs = (hb + 1) / 2;
-    frames_s2d_fast_kernel<<<n * pairs, 256, 2 * smem, stream>>>(reinterpret_cast<const uint8_t*>(frames), mean3,
-                                                                  reinterpret_cast<bf16*>(out), h, w, pad_top, pad_left,
-                                                                  hb, wb, (long long)n * h * w * 3);
+    const int n_units = n * pairs;
+    const int per_sm = getenv("VL_S2D_CTAS") ? atoi(getenv("VL_S2D_CTAS")) : 8;
+    const int grid_fast = n_units < vl::num_sms() * per_sm ? n_units : vl::num_sms() * per_sm;
+    frames_s2d_fast_kernel<<<grid_fast, 256, 2 * smem, stream>>>(reinterpret_cast<const uint8_t*>(frames), mean3,
+                                                                 reinterpret_cast<bf16*>(out), h, w, pad_top, pad_left,
+                                                                 hb, wb, (long long)n * h * w * 3, n_units);
     VL_LAUNCHED();
     return 0;
   }

@@ -282,6 +282,85 @@ __global__ void maxpool_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict_
   }
 }
 
+// Second generation of the pooling gradient (pool5, alexnet.py:211): a thread owns 8 channels of a 2 x 2 pixel block,
+// so the list of (window, window position) pairs is fixed (see pool_lrn_bwd_kernel4 in encoder_fused.cu) and the gather
+// runs on bf16 pairs: argmax byte b -> half-word b << 8, HSET2.EQ against the position code -> 1.0 / 0.0, HFMA2
+// accumulates dy; the ReLU mask of the producing layer is one HSET2 + LOP3 per pair.  32-bit index arithmetic.
+__device__ __forceinline__ uint32_t mp_heq2(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("set.eq.bf16x2.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+__device__ __forceinline__ uint32_t mp_hfma2(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t d;
+  asm("fma.rn.bf16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+__device__ __forceinline__ uint32_t mp_gt0_mask(uint32_t a) {
+  uint32_t d;
+  asm("set.gt.u32.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(0u));
+  return d;
+}
+__device__ __forceinline__ void mp_gather(const bf16* __restrict__ g, const uint8_t* __restrict__ a, uint32_t code2,
+                                          uint32_t (&acc)[4]) {
+  const uint4 gv = __ldg(reinterpret_cast<const uint4*>(g));
+  const uint2 av = __ldg(reinterpret_cast<const uint2*>(a));
+  const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w};
+  const uint32_t h[4] = {__byte_perm(av.x, 0u, 0x1404), __byte_perm(av.x, 0u, 0x3424), __byte_perm(av.y, 0u, 0x1404),
+                         __byte_perm(av.y, 0u, 0x3424)};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) acc[i] = mp_hfma2(mp_heq2(h[i], code2), gw[i], acc[i]);
+}
+
+__global__ void __launch_bounds__(256)
+    maxpool_bwd_kernel2(const bf16* __restrict__ dy, const uint8_t* __restrict__ arg, bf16* __restrict__ dx,
+                        const bf16* __restrict__ relu_of, int n, int h, int w, int c, int p, int q, int total) {
+  const int cpr = c >> 3;
+  const int jp = (h + 1) >> 1, cp = (w + 1) >> 1;
+  constexpr uint32_t DEAD = 0xFF00FF00u;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int ch = idx % cpr;
+    int t = idx / cpr;
+    const int b = t % cp;
+    t /= cp;
+    const int j = t % jp;
+    const int nn = t / jp;
+    const int c0 = ch * 8;
+    const bool pa_ok = j >= 1 && j - 1 < p, pb_ok = j < p, qa_ok = b >= 1 && b - 1 < q, qb_ok = b < q;
+    const int pa = min(max(j - 1, 0), p - 1), pb = min(j, p - 1), qa = min(max(b - 1, 0), q - 1), qb = min(b, q - 1);
+    const int pooled = nn * (p * q * c) + c0;  // < 2^31 elements for every tensor this kernel serves (host checks)
+    const int o_aa = pooled + (pa * q + qa) * c, o_ab = pooled + (pa * q + qb) * c;
+    const int o_ba = pooled + (pb * q + qa) * c, o_bb = pooled + (pb * q + qb) * c;
+#define MP_CODE(k) ((uint32_t)(k) * 0x01000100u)
+    const uint32_t c_aa = pa_ok && qa_ok ? MP_CODE(8) : DEAD;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+#pragma unroll
+      for (int s2 = 0; s2 < 2; ++s2) {
+        const int row = 2 * j + r, col = 2 * b + s2;
+        if (row >= h || col >= w) continue;
+        uint32_t acc[4] = {0u, 0u, 0u, 0u};
+        // windows of pixel (r, s2) of the block: rows (j-1: only r = 0, window row 2) and j (window row r);
+        // columns (b-1: only s2 = 0, window column 2) and b (window column s2)
+        if (r == 0 && s2 == 0) mp_gather(dy + o_aa, arg + o_aa, c_aa, acc);
+        if (r == 0) mp_gather(dy + o_ab, arg + o_ab, pa_ok && qb_ok ? MP_CODE(6 + s2) : DEAD, acc);
+        if (s2 == 0) mp_gather(dy + o_ba, arg + o_ba, pb_ok && qa_ok ? MP_CODE(3 * r + 2) : DEAD, acc);
+        mp_gather(dy + o_bb, arg + o_bb, pb_ok && qb_ok ? MP_CODE(3 * r + s2) : DEAD, acc);
+        const int pix = ((nn * h + row) * w + col) * c + c0;
+        if (relu_of != nullptr) {
+          const uint4 mv = __ldg(reinterpret_cast<const uint4*>(relu_of + pix));
+          acc[0] &= mp_gt0_mask(mv.x);
+          acc[1] &= mp_gt0_mask(mv.y);
+          acc[2] &= mp_gt0_mask(mv.z);
+          acc[3] &= mp_gt0_mask(mv.w);
+        }
+        *reinterpret_cast<uint4*>(dx + pix) = make_uint4(acc[0], acc[1], acc[2], acc[3]);
+      }
+    }
+#undef MP_CODE
+  }
+}
+
 __global__ void maxpool_bwd_kernel(const bf16* __restrict__ dy, const uint8_t* __restrict__ arg, bf16* __restrict__ dx,
                                    const bf16* __restrict__ relu_of, int n, int h, int w, int c, int p, int q,
                                    long long total_chunks) {
@@ -752,6 +831,16 @@ extern "C" int vl_maxpool_bwd(const void* dy, const void* argmax, void* dx, cons
   VL_REQUIRE(dy && argmax && dx && c % 8 == 0, "vl_maxpool_bwd: bad arguments");
   const int p = (h - 3) / 2 + 1, q = (w - 3) / 2 + 1;
   const long long total = (long long)n * h * w * (c / 8);
+  if ((long long)n * h * w * c < (1LL << 31) && !getenv("VL_MAXPOOL_BWD_V1")) {
+    // 2 x 2 pixel blocks, packed gather (the accumulation in bf16 is exact for one contribution and rounds once per
+    // further one, like the fused LRN / pool backward)
+    const long long blocks2 = (long long)n * ((h + 1) / 2) * ((w + 1) / 2) * (c / 8);
+    maxpool_bwd_kernel2<<<sweep_grid(blocks2, 256), 256, 0, stream>>>(
+        reinterpret_cast<const bf16*>(dy), reinterpret_cast<const uint8_t*>(argmax), reinterpret_cast<bf16*>(dx),
+        reinterpret_cast<const bf16*>(relu_of), n, h, w, c, p, q, (int)blocks2);
+    VL_LAUNCHED();
+    return 0;
+  }
   maxpool_bwd_kernel<<<sweep_grid(total, 256), 256, 0, stream>>>(
       reinterpret_cast<const bf16*>(dy), reinterpret_cast<const uint8_t*>(argmax), reinterpret_cast<bf16*>(dx),
       reinterpret_cast<const bf16*>(relu_of), n, h, w, c, p, q, total);
