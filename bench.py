@@ -319,6 +319,17 @@ def run_ours(args):
         cpu = {"value": cpu_value, "unit": "clips/s", "cores": cores, "kind": "port",
                "sample": "%d clips x %d frames train step of the same model (torch-CPU port of the reference's TF "
                          "graph, oracle/lrcn_torch.py), 1 warm-up + 2 timed steps" % (CPU_SAMPLE_CLIPS, FPC)}
+    # DRAM traffic of the contraction launches of one step, from the committed ncu capture (bytes per step: the roofline
+    # entry aggregates the launches of a step, and so does this number); null when the capture is absent
+    traffic, traffic_note = None, None
+    tpath = os.path.join(ROOT, "profiles", "contraction_dram_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            with open(tpath) as fh:
+                tj = json.load(fh)
+            traffic, traffic_note = tj.get("bytes_per_step"), tj.get("source")
+        except Exception:
+            traffic, traffic_note = None, None
     out = {
         "metric": "clips/sec (16x227x227) LRCN train step", "value": value, "unit": "clips/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
@@ -336,7 +347,8 @@ def run_ours(args):
                          "(double buffered) inside the timed region; Engine.prefetch + Engine.train_step"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                     "frac": achieved / peak_tf, "traffic": None, "peak_source": peak_src + " (sustained bf16)",
+                     "frac": achieved / peak_tf, "traffic": traffic, "traffic_note": traffic_note,
+                     "peak_source": peak_src + " (sustained bf16)",
                      "kernel": "tcgen05 contraction kernels (umma_gemm_kernel + conv_flat_kernel), all launches of a step",
                      "launches_per_step": n_gemm, "kernel_ms_per_step": gemm_ms,
                      "note": "kernel_ms = sum of the per-launch CUDA-event durations of one extra step run on a single "
