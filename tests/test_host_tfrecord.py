@@ -124,3 +124,33 @@ def test_crop_and_mirror_draws_follow_the_reference_rng_order(tmp_path):
                  epochs=1, save_freq_per_epoch=1)
     dc.next_batch()
     assert dc.last_crops.tolist() == [[2, 2, 0]] * 4  # floor((12-8)/2), floor((14-9)/2)
+
+
+def test_read_time_resize_modes_keep_frames_at_their_serialized_size(tmp_path):
+    """imgproc raw_resize / resize (dataset_.py:481-491): the host hands over the serialized frames untouched together
+    with the target of the device-side imresize; crops are drawn against raw_image_shape; resize loses against a crop
+    (`elif`), and a double resampling is refused."""
+    base, frames, _ = _write_dataset(tmp_path, [1, 2], 2, (6, 7, 3))
+    rr = Dataset(_opts(base, (8, 9, 3), [defs.imgproc.raw_resize, defs.imgproc.center_crop], raw=(12, 14, 3)),
+                 batch_size=2, num_classes=7, epochs=1, save_freq_per_epoch=1)
+    assert rr.resize_to == (12, 14)
+    f, onehot, cpv = rr.next_batch()
+    assert f.shape == (6, 6, 7, 3) and np.array_equal(f, frames) and rr.stored_shape == (6, 7, 3)
+    assert rr.last_crops.tolist() == [[2, 2, 0]] * 6  # centre crop of the 12 x 14 resampled frame to 8 x 9
+    rs = Dataset(_opts(base, (8, 9, 3), [defs.imgproc.resize]), batch_size=2, num_classes=7, epochs=1,
+                 save_freq_per_epoch=1)
+    assert rs.resize_to == (8, 9)
+    f2, _, _ = rs.next_batch()
+    assert f2.shape == (6, 6, 7, 3) and not rs.last_crops.any()
+    # crop wins over resize: frames must then already have raw_image_shape
+    rc = Dataset(_opts(base, (4, 5, 3), [defs.imgproc.resize, defs.imgproc.center_crop], raw=(6, 7, 3)), batch_size=2,
+                 num_classes=7, epochs=1, save_freq_per_epoch=1)
+    assert rc.resize_to is None
+    rc.next_batch()
+    assert rc.last_crops.tolist() == [[1, 1, 0]] * 6
+    with pytest.raises(Exception, match="twice"):
+        Dataset(_opts(base, (8, 9, 3), [defs.imgproc.raw_resize, defs.imgproc.resize], raw=(12, 14, 3)), batch_size=2,
+                num_classes=7, epochs=1, save_freq_per_epoch=1)
+    with pytest.raises(Exception, match="raw_image_shape"):
+        Dataset(_opts(base, (8, 9, 3), [defs.imgproc.raw_resize]), batch_size=2, num_classes=7, epochs=1,
+                save_freq_per_epoch=1)
