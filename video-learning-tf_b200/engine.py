@@ -739,7 +739,8 @@ class Engine(object):
         for ev in da2_ready:
             self._side.wait_event(ev)
         with torch.cuda.stream(self._side):
-            K.conv_wgrad(s2, A["p1"][:n], G["da2"][:n], self.var2d("dcnn/conv2W", self.grads))
+            # swapped operands (dy^T on M): 547 us against 570 us at 1024 frames (tests/bringup/wgrad_probe.py)
+            K.conv_wgrad_t(s2, A["p1"][:n], G["da2"][:n], self.var2d("dcnn/conv2W", self.grads))
         if len(halves) > 1:
             main.wait_stream(self._side2)
         nv.call("vl_s2d_unpack_grad", self.dws1, self.var("dcnn/conv1W", self.grads), s1.kh, s1.kw, 3, 96, s1.stride)
