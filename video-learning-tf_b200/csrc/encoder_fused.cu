@@ -1356,6 +1356,7 @@ extern "C" int vl_pool_lrn_bwd(const void* x, const void* dy, const void* argmax
   const long long blocks3 = (long long)n * h < (long long)vl::num_sms() * per_sm ? (long long)n * h : (long long)vl::num_sms() * per_sm;
   // fourth generation (2x2 pixel blocks, uniform control flow): the two AlexNet geometries, beta = 0.75
   const int v4 = getenv("VL_LRN_BWD_V4") ? atoi(getenv("VL_LRN_BWD_V4")) : 2;
+  const long long gmul = getenv("VL_LRN_BWD_GRID") ? atoi(getenv("VL_LRN_BWD_GRID")) : 4;  // CTAs per SM in the grid
   if (v4 && beta == 0.75f && c == 96 && h == 57 && w == 57) {
     const long long units = (long long)n * 29;
     if (v4 == 3) {  // 80 registers (a few spills), three CTAs per SM
@@ -1364,7 +1365,7 @@ extern "C" int vl_pool_lrn_bwd(const void* x, const void* dy, const void* argmax
           reinterpret_cast<const bf16*>(x), reinterpret_cast<const bf16*>(dy), reinterpret_cast<const uint8_t*>(argmax),
           reinterpret_cast<bf16*>(dx), dbias, n, alpha, bias);
     } else if (v4 == 2) {
-      const long long g = units < (long long)vl::num_sms() * 4 ? units : (long long)vl::num_sms() * 4;
+      const long long g = units < (long long)vl::num_sms() * gmul ? units : (long long)vl::num_sms() * gmul;
       pool_lrn_bwd_kernel4<12, 8, 96, 57, 57, 256, 2><<<(int)g, 256, 0, stream>>>(
           reinterpret_cast<const bf16*>(x), reinterpret_cast<const bf16*>(dy), reinterpret_cast<const uint8_t*>(argmax),
           reinterpret_cast<bf16*>(dx), dbias, n, alpha, bias);
@@ -1380,12 +1381,12 @@ extern "C" int vl_pool_lrn_bwd(const void* x, const void* dy, const void* argmax
   if (v4 && beta == 0.75f && c == 256 && h == 28 && w == 28) {
     const long long units = (long long)n * 14;
     if (v4 >= 2) {  // 72 registers: two CTAs of 448 threads per SM (243 us against 293 us with one CTA, 128 registers)
-      const long long g = units < (long long)vl::num_sms() * 4 ? units : (long long)vl::num_sms() * 4;
+      const long long g = units < (long long)vl::num_sms() * gmul ? units : (long long)vl::num_sms() * gmul;
       pool_lrn_bwd_kernel4<8, 32, 256, 28, 28, 448, 2><<<(int)g, 448, 0, stream>>>(
           reinterpret_cast<const bf16*>(x), reinterpret_cast<const bf16*>(dy), reinterpret_cast<const uint8_t*>(argmax),
           reinterpret_cast<bf16*>(dx), dbias, n, alpha, bias);
     } else if (v4 == 4) {
-      const long long g = units < (long long)vl::num_sms() * 4 ? units : (long long)vl::num_sms() * 4;
+      const long long g = units < (long long)vl::num_sms() * gmul ? units : (long long)vl::num_sms() * gmul;
       pool_lrn_bwd_kernel4<8, 32, 256, 28, 28, 448, 1><<<(int)g, 448, 0, stream>>>(
           reinterpret_cast<const bf16*>(x), reinterpret_cast<const bf16*>(dy), reinterpret_cast<const uint8_t*>(argmax),
           reinterpret_cast<bf16*>(dx), dbias, n, alpha, bias);
