@@ -1,17 +1,21 @@
-// Second-generation HBM-bound kernels of the AlexNet encoder (sm_100a).
+// HBM-bound kernels of the AlexNet encoder (sm_100a).
 //
-//   vl_frames_s2d          frames (uint8 / fp32) -> mean-subtracted bf16 space-to-depth tensor: the 11x11 stride-4
+//   vl_frames_s2d(_crop)   frames (uint8 / fp32) -> mean-subtracted bf16 space-to-depth tensor: the 11x11 stride-4
 //                          SAME conv1 (alexnet.py:60-77) becomes a 3x3 stride-1 VALID convolution over 48 channels
-//                          that the im2col-TMA contraction kernel consumes directly (no 2.5 GB patch matrix).
+//                          (frames_s2d_direct_kernel: register-only fast path for plain uint8 frames;
+//                          frames_s2d_kernel: crop / mirror / fp32 feed)
 //   vl_s2d_pack_filter     conv1 HWIO fp32 filter -> bf16 [9 taps x 64, cout] operand of that convolution
 //   vl_s2d_unpack_grad     filter gradient of the 3x3x48 convolution -> HWIO gradient of the 11x11x3 filter
-//   vl_lrn_pool_fwd        LRN + 3x3/2 max-pool (alexnet.py:80-98,121-139): LRN evaluated once per input pixel into
-//                          shared memory (bf16, as the unfused path stores it), pooled from shared memory
-//   vl_pool_lrn_bwd        MaxPoolGrad -> LRNGrad -> ReluGrad (+ bias gradient), one 16-byte chunk per thread, channel
-//                          halos exchanged with warp shuffles (every expensive term is evaluated exactly once)
+//   vl_lrn_pool_fwd        LRN + 3x3/2 max-pool (alexnet.py:80-98,121-139): lrn_pool_fwd_kernel3 streams the rows of
+//                          the two AlexNet geometries through a five-row ring in shared memory; lrn_pool_fwd_kernel2
+//                          (strip per CTA, run-time extents) serves every other shape
+//   vl_pool_lrn_bwd        MaxPoolGrad -> LRNGrad -> ReluGrad (+ bias gradient): pool_lrn_bwd_kernel4 (2 x 2 pixel
+//                          blocks, packed gather) for the two AlexNet geometries, pool_lrn_bwd_kernel2 (per pixel,
+//                          run-time extents) otherwise
 //
-// All global accesses are 16-byte vectors over the channel axis of NHWC tensors; these kernels are judged on
-// achieved HBM GB/s (DESIGN.md lists the algorithmic bytes of each).
+// All global accesses are 16-byte vectors over the channel axis of NHWC tensors (spelled through uint4: a copy of a
+// struct of four bf16x2 compiles to four 32-bit accesses); these kernels are judged on achieved HBM GB/s (DESIGN.md
+// lists the algorithmic bytes and the instruction budget of each).
 #include "common.cuh"
 #include "../../include/vlb200.h"
 
@@ -649,135 +653,6 @@ __global__ void __launch_bounds__(256, 3)
   }
 }
 
-// Instantiated-geometry version: C_ = LPP * 8 * CPL channels, every lane live, CPL independent 16-byte loads per
-// lane in flight.  Same arithmetic as pool_lrn_bwd_kernel2.
-template <int LPP, int CPL, int C_, int H_, int W_>
-__global__ void __launch_bounds__(128, 4)
-    pool_lrn_bwd_kernel3(const bf16* __restrict__ x, const bf16* __restrict__ dy, const uint8_t* __restrict__ arg,
-                         bf16* __restrict__ dx, float* __restrict__ dbias, int n, float alpha, float beta, float bias) {
-  constexpr int NE = 8 * CPL;
-  constexpr int c = C_, h = H_, w = W_;
-  constexpr int p = (h - 3) / 2 + 1, q = (w - 3) / 2 + 1;
-  static_assert(LPP * NE == C_, "lanes x channels per lane must cover the channel axis exactly");
-  __shared__ float bsum[C_];
-  const int l = threadIdx.x % LPP;
-  const int grp = threadIdx.x / LPP;
-  constexpr int ngrp = 128 / LPP;
-  const int c0 = l * NE;
-  if (dbias != nullptr) {
-    for (int i = threadIdx.x; i < c; i += blockDim.x) bsum[i] = 0.f;
-    __syncthreads();
-  }
-  float bacc[NE];
-#pragma unroll
-  for (int j = 0; j < NE; ++j) bacc[j] = 0.f;
-  const float k2ab = 2.0f * alpha * beta;
-  const int rows_total = n * h;
-  for (int row = blockIdx.x; row < rows_total; row += gridDim.x) {
-    const int nn = row / h;
-    const int hh = row - nn * h;
-    const int p_lo = max(0, (hh - 1) >> 1), p_hi = min(p - 1, hh >> 1);
-    const bf16* xrow = x + (long long)row * (w * c);
-    bf16* dxrow = dx + (long long)row * (w * c);
-    const bf16* dyimg = dy + (long long)nn * (p * q * c);
-    const uint8_t* argimg = arg + (long long)nn * (p * q * c);
-    for (int ww0 = 0; ww0 < w; ww0 += ngrp) {
-      const int ww = ww0 + grp;
-      const bool live = ww < w;
-      float xv[NE], gv[NE];
-#pragma unroll
-      for (int j = 0; j < NE; ++j) xv[j] = gv[j] = 0.f;
-      if (live) {
-        Bf16x8 xin[CPL];
-#pragma unroll
-        for (int k = 0; k < CPL; ++k) xin[k] = ld8(xrow + ww * c + c0 + 8 * k);
-        __nv_bfloat162 g2[4 * CPL];
-#pragma unroll
-        for (int i = 0; i < 4 * CPL; ++i) g2[i] = __floats2bfloat162_rn(0.f, 0.f);
-        const int q_lo = max(0, (ww - 1) >> 1), q_hi = min(q - 1, ww >> 1);
-        for (int pp = p_lo; pp <= p_hi; ++pp) {
-          const int r3 = (hh - 2 * pp) * 3;
-          for (int qq = q_lo; qq <= q_hi; ++qq) {
-            const int o = (pp * q + qq) * c + c0;
-            const uint32_t code4 = (uint32_t)(r3 + ww - 2 * qq) * 0x01010101u;
-#pragma unroll
-            for (int k = 0; k < CPL; ++k) {
-              const uint4 g = *reinterpret_cast<const uint4*>(dyimg + o + 8 * k);
-              const uint2 a = *reinterpret_cast<const uint2*>(argimg + o + 8 * k);
-              const uint32_t mlo = __vcmpeq4(a.x, code4), mhi = __vcmpeq4(a.y, code4);
-              const uint32_t gw[4] = {g.x & __byte_perm(mlo, 0, 0x1100), g.y & __byte_perm(mlo, 0, 0x3322),
-                                      g.z & __byte_perm(mhi, 0, 0x1100), g.w & __byte_perm(mhi, 0, 0x3322)};
-#pragma unroll
-              for (int i = 0; i < 4; ++i)
-                g2[4 * k + i] = __hadd2(g2[4 * k + i], *reinterpret_cast<const __nv_bfloat162*>(&gw[i]));
-            }
-          }
-        }
-#pragma unroll
-        for (int k = 0; k < CPL; ++k) {
-          float t8[8];
-          unpack8(xin[k], t8);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) xv[8 * k + j] = t8[j];
-        }
-#pragma unroll
-        for (int i = 0; i < 4 * CPL; ++i) {
-          const float2 t = __bfloat1622float2(g2[i]);
-          gv[2 * i] = t.x;
-          gv[2 * i + 1] = t.y;
-        }
-      }
-      float sq[NE], ssum[NE];
-#pragma unroll
-      for (int j = 0; j < NE; ++j) sq[j] = xv[j] * xv[j];
-      window5n<LPP, NE>(sq, l, ssum);
-      float pw[NE], tt[NE], tsum[NE];
-#pragma unroll
-      for (int j = 0; j < NE; ++j) {
-        const float sc = fmaf(alpha, ssum[j], bias);
-        float inv;
-        if (beta == 0.75f) {
-          const float rs = rsqrt_approx(sc);
-          pw[j] = rs * sqrt_approx(rs);
-          inv = rs * rs;
-        } else {
-          pw[j] = __powf(sc, -beta);
-          inv = __fdividef(1.0f, sc);
-        }
-        tt[j] = (gv[j] * xv[j]) * (pw[j] * inv);
-      }
-      window5n<LPP, NE>(tt, l, tsum);
-      if (live) {
-#pragma unroll
-        for (int k = 0; k < CPL; ++k) {
-          float out[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int e = 8 * k + j;
-            const float g = fmaf(gv[e], pw[e], -(k2ab * xv[e]) * tsum[e]);
-            out[j] = xv[e] > 0.f ? g : 0.f;  // ReLU gradient of the producing conv
-          }
-          const Bf16x8 packed = pack8(out);
-          st8(dxrow + ww * c + c0 + 8 * k, packed);
-          if (dbias != nullptr) {
-            float rb[8];
-            unpack8(packed, rb);  // the bias gradient sums the bf16 values that are stored (as vl_colsum would)
-#pragma unroll
-            for (int j = 0; j < 8; ++j) bacc[8 * k + j] += rb[j];
-          }
-        }
-      }
-    }
-  }
-  if (dbias != nullptr) {
-#pragma unroll
-    for (int j = 0; j < NE; ++j) atomicAdd(&bsum[c0 + j], bacc[j]);
-    __syncthreads();
-    for (int i = threadIdx.x; i < c; i += blockDim.x) atomicAdd(dbias + i, bsum[i]);
-  }
-}
-
-
 // ------------------------------------------------------------------------------------------------
 // Fourth generation of the fused backward: uniform control flow and a packed pooled-gradient gather.
 //
@@ -1350,10 +1225,6 @@ extern "C" int vl_pool_lrn_bwd(const void* x, const void* dy, const void* argmax
       reinterpret_cast<bf16*>(dx), dbias, n, h, w, c, alpha, beta, bias
   (void)p;
   (void)q;
-  // CTAs per SM of the instantiated kernels: 12 queued (3 resident) by default; VL_LRN_BWD_CTAS=2 leaves registers
-  // for a co-resident contraction CTA of another stream
-  const int per_sm = getenv("VL_LRN_BWD_CTAS") ? atoi(getenv("VL_LRN_BWD_CTAS")) : 4;
-  const long long blocks3 = (long long)n * h < (long long)vl::num_sms() * per_sm ? (long long)n * h : (long long)vl::num_sms() * per_sm;
   // fourth generation (2x2 pixel blocks, uniform control flow): the two AlexNet geometries, beta = 0.75
   const int v4 = getenv("VL_LRN_BWD_V4") ? atoi(getenv("VL_LRN_BWD_V4")) : 2;
   const long long gmul = getenv("VL_LRN_BWD_GRID") ? atoi(getenv("VL_LRN_BWD_GRID")) : 4;  // CTAs per SM in the grid
@@ -1399,19 +1270,8 @@ extern "C" int vl_pool_lrn_bwd(const void* x, const void* dy, const void* argmax
     VL_LAUNCHED();
     return 0;
   }
-  if (c == 96 && h == 57 && w == 57 && !getenv("VL_LRN_BWD_V2"))  // conv1 block of the 227x227 AlexNet
-    pool_lrn_bwd_kernel3<4, 3, 96, 57, 57><<<(int)blocks3, 128, 0, stream>>>(
-        reinterpret_cast<const bf16*>(x), reinterpret_cast<const bf16*>(dy), reinterpret_cast<const uint8_t*>(argmax),
-        reinterpret_cast<bf16*>(dx), dbias, n, alpha, beta, bias);
-  else if (c == 256 && h == 28 && w == 28 && getenv("VL_LRN_BWD_V3"))  // conv2 block (slower than kernel2: 612 vs 555 us)
-    pool_lrn_bwd_kernel3<16, 2, 256, 28, 28><<<(int)blocks3, 128, 0, stream>>>(
-        reinterpret_cast<const bf16*>(x), reinterpret_cast<const bf16*>(dy), reinterpret_cast<const uint8_t*>(argmax),
-        reinterpret_cast<bf16*>(dx), dbias, n, alpha, beta, bias);
-  else if (c == 96 && h == 57 && w == 57)
-    pool_lrn_bwd_kernel2<16, 96, 57, 57><<<(int)blocks, 256, 0, stream>>>(VL_BWD_ARGS);
-  else if (c == 256 && h == 28 && w == 28)
-    pool_lrn_bwd_kernel2<32, 256, 28, 28><<<(int)blocks, 256, 0, stream>>>(VL_BWD_ARGS);
-  else if (lpp == 16)
+  // every other geometry (c <= 256, c % 8 == 0): the per-pixel kernel with run-time extents
+  if (lpp == 16)
     pool_lrn_bwd_kernel2<16, 0, 0, 0><<<(int)blocks, 256, 0, stream>>>(VL_BWD_ARGS);
   else
     pool_lrn_bwd_kernel2<32, 0, 0, 0><<<(int)blocks, 256, 0, stream>>>(VL_BWD_ARGS);
