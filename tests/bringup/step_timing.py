@@ -46,6 +46,8 @@ print("train step: %.3f ms  %.1f clips/s  (%.1f%% of sustained tensor peak), lau
 print("loss etc:", eng.train_step(frames, labels, 1e-3))
 print("max mem GB", torch.cuda.max_memory_allocated() / 1e9)
 
+if "--serial" in sys.argv:
+    eng.set_serial(True)  # every kernel on one stream: durations are those of the kernels alone
 if "--profile" in sys.argv:
     from torch.profiler import profile, ProfilerActivity
     import re
