@@ -25,3 +25,16 @@ for mode in (0, 1, 2, 3):
         err = (out - ref).abs().max().item() / ref.abs().max().item()
         line.append("%d:%s" % (off, "ok" if err < 1e-2 else "BAD(%.2f)" % err))
     print("mode %d (%s%s): %s" % (mode, "shift A" if mode & 2 else "shift B", ", base_offset" if mode & 1 else "", " ".join(line)), flush=True)
+
+# mode 4: N-major B with OVERLAPPING 64-wide atoms (leading byte offset = one pixel row): three taps of a filter row
+# through one descriptor.  D[m][(s, c)] = sum_{k<64} W[m][k] * X[off + k + s][c]
+line = []
+for off in (0, 1, 2, 3, 5, 8, 9, 59, 118, 200):
+    n = 192
+    out = torch.zeros(128, n, device="cuda")
+    nv.check(L.vl_debug_shift_mma(w.data_ptr(), x.data_ptr(), 512, off, n, 4, out.data_ptr(), st))
+    torch.cuda.synchronize()
+    ref = torch.cat([w.float() @ x[off + s:off + s + 64].float() for s in range(3)], dim=1)
+    err = (out - ref).abs().max().item() / ref.abs().max().item()
+    line.append("%d:%s" % (off, "ok" if err < 1e-2 else "BAD(%.2f)" % err))
+print("mode 4 (N-major B, overlapping atoms, LBO = 128 B): %s" % " ".join(line), flush=True)

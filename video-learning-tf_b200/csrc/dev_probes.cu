@@ -238,6 +238,20 @@ __global__ void __launch_bounds__(128, 1)
       return d;
     };
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+    if (mode & 4) {
+      // mode bit 2: N-major B whose 64-wide N atoms OVERLAP: atom s starts one pixel row (128 B) after atom s-1
+      // (leading byte offset 128 B instead of a separate 8 KB block per atom), i.e. the three taps of a filter row
+      // addressed through ONE descriptor over the same staged rows:  D[m][(s, c)] = sum_k W[m][k] * X[off + k + s][c],
+      // k < 64 pixel rows, n = 192.  K advances by 16 rows = 2048 B per UMMA.
+      const uint32_t idesc_mn = idesc | (1u << 16);
+      auto desc_mn = [&](uint32_t addr) {
+        return (static_cast<uint64_t>((1024u >> 4) | (1u << 14) | (2u << 29)) << 32) |
+               (static_cast<uint64_t>(128u >> 4) << 16) | ((addr >> 4) & 0x3FFFu);
+      };
+      const uint32_t xb = smem_u32(sX) + off * 128;
+      for (int k = 0; k < 4; ++k)
+        umma_bf16(tmem_base, desc(smem_u32(sW) + k * 32), desc_mn(xb + k * 2048), idesc_mn, (uint32_t)k);
+    } else
     // K-steps advance by 32 B inside the swizzle row; the base offset refers to the row phase of the start address
     for (int k = 0; k < 4; ++k) umma_bf16(tmem_base, desc(a_addr + k * 32), desc(b_addr + k * 32), idesc, (uint32_t)k);
     umma_commit(done);
