@@ -90,6 +90,10 @@ typedef struct vl_gemm_desc {
    * group g -> C[n][sh*Y+dy][sw*X+dx][g*c_goff + ch] of an NHWC tensor [n][d2s_h][d2s_w][c_ld]; rows / columns
    * beyond d2s_h / d2s_w are dropped.  d2s_c % 16 == 0. */
   int32_t d2s_sh, d2s_sw, d2s_c, d2s_h, d2s_w;
+  /* VL_A_TILED_MN x VL_B_IM2COL_MN (swapped filter gradient) only: 1 = one k-block per OUTPUT ROW (q <= 64), an n-block =
+   * the kw taps of one filter row, which contract against ONE tiled box of 64 + kw - 1 input pixels through an N-major
+   * descriptor whose atoms overlap by one pixel row (3x less operand traffic than one im2col box per tap). */
+  int32_t row_shift;
   vl_conv_geom conv;     /* used when a_mode is an im2col mode                                      */
 } vl_gemm_desc;
 

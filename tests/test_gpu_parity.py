@@ -209,6 +209,15 @@ def test_conv1_space_to_depth_path_vs_oracle(vl):
     dws2 = torch.zeros_like(dws)
     K.conv_wgrad_t(s1s, xs, dev(dy, torch.bfloat16), dws2)
     assert rel(dws2.cpu().numpy(), dws.cpu().numpy()) < 1e-3
+    # row-shift form: one k-block per output row, the three taps of a filter row contract against ONE staged input row
+    # through an N-major descriptor with overlapping atoms; split-K over rows (also an uneven split)
+    for split in (0, 5):
+        dws3 = torch.zeros_like(dws)
+        K.conv_wgrad_t(s1s, xs, dev(dy, torch.bfloat16), dws3, split_k=split, row_shift=True)
+        assert rel(dws3.cpu().numpy(), dws.cpu().numpy()) < 1e-3
+    dw3 = torch.empty(11, 11, 3, 96, device="cuda")
+    nv.call("vl_s2d_unpack_grad", dws3, dw3, 11, 11, 3, 96, 4)
+    assert rel(dw3.cpu().numpy(), dw_ref) < 1e-3
 
 
 def test_staging_with_crop_and_mirror_bit_exact(vl):

@@ -25,7 +25,7 @@ class GemmDesc(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in (
         "m", "n", "k", "groups", "a_mode", "b_mode", "a_ld", "b_ld", "a_goff", "b_goff", "c_goff",
         "b_tap_stride", "b_row_goff", "b_tap_inner", "c_ld", "c_dtype", "c_atomic", "relu", "split_k", "msub", "block_n",
-        "mask_ld", "d2s_sh", "d2s_sw", "d2s_c", "d2s_h", "d2s_w")] + [
+        "mask_ld", "d2s_sh", "d2s_sw", "d2s_c", "d2s_h", "d2s_w", "row_shift")] + [
         ("conv", ConvGeom)]
 
 

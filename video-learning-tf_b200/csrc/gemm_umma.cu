@@ -61,6 +61,8 @@ struct KParams {
   int P, Q, PQ, stride_h, stride_w, lower_h, lower_w, cin_g;
   FastDiv fd_nblk, fd_mblk, fd_groups, fd_cchunks, fd_kw, fd_PQ, fd_Q;
   int d2s_sh, d2s_sw, d2s_c, d2s_h, d2s_w;  // depth-to-space epilogue (d2s_c > 0), see vl_gemm_desc
+  int row_shift;  // transposed-im2col B through ONE tiled box per filter row (see vl_gemm_desc.row_shift)
+  FastDiv fd_P;
   FastDiv fd_d2s_c, fd_d2s_sw;
   void* C;
   int c_ld, c_dtype, c_atomic, relu;
@@ -77,6 +79,15 @@ struct KParams {
   int mn_step_rows, mn_step_rem;  // transposed im2col: 64 pixels = mn_step_rows image rows + mn_step_rem pixels
   int dbg;  // development probes (VL_GEMM_DBG): 1 = no MMA, 2 = no A loads, 4 = no B loads, 8 = no stores
 };
+
+__device__ __forceinline__ void tma_load_tiled_4d_u32(uint32_t dst, const CUtensorMap* m, uint32_t bar, int32_t c0,
+                                                      int32_t c1, int32_t c2, int32_t c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      :
+      : "r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
 
 struct TileCoord {
   int m_blk, n_blk, g, kb_begin, kb_end;
@@ -207,7 +218,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
         }
       }
       int b_valid = 0;  // transposed-im2col B: 64-column chunks (tap, channel chunk) of this n-block
-      if (BMODE == VL_B_IM2COL_MN) {
+      if (BMODE == VL_B_IM2COL_MN && p.row_shift) {
+        // one k-block = one OUTPUT ROW (q <= 64 pixels, zero padded to 64 by the out-of-bounds fill of the A box);
+        // the n-block is one filter row: its kw taps read the same staged input row shifted by 0..kw-1 pixels
+        fd_divmod(t.kb_begin, p.fd_P, pn, pp);
+        pq = 0;
+        b_valid = BN >> 6;
+      } else if (BMODE == VL_B_IM2COL_MN) {
         int rem;
         fd_divmod(t.kb_begin * BK, p.fd_PQ, pn, rem);
         fd_divmod(rem, p.fd_Q, pp, pq);
@@ -224,7 +241,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
         }
       }
       const uint32_t a_bytes = !ld_a ? 0u : (AM == VL_A_IM2COL_MN ? 8192u * a_valid : a_tile_bytes);
-      const uint32_t b_bytes = !ld_b ? 0u : (BMODE == VL_B_IM2COL_MN ? 8192u * b_valid : (uint32_t)p.b_stage_bytes);
+      const uint32_t b_bytes = !ld_b ? 0u
+                               : (BMODE == VL_B_IM2COL_MN ? (p.row_shift ? (uint32_t)(64 + p.kw - 1) * 128u : 8192u * b_valid)
+                                                          : (uint32_t)p.b_stage_bytes);
       const uint32_t bytes = b_bytes + a_bytes;
       for (int kb = t.kb_begin; kb < t.kb_end; ++kb) {
         mbar_wait_u32(empty_u32 + stage * 8, phase ^ 1u);
@@ -239,6 +258,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 #pragma unroll
               for (int s = 0; s < MAX_MSUB; ++s)
                 if (s < msub) tma_load_2d_u32(sA + s * A_SUB_BYTES, &tmA, fb, a_c0 + kb * BK, m0 + s * BM);
+            } else if (AM == VL_A_TILED_MN && BMODE == VL_B_IM2COL_MN && p.row_shift) {
+              // dy^T of output row (pn, pp): 4-D box (64 channels, 64 pixels, 1 row); pixels >= q are zero filled
+#pragma unroll
+              for (int j = 0; j < 2 * MAX_MSUB; ++j)
+                if (j < 2 * msub) tma_load_tiled_4d_u32(sA + j * 8192, &tmA, fb, a_c0 + m0 + j * 64, 0, pp, pn);
             } else if (AM == VL_A_TILED_MN) {
 #pragma unroll
               for (int j = 0; j < 2 * MAX_MSUB; ++j)
@@ -263,6 +287,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
             if (BMODE == VL_B_TILED_K) {
               const int tapb = p.flip ? (taps - 1 - tap) : tap;
               tma_load_2d_u32(sB, &tmB, fb, b_c0 + tap * p.b_tap_inner + cc * BK, b_r0 + tapb * p.b_tap_stride);
+            } else if (BMODE == VL_B_IM2COL_MN && p.row_shift) {
+              // input row (pp * stride + lower_h + filter row) of image pn, 64 + kw - 1 pixels from lower_w: ONE tiled box
+              tma_load_tiled_4d_u32(sB, &tmB, fb, b_c0, p.lower_w, pp * p.stride_h + p.lower_h + t.n_blk, pn);
             } else if (BMODE == VL_B_IM2COL_MN) {  // this k-block's 64 pixels start at (pn, pp, pq)
               const int bx = pq * p.stride_w + p.lower_w, by = pp * p.stride_h + p.lower_h;
 #pragma unroll
@@ -277,7 +304,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
         }
         __syncwarp();
         // ---- advance the contraction walk ----
-        if (AM == VL_A_IM2COL_MN || BMODE == VL_B_IM2COL_MN) {
+        if (BMODE == VL_B_IM2COL_MN && p.row_shift) {
+          if (++pp == p.P) {
+            pp = 0;
+            ++pn;
+          }
+        } else if (AM == VL_A_IM2COL_MN || BMODE == VL_B_IM2COL_MN) {
           pq += mn_step_rem;  // advance 64 pixels = mn_step_rows rows + mn_step_rem pixels
           pp += mn_step_rows;
           if (pq >= p.Q) {
@@ -647,6 +679,22 @@ int make_im2col_map(CUtensorMap* m, const void* base, const vl_conv_geom& g, int
   return 0;
 }
 
+// NHWC bf16 tensor seen as (C, W, H, N) with channel pitch `c_pitch`: tiled boxes of 64 channels x `box_w` pixels of
+// one image row, 128B swizzle; channels >= c_valid and pixels outside [0, w) are zero filled.
+int make_row_map(CUtensorMap* m, const void* base, long long c_valid, long long c_pitch, int w, int h, int n, int box_w) {
+  VL_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (c_pitch * 2) % 16 == 0, "row TMA map: 16B alignment");
+  VL_REQUIRE(box_w >= 1 && box_w <= 256, "row TMA map: box of %d pixels", box_w);
+  cuuint64_t dims[4] = {(cuuint64_t)c_valid, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+  cuuint64_t strides[3] = {(cuuint64_t)c_pitch * 2, (cuuint64_t)c_pitch * w * 2, (cuuint64_t)c_pitch * w * h * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)box_w, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = g_encode_tiled(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  VL_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (row map) failed (%d)", (int)r);
+  return 0;
+}
+
 int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 FastDiv make_fastdiv(int d) {
@@ -742,6 +790,14 @@ extern "C" int vl_gemm(const vl_gemm_desc* d, const void* a, const void* b, void
     VL_REQUIRE(d->k == cg.n * cg.p * cg.q, "vl_gemm: k (%d) must equal n*p*q for transposed im2col B", d->k);
     VL_REQUIRE(d->n == p.taps * p.cchunks * 64, "vl_gemm: n must be taps * ceil(cin_g/64) * 64 for transposed im2col B");
     VL_REQUIRE(d->c_dtype == VL_DT_F32 && BN <= 64 * 2 * MAX_MSUB, "vl_gemm: transposed im2col B: fp32 output, block_n <= 256");
+    if (d->row_shift) {
+      // one k-block per output row; an n-block = the kw taps of one filter row over ONE staged input row
+      VL_REQUIRE(cg.q <= 64 && cg.cin_g <= 64 && cg.stride_w == 1 && BN == cg.kw * 64 && d->groups == 1,
+                 "vl_gemm: row_shift needs q <= 64, cin_g <= 64, stride_w 1, block_n == kw*64, one group (q=%d cin_g=%d "
+                 "block_n=%d)", cg.q, cg.cin_g, BN);
+      p.row_shift = 1;
+      p.kb_total = cg.n * cg.p;
+    }
   }
   // two 128-row sub-tiles per CTA tile when the accumulators fit (2 * BN <= 256 TMEM columns per stage) and there
   // are enough rows to keep every SM busy with the halved tile count
@@ -793,6 +849,7 @@ extern "C" int vl_gemm(const vl_gemm_desc* d, const void* a, const void* b, void
   p.fd_kw = make_fastdiv(p.kw);
   p.fd_PQ = make_fastdiv(p.PQ);
   p.fd_Q = make_fastdiv(p.Q);
+  p.fd_P = make_fastdiv(p.P);
   p.d2s_c = d->d2s_c;
   if (p.d2s_c > 0) {
     VL_REQUIRE(d->a_mode == VL_A_IM2COL_K && d->b_mode == VL_B_TILED_K && !d->c_atomic && bias == nullptr &&
@@ -828,6 +885,7 @@ extern "C" int vl_gemm(const vl_gemm_desc* d, const void* a, const void* b, void
 
   // ---- smem pipeline ----
   p.b_stage_bytes = BN * 128;
+  if (p.row_shift) p.b_stage_bytes = (64 + cg.kw - 1) * 128;  // one staged input row serves the kw taps: smaller stages, deeper ring
   p.stage_bytes = p.msub * A_SUB_BYTES + ((p.b_stage_bytes + 1023) / 1024) * 1024;
   int stages = (SMEM_LIMIT - 1024 - BAR_REGION) / p.stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
@@ -845,6 +903,9 @@ extern "C" int vl_gemm(const vl_gemm_desc* d, const void* a, const void* b, void
   p.b_desc_hi = hi;
   p.a_lbo_enc = a_mn ? (8192u >> 4) : 1u;
   p.b_lbo_enc = b_mn ? (8192u >> 4) : 1u;
+  // row_shift: the N atoms of a filter row OVERLAP, atom s starts one pixel row (128 B) after atom s-1
+  // (verified on hardware: profiles/r01_shift_mma_v2.txt, mode 4)
+  if (p.row_shift) p.b_lbo_enc = 128u >> 4;
   p.a_kstep_enc = a_mn ? (2048u >> 4) : (32u >> 4);
   p.b_kstep_enc = b_mn ? (2048u >> 4) : (32u >> 4);
 
@@ -853,6 +914,8 @@ extern "C" int vl_gemm(const vl_gemm_desc* d, const void* a, const void* b, void
   if (d->a_mode == VL_A_TILED_K) {
     long long inner = (long long)d->a_goff * (d->groups - 1) + d->k;
     if (make_tiled_map(&tmA, a, inner, d->m, d->a_ld, 64, BM) != 0) return -1;
+  } else if (d->a_mode == VL_A_TILED_MN && p.row_shift) {
+    if (make_row_map(&tmA, a, d->m, d->a_ld, cg.q, cg.p, cg.n, 64) != 0) return -1;
   } else if (d->a_mode == VL_A_TILED_MN) {
     long long inner = (long long)d->a_goff * (d->groups - 1) + d->m;
     if (make_tiled_map(&tmA, a, inner, d->k, d->a_ld, 64, 64) != 0) return -1;
@@ -872,6 +935,8 @@ extern "C" int vl_gemm(const vl_gemm_desc* d, const void* a, const void* b, void
       outer = (long long)d->b_row_goff * (d->groups - 1) + d->n;
     }
     if (make_tiled_map(&tmB, b, inner, outer, d->b_ld, 64, BN) != 0) return -1;
+  } else if (b_im2col && p.row_shift) {
+    if (make_row_map(&tmB, b, cg.c, cg.c, cg.w, cg.h, cg.n, 64 + cg.kw - 1) != 0) return -1;
   } else if (b_im2col) {
     if (make_im2col_map(&tmB, b, cg, 64, cg.c) != 0) return -1;
   } else {

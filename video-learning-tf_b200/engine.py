@@ -735,7 +735,10 @@ class Engine(object):
                 nv.call("vl_pool_lrn_bwd", A["a1"][lo:hi], G["dp1"][lo:hi], A["arg1"][lo:hi], G["da1"][lo:hi],
                         self.var("dcnn/conv1b", self.grads), m, s1.p, s1.q, 96, LRN["radius"], LRN["alpha"],
                         LRN["beta"], LRN["bias"])
-                K.conv_wgrad_t(s1s, A["x_s2d"][lo:hi], G["da1"][lo:hi], self.dws1)  # split-K atomics: halves add up
+                # row-shift form when an output row fits one k-block (q <= 64): the taps of a filter row share one
+                # staged input row (kernels.conv_wgrad_t); split-K atomics: halves add up
+                K.conv_wgrad_t(s1s, A["x_s2d"][lo:hi], G["da1"][lo:hi], self.dws1,
+                               row_shift=(s1s.q <= 64 and s1s.cin_g <= 64 and os.environ.get("VL_WGRAD_ROW", "1") != "0"))
         for ev in da2_ready:
             self._side.wait_event(ev)
         with torch.cuda.stream(self._side):

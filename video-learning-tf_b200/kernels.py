@@ -280,7 +280,7 @@ def conv_wgrad(spec, x, dy, dw, split_k=0, block_n=0, msub=0):
     return dw
 
 
-def conv_wgrad_t(spec, x, dy, dw, split_k=0, block_n=0, a_ld=0):
+def conv_wgrad_t(spec, x, dy, dw, split_k=0, block_n=0, a_ld=0, row_shift=False):
     """Same contract as conv_wgrad with the operands swapped: output channels (dy^T) on the M side, the (tap, channel
     chunk) axis of im2col(x)^T on the N side.  Every UMMA is 128 x block_n x 16 with block_n = 192 / 256 instead of
     a narrow cout-wide one, and the split-K red.adds of a warp coalesce."""
@@ -298,6 +298,10 @@ def conv_wgrad_t(spec, x, dy, dw, split_k=0, block_n=0, a_ld=0):
     d.block_n = block_n or (192 if chunks % 3 == 0 else 256)
     d.msub = 1
     d.conv = spec.geom(n)
+    if row_shift:  # one k-block per output row, the taps of a filter row over one staged input row (conv1)
+        assert spec.q <= 64 and spec.cin_g <= 64 and spec.stride == 1 and spec.groups == 1
+        d.row_shift = 1
+        d.block_n = spec.kw * 64
     assert dw.dtype == F32
     nv.gemm(d, dy, x, dw)
     return dw
