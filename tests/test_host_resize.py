@@ -54,3 +54,20 @@ def test_product_coefficient_tables_equal_the_oracle():
 def test_golden_records_its_pillow_version():
     g = np.load(GOLD)
     assert str(g["pillow_version"]).count(".") >= 1
+
+
+def test_oracle_resize_against_live_pil_on_random_extents():
+    """Where Pillow is importable (it is in the build container), the restatement is also checked against PIL directly on
+    random extents, including 1-pixel axes, strong down-scaling and up-scaling."""
+    Image = pytest.importorskip("PIL.Image")
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.integers(1, 40), st.integers(1, 40), st.integers(1, 40), st.integers(1, 40), st.integers(0, 2 ** 31 - 1))
+    def check(h, w, oh, ow, seed):
+        a = np.random.default_rng(seed).integers(0, 256, (h, w, 3), dtype=np.uint8)
+        ref = np.asarray(Image.fromarray(a).resize((ow, oh), resample=Image.BILINEAR))
+        got = R.imresize_bilinear(a, oh, ow)
+        assert np.array_equal(got, ref), (h, w, oh, ow)
+
+    check()
