@@ -131,3 +131,44 @@ def test_adam_matches_torch_formula():
         v = 0.999 * v + 0.001 * g.astype(np.float64) ** 2
         ref -= 0.01 * np.sqrt(1 - 0.999 ** t) / (1 - 0.9 ** t) * m / (np.sqrt(v) + 1e-8)
     assert np.allclose(p["w"], ref, atol=1e-5)
+
+
+@pytest.mark.parametrize("h,w,k,sh,sw,groups", [(6, 7, 5, 2, 2, 2), (5, 5, 3, 2, 1, 1), (4, 6, 3, 1, 2, 1)])
+def test_depth_to_space_formulation_of_the_data_gradient(h, w, k, sh, sw, groups):
+    """The algebra behind `vl_pack_dgrad_d2s` / `kernels.conv_dgrad_d2s` (include/vlb200.h): the data gradient of a
+    stride-1 SAME convolution equals a stride-(sh, sw) correlation over dy with a (k+sh-1) x (k+sw-1) filter that holds,
+    for every sub-position (dy, dx) of an output block, the rotated filter shifted by (dy, dx) - also where h % sh != 0."""
+    rng = np.random.default_rng(7)
+    cin_g, cout_g = 4, 3
+    cin, cout = cin_g * groups, cout_g * groups
+    x = rng.standard_normal((2, h, w, cin)).astype(np.float32)
+    wt = rng.standard_normal((k, k, cin_g, cout)).astype(np.float32)
+    dy = rng.standard_normal((2, h, w, cout)).astype(np.float32)
+    dx_ref, _, _ = O.conv2d_same_backward(x, wt, dy, 1, groups)
+    pad = (k - 1) // 2            # SAME, stride 1, odd k: pad_top = pad_left = (k-1)/2
+    pt = k - 1 - pad              # top / left padding of the walk over dy
+    kh2, kw2 = k + sh - 1, k + sw - 1
+    py, qx = -(-h // sh), -(-w // sw)
+    dyp = np.zeros((2, h + 2 * kh2, w + 2 * kw2, cout), np.float32)   # generous zero border
+    dyp[:, kh2:kh2 + h, kw2:kw2 + w] = dy
+    got = np.zeros_like(dx_ref)
+    for g in range(groups):
+        wp = np.zeros((kh2, kw2, cout_g, sh, sw, cin_g), np.float32)  # [ty][tx][k][(dy, dx, c)]
+        for dyy in range(sh):
+            for dxx in range(sw):
+                for ty in range(kh2):
+                    for tx in range(kw2):
+                        r, q = k - 1 + dyy - ty, k - 1 + dxx - tx
+                        if 0 <= r < k and 0 <= q < k:
+                            wp[ty, tx, :, dyy, dxx, :] = wt[r, q, :, g * cout_g:(g + 1) * cout_g].T
+        for Y in range(py):
+            for X in range(qx):
+                y0, x0 = kh2 + sh * Y - pt, kw2 + sw * X - pt
+                patch = dyp[:, y0:y0 + kh2, x0:x0 + kw2, g * cout_g:(g + 1) * cout_g]  # [n][ty][tx][k]
+                blk = np.einsum("nabk,abkyxc->nyxc", patch, wp)
+                for dyy in range(sh):
+                    for dxx in range(sw):
+                        yy, xx = sh * Y + dyy, sw * X + dxx
+                        if yy < h and xx < w:
+                            got[:, yy, xx, g * cin_g:(g + 1) * cin_g] = blk[:, dyy, dxx]
+    assert np.abs(got - dx_ref).max() < 1e-4 * max(1.0, np.abs(dx_ref).max())
