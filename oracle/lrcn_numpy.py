@@ -218,7 +218,10 @@ def maxpool_3x3s2_backward(x_shape, arg, dy):
 
 
 def sigmoid(x):
-    return (1.0 / (1.0 + np.exp(-x))).astype(F32)
+    # overflow-free form (the benchmark's input range saturates the gates: |x| reaches 1e3 and beyond)
+    x = np.asarray(x, dtype=F32)
+    e = np.exp(-np.abs(x))
+    return np.where(x >= 0, 1.0 / (1.0 + e), e / (1.0 + e)).astype(F32)
 
 
 def lstm_forward(x, kernels, biases, forget_bias=1.0, q=None):

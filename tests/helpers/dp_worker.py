@@ -13,8 +13,16 @@ import vlb200  # noqa: E402,F401
 from vlb200 import engine as E  # noqa: E402
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
-torch.cuda.set_device(local)
-dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+if torch.cuda.device_count() >= world:
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+else:
+    # a box with fewer GPUs than ranks (the driver's 1-GPU box): both ranks share cuda:0 and exchange through gloo
+    # (NCCL refuses two ranks on one device); the engine's data-parallel logic is the same, only the transport differs
+    local = 0
+    torch.cuda.set_device(0)
+    dist.init_process_group("gloo")
+print("dp_worker rank %d/%d on cuda:%d, backend %s" % (rank, world, local, dist.get_backend()))
 fpc, clips_per_rank, classes = 2, 2, 101
 cfg = E.EngineConfig(workflow="lrcn", fusion="avg", fpc=fpc, num_classes=classes, lstm_hidden=256, clip_norm=10,
                      dropout_keep_prob=0.0, optimizer="sgd")
@@ -50,8 +58,9 @@ dist.broadcast(flag, 0)
 # both ranks must hold identical parameters after the step
 digest = torch.tensor([float(sum(np.float64(v).sum() for k, v in sd.items() if k != "global_step"))], device="cuda:%d" % local,
                       dtype=torch.float64)
-other = [torch.zeros_like(digest) for _ in range(world)]
-dist.all_gather(other, digest)
-same = all(abs(o.item() - other[0].item()) == 0.0 for o in other)
+# (all_reduce only: gloo moves CUDA tensors for broadcast / all_reduce, not for all_gather)
+both = torch.cat([digest, -digest])
+dist.all_reduce(both, op=dist.ReduceOp.MAX)
+same = (both[0].item() == -both[1].item())
 dist.destroy_process_group()
 sys.exit(0 if (flag.item() == 1 and same) else 1)

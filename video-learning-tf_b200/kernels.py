@@ -80,8 +80,9 @@ def _ld(t):
 # ----------------------------------------------------------------------------------------------------
 # dense layers: tf.nn.relu_layer / tf.nn.xw_plus_b (alexnet.py:228,248,275; tf_util.py:56; lstm.py:141 x-part)
 # ----------------------------------------------------------------------------------------------------
-def linear_fwd(x, w, bias, out, relu=False, n=None, block_n=0):
-    """out[M,N] = act(x[M,K] @ w[K,N] + bias).  x, w bf16 (w in TF [in,out] layout, row pitch % 8 == 0)."""
+def linear_fwd(x, w, bias, out, relu=False, n=None, block_n=0, msub=0):
+    """out[M,N] = act(x[M,K] @ w[K,N] + bias).  x, w bf16 (w in TF [in,out] layout, row pitch % 8 == 0).
+    block_n / msub = 0: the library's tile choice."""
     m, k = x.shape
     n = out.shape[1] if n is None else n
     d = nv.GemmDesc()
@@ -93,6 +94,7 @@ def linear_fwd(x, w, bias, out, relu=False, n=None, block_n=0):
     d.relu = 1 if relu else 0
     d.split_k = 1
     d.block_n = block_n
+    d.msub = msub
     nv.gemm(d, x, w, out, bias)
     return out
 
