@@ -155,7 +155,8 @@ int vl_frames_s2d(const void* frames, int32_t is_u8, const float* mean3, void* o
                   int32_t s, int32_t pad_top, int32_t pad_left, int32_t hb, int32_t wb, vl_stream_t stream);
 /* Same staging with the reference's read-time preprocessing fused in (dataset_.py:444-461 crop_image, :498-500
  * rand_mirror, :521-530 sub_mean): frames are stored as [n][hr][wr][3]; crops = DEVICE int32 [n][3] = (y0, x0, mirror)
- * selects the h x w window at (y0, x0) of frame i, read right-to-left when mirror != 0.  crops may be NULL when
+ * selects the h x w window at (y0, x0) of frame i, read right-to-left when mirror != 0 (y0 / x0 are clamped into
+ * [0, hr - h] / [0, wr - w] by the kernel: it never reads outside the frame buffer).  crops may be NULL when
  * hr == h and wr == w. */
 int vl_frames_s2d_crop(const void* frames, int32_t is_u8, const float* mean3, void* out, int32_t n, int32_t hr,
                        int32_t wr, const int32_t* crops, int32_t h, int32_t w, int32_t s, int32_t pad_top,
@@ -223,6 +224,12 @@ int vl_pack_bf16(const float* src, int32_t rows, int32_t cols, void* dst, int32_
 int vl_pack_bf16_t(const float* src, int32_t rows, int32_t cols, void* dst, int32_t dst_ld, int32_t src_grp,
                    int32_t dst_grp, vl_stream_t stream);
 int vl_cast_f32_to_bf16(const float* src, void* dst, int64_t n, vl_stream_t stream);
+/* dst[i] = bf16(src[table[i]]), 0 where table[i] < 0; n % 8 == 0, table / dst 16-byte aligned.  Refreshes every
+ * permuted / zero-padded bf16 operand copy of the convolution filters (the layouts of vl_s2d_pack_filter,
+ * vl_pack_bf16_t, vl_pack_dgrad_d2s, vl_pack_bf16, vl_cast_f32_to_bf16) in ONE launch from a precomputed index table;
+ * replaces the per-variable tf.assign traffic behind opt.apply_gradients (train.py:217). */
+int vl_gather_bf16(const float* src, const int32_t* table, void* dst, int64_t n, vl_stream_t stream);
+
 /* dst[cols][rows] = src[rows][cols]^T (fp32): recurrent weights for the BPTT kernel. */
 int vl_transpose_f32(const float* src, float* dst, int32_t rows, int32_t cols, vl_stream_t stream);
 
@@ -271,8 +278,9 @@ int vl_mul(const float* a, const float* b, float* y, void* y_bf16, int64_t n, vl
 
 /* mean(softmax_cross_entropy_with_logits) (train.py:121-123) + accuracy (train.py:145-147) + d(loss)/d(logits).
  * logits[rows][c] fp32, labels[rows][c] int32 one/multi-hot; row_loss is a scratch/result buffer of 2*rows floats
- * (per-row loss, then per-row correct flag); out_scalars[0] = mean loss over `rows`, [1] = #correct;
- * dlogits = (softmax * sum(labels) - labels) * grad_scale  (grad_scale = 1/global_rows). */
+ * (per-row loss, then per-row correct flag); out_scalars[0] = grad_scale * sum of the row losses, [1] = #correct;
+ * dlogits = (softmax * sum(labels) - labels) * grad_scale.  grad_scale = 1 / (rows of the GLOBAL batch): on one
+ * rank out_scalars[0] is the mean loss, over data-parallel ranks the SUM of out_scalars[0] is. */
 int vl_softmax_ce(const float* logits, const int32_t* labels, int32_t rows, int32_t c, float grad_scale,
                   float* row_loss, float* out_scalars, float* dlogits, void* dlogits_bf16, int32_t dl_ld,
                   vl_stream_t stream);

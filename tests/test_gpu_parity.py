@@ -500,6 +500,44 @@ def test_dropout_mask_statistics(vl):
     assert torch.equal(mask, mask2)  # counter based: reproducible
 
 
+@pytest.mark.parametrize("workflow", ["lrcn", "singleframe"])
+def test_shadow_gather_equals_the_pack_kernels(vl, workflow):
+    """Engine.refresh_shadows refreshes every permuted / padded bf16 operand copy with ONE vl_gather_bf16 launch over a
+    precomputed index table (shadow_table.py); each copy must be bit-identical to the stand-alone packing kernel whose
+    layout it restates (include/vlb200.h)."""
+    E, nv, K = vl["E"], vl["nv"], vl["K"]
+    cfg = E.EngineConfig(workflow=workflow, fusion="avg", fpc=2, num_classes=101, lstm_hidden=256)
+    eng = E.Engine(cfg, max_clips=1, params=E.init_variables(cfg, seed=17))
+    sp, sh = eng.sp, eng.sh
+    s1, s1s = sp["conv1"], sp["conv1_s2d"]
+    ref = torch.empty_like(sh["conv1_fwd"])
+    nv.call("vl_s2d_pack_filter", eng.var("dcnn/conv1W"), ref, s1.kh, s1.kw, 3, 96, s1.stride, s1s.cchunks * 64, 1)
+    assert torch.equal(ref, sh["conv1_fwd"])
+    for name in ("conv2", "conv3", "conv4", "conv5"):
+        s = sp[name]
+        w = eng.var2d("dcnn/%sW" % name)
+        ref = torch.empty_like(sh[name])
+        nv.call("vl_cast_f32_to_bf16", w, ref, w.numel())
+        assert torch.equal(ref, sh[name]), name
+        ref = torch.empty_like(sh[name + "_fwd"])
+        nv.call("vl_pack_bf16_t", w, s.taps * s.cin_g, s.cout, ref, s.k_packed, s.cin_g, s.cchunks * 64)
+        assert torch.equal(ref, sh[name + "_fwd"]), name
+    s2 = sp["conv2"]
+    ref = torch.empty_like(sh["conv2_d2s"])
+    nv.call("vl_pack_dgrad_d2s", eng.var("dcnn/conv2W"), ref, s2.kh, s2.kw, s2.cin_g, s2.cout_g, s2.groups, 2, 2)
+    assert torch.equal(ref, sh["conv2_d2s"])
+    for key, wname in (("fc8", "dcnn/fc8W"), ("output_fc", "output_fc_w")):
+        if key in sh:
+            w = eng.var(wname)
+            ref = torch.empty_like(sh[key])
+            nv.call("vl_pack_bf16", w, w.shape[0], w.shape[1], ref, w.shape[0], eng.c_pad, w.shape[0], w.shape[0])
+            assert torch.equal(ref, sh[key]), key
+    assert ("fc8" in sh) == (workflow == "singleframe") and ("output_fc" in sh) == (workflow == "lrcn")
+    # same-layout copies
+    for key, wname in (("fc6", "dcnn/fc6W"), ("fc7", "dcnn/fc7W")):
+        assert torch.equal(eng.var(wname).to(torch.bfloat16), sh[key]), key
+
+
 # ----------------------------------------------------------------------------------------------------------
 # whole path
 # ----------------------------------------------------------------------------------------------------------

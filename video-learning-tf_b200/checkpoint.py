@@ -19,28 +19,53 @@ def checkpoint_folder(run_folder):
     return os.path.join(run_folder, "checkpoints")
 
 
+OPTIMIZER_SUFFIXES = ("/Adam", "/Adam_1")
+OPTIMIZER_SCALARS = ("beta1_power", "beta2_power")
+
+
+def _is_optimizer_key(key):
+    return key in OPTIMIZER_SCALARS or key.endswith(OPTIMIZER_SUFFIXES)
+
+
+def _write_atomic(path, writer, mode="wb"):
+    """Write through a temporary file in the same folder and os.replace it: a crash never leaves a partial file
+    under the final name."""
+    tmp = path + ".tmp%d" % os.getpid()
+    with open(tmp, mode) as f:
+        writer(f)
+        f.flush()
+        os.fsync(f.fileno())
+    os.replace(tmp, path)
+
+
 def save(engine, run_folder, progress_str, batch_index, epoch_index, max_to_keep=None):
+    """Variables + optimiser slots (tf.train.Saver saves all global variables: feeder.py:263-288) + the `.snap`
+    progress pickle.  Order: weights, snap, and only then the `checkpoint` index, each through an atomic rename, so
+    `resume_file: latest` never points at a partial checkpoint."""
     folder = checkpoint_folder(run_folder)
     os.makedirs(folder, exist_ok=True)
     gs = engine.global_step
     prefix = os.path.join(folder, "%s_%s.graph-%d" % (time.strftime("%d%m%y_%H%M%S"), progress_str, gs))
-    sd = engine.state_dict()
-    np.savez(prefix + ".npz", **{k.replace("/", "|"): v for k, v in sd.items()})
-    with open(prefix + ".snap", "wb") as f:
-        pickle.dump([batch_index, epoch_index, gs], f)
-    with open(os.path.join(folder, "checkpoint"), "a") as f:
-        f.write(os.path.basename(prefix) + "\n")
-    info("Saved checkpoint %s" % prefix)
-    if max_to_keep:
-        with open(os.path.join(folder, "checkpoint")) as f:
+    sd = dict(engine.state_dict())
+    sd.update(engine.optimizer_state_dict())
+    _write_atomic(prefix + ".npz", lambda f: np.savez(f, **{k.replace("/", "|"): v for k, v in sd.items()}))
+    _write_atomic(prefix + ".snap", lambda f: pickle.dump([batch_index, epoch_index, gs], f))
+    index = os.path.join(folder, "checkpoint")
+    names = []
+    if os.path.exists(index):
+        with open(index) as f:
             names = [l.strip() for l in f if l.strip()]
-        for old in names[:-max_to_keep]:
-            for ext in (".npz", ".snap"):
-                p = os.path.join(folder, old + ext)
-                if os.path.exists(p):
-                    os.remove(p)
-        with open(os.path.join(folder, "checkpoint"), "w") as f:
-            f.write("\n".join(names[-max_to_keep:]) + "\n")
+    names.append(os.path.basename(prefix))
+    stale = names[:-max_to_keep] if max_to_keep else []
+    if max_to_keep:
+        names = names[-max_to_keep:]
+    _write_atomic(index, lambda f: f.write("\n".join(names) + "\n"), mode="w")
+    for old in stale:  # only after the index stopped naming them
+        for ext in (".npz", ".snap"):
+            p = os.path.join(folder, old + ext)
+            if os.path.exists(p):
+                os.remove(p)
+    info("Saved checkpoint %s" % prefix)
     return prefix
 
 
@@ -72,6 +97,7 @@ def restore(engine, prefix, ignorable=("global_step",), is_validation=False):
     blob = np.load(prefix + ".npz")
     sd = {k.replace("|", "/"): blob[k] for k in blob.files}
     want = {name for name, _ in engine.var_shapes}
+    opt_sd = {k: sd.pop(k) for k in list(sd) if _is_optimizer_key(k)}  # optimiser slots: outside the name diff
     have = set(sd) - {"global_step"}
     missing, extra = want - have, have - want
     if missing:
@@ -81,6 +107,10 @@ def restore(engine, prefix, ignorable=("global_step",), is_validation=False):
     if is_validation:
         sd.pop("global_step", None)  # ignorable in validation (feeder.py:226-227)
     engine.load_state_dict(sd)
+    if not is_validation:  # ignorable in validation, like global_step
+        n_slots = engine.load_optimizer_state_dict(opt_sd)
+        if engine.cfg.optimizer == "adam" and n_slots == 0:
+            warning("Checkpoint %s holds no Adam slots: the moments restart from zero" % prefix)
     snap = [0, 0, int(sd.get("global_step", 0))]
     if os.path.exists(prefix + ".snap"):
         with open(prefix + ".snap", "rb") as f:

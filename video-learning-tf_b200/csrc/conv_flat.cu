@@ -32,7 +32,7 @@ namespace {
 using namespace vl::ptx;
 typedef __nv_bfloat16 bf16;
 
-constexpr int EPI_GROUPS = 2;                           // epilogue groups of four warps (one per TMEM lane quadrant)
+constexpr int EPI_GROUPS = 4;                           // epilogue groups of four warps (one per TMEM lane quadrant); p.epi_groups of them work
 constexpr int NUM_THREADS = 64 + EPI_GROUPS * 128;      // warp0 TMA, warp1 MMA (+TMEM alloc), then the epilogue warps
 constexpr int TMEM_COLS = 512;    // 2 accumulator stages x 256 fp32 columns
 constexpr int ACC_STRIDE_COLS = 256;
@@ -69,6 +69,9 @@ struct FParams {
   const float* bias;
   uint32_t idesc;
   int dbg;
+  int x_loads, x_load_rows;            // the input tile arrives as x_loads TMA boxes of x_load_rows rows each
+  int epi_groups;                      // epilogue groups that drain the accumulator (<= EPI_GROUPS)
+  int stage_bufs;                      // transposition buffers per group: 2 (double buffered) or 1 (shared memory is tight)
   int tma_store;                       // 1: the epilogue leaves through TMA tensor stores (tmY)
   int direct;                          // 1: the epilogue stores 2-byte elements straight from registers (default)
 };
@@ -137,7 +140,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], 4 * EPI_GROUPS);
+      mbar_init(&tmem_empty[s], 4 * p.epi_groups);
     }
     fence_barrier_init();
   }
@@ -182,8 +185,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
         if (elect_one()) {
           mbar_expect_tx_u32(xf_u32 + xs * 8, (p.dbg & 2) ? 0u : (uint32_t)p.x_box_bytes);
           if (!(p.dbg & 2))
-            tma_load_4d_u32(x_u32 + xs * p.x_stage_bytes, &tmX, xf_u32 + xs * 8, t.g * p.a_goff + cc * 64, -p.pad_left,
-                            row0, t.img);
+            for (int j = 0; j < p.x_loads; ++j)
+              tma_load_4d_u32(x_u32 + xs * p.x_stage_bytes + j * p.x_load_rows * p.Wp * 128, &tmX, xf_u32 + xs * 8,
+                              t.g * p.a_goff + cc * 64, -p.pad_left, row0 + j * p.x_load_rows, t.img);
         }
         __syncwarp();
         if (++xs == x_stages) {
@@ -266,10 +270,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
                 }
                 accumulate = 1;
                 a_lo += (uint32_t)(p.w_tap_bytes >> 4);
-                b_lo += 8;
-                if (++ts == kw) {
-                  ts = 0;
-                  b_lo += row_skip;
+                if (!(p.dbg & 128)) {  // probe bit 128: every tap reads the un-shifted (atom-aligned) tile
+                  b_lo += 8;
+                  if (++ts == kw) {
+                    ts = 0;
+                    b_lo += row_skip;
+                  }
                 }
               }
             }
@@ -291,19 +297,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
       if (elect_one()) umma_commit_u32(smem_u32(&tmem_full[acc]));
       __syncwarp();
     }
-  } else {
+  } else if (((warp - 2) >> 2) < p.epi_groups) {
     // ===================== epilogue: D^T[channel lane][flat position] -> NHWC =====================
     // Each thread owns one output channel (TMEM lane).  16 positions at a time are transposed through a small
     // double-buffered shared-memory stage ([position][channel] bf16) so that global stores are 16-byte vectors over
     // the channel axis (one contiguous 2*mc-byte run per position) instead of 2-byte scatters.
-    // EPI_GROUPS x 4 epilogue warps: warp % 4 selects the TMEM lane quadrant, (warp - 2) / 4 the group; group g
-    // drains the 16-position chunks g, g + EPI_GROUPS, ... (a single warp sustains only ~650 cycles per chunk).
+    // epi_groups x 4 epilogue warps: warp % 4 selects the TMEM lane quadrant, (warp - 2) / 4 the group; group g
+    // drains the 16-position chunks g, g + epi_groups, ... (a single warp sustains only ~650 cycles per chunk, so a
+    // short-K tile - conv1: 27 UMMAs = 3.2 k cycles for 15 chunks - needs four groups to stay under its main loop).
     const int quad = warp & 3;
     const int grp = (warp - 2) >> 2;
     const int etid = (threadIdx.x - 64) & 127;  // 0..127 inside the group
     const int m_local = quad * 32 + lane;
     bf16* out = reinterpret_cast<bf16*>(p.C);
-    bf16* stage = reinterpret_cast<bf16*>(w_tiles + p.w_region) + grp * (2 * 16 * 128);  // [2][16][128] per group  // [2][16][128]
+    const int ngrp = p.epi_groups;
+    const int bufs = p.stage_bufs;
+    bf16* stage = reinterpret_cast<bf16*>(w_tiles + p.w_region) + grp * (bufs * 16 * 128);  // [bufs][16][128] per group
     int local = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
       const FTile t = decode(p, tile);
@@ -357,14 +366,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
               }
             }
           }
-          col_c += 16 * EPI_GROUPS;
+          col_c += 16 * ngrp;
           while (col_c >= p.Wp) {
             col_c -= p.Wp;
             ++row_c;
           }
           return;
         }
-        bf16* sb = stage + buf * (16 * 128);
+        bf16* sb = stage + (bufs == 2 ? buf : 0) * (16 * 128);
         if (m_ok) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
@@ -388,7 +397,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
               tma_store_4d(&tmY, src, cch, col_c - p.Wp, orow0 + row_c + 1, t.img);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
-          col_c += 16 * EPI_GROUPS;
+          col_c += 16 * ngrp;
           while (col_c >= p.Wp) {
             col_c -= p.Wp;
             ++row_c;
@@ -412,7 +421,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
             }
           }
         }
-        col_c += 16 * EPI_GROUPS;  // the other groups handle the chunks in between
+        if (bufs == 1) asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory");  // single stage: reads done before the next chunk's writes
+        col_c += 16 * ngrp;  // the other groups handle the chunks in between
         while (col_c >= p.Wp) {
           col_c -= p.Wp;
           ++row_c;
@@ -421,7 +431,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
       uint32_t va[16], vb[16];
       const int first = grp * 16;
       if (first < p.npos && !(p.dbg & 64)) tmem_ld_x16(taddr + first, va);
-      constexpr int STEP = 16 * EPI_GROUPS;
+      const int STEP = 16 * ngrp;
       for (int c0 = first; c0 < p.npos && !(p.dbg & 64); c0 += 2 * STEP) {
         tmem_ld_wait();
         const bool has_b = c0 + STEP < p.npos;
@@ -576,6 +586,11 @@ extern "C" int vl_conv_flat(const vl_conv_flat_desc* d, const void* x, const voi
   p.x_box_bytes = box_rows * p.Wp * 128;
   p.x_stage_bytes = ((p.x_box_bytes + 1023) / 1024) * 1024;
   p.x_stages = MAX_X_STAGES;
+  // several smaller boxes per tile keep more requests of the TMA unit in flight (VL_FLAT_XSPLIT = boxes per tile)
+  p.x_loads = 1;
+  if (getenv("VL_FLAT_XSPLIT")) p.x_loads = atoi(getenv("VL_FLAT_XSPLIT"));
+  if (p.x_loads < 1 || box_rows % p.x_loads != 0) p.x_loads = 1;
+  p.x_load_rows = box_rows / p.x_loads;
   // Epilogue modes.  Default: 16 positions x 128 channels are transposed through a shared-memory stage and leave
   // through ONE TMA tensor store per chunk when the padded row width is a multiple of 16 (conv2: chunks never straddle
   // rows; a store with a negative start column faults), else through per-thread 16-byte stores.  Measured at 1024
@@ -586,18 +601,31 @@ extern "C" int vl_conv_flat(const vl_conv_flat_desc* d, const void* x, const voi
   // anything else.
   const char* epi_env = getenv("VL_FLAT_EPI");
   p.direct = (epi_env && !strcmp(epi_env, "direct")) ? 1 : 0;
-  const int STAGE_BYTES = p.direct ? 0 : EPI_GROUPS * 2 * 16 * 128 * 2;  // transposition stages (per group, double buffered)
-  const int w_avail = SMEM_LIMIT - 1024 - BAR_REGION - STAGE_BYTES - 1024 - p.x_stages * p.x_stage_bytes;
+  // epilogue groups: a short contraction (conv1: 27 UMMAs per 15-chunk tile) is bound by the accumulator drain, which
+  // scales with the number of groups; long contractions keep two groups and more shared memory for the filter ring
+  const int umma_per_tile = d->kh * d->kw * ((d->cin_g + 15) / 16);
+  p.epi_groups = umma_per_tile <= 48 ? 4 : 2;
+  if (getenv("VL_FLAT_GROUPS")) p.epi_groups = atoi(getenv("VL_FLAT_GROUPS"));
+  if (p.epi_groups < 1) p.epi_groups = 1;
+  if (p.epi_groups > EPI_GROUPS) p.epi_groups = EPI_GROUPS;
+  p.stage_bufs = 2;
+  int STAGE_BYTES = p.direct ? 0 : p.epi_groups * p.stage_bufs * 16 * 128 * 2;  // transposition stages per group
+  int w_avail = SMEM_LIMIT - 1024 - BAR_REGION - STAGE_BYTES - 1024 - p.x_stages * p.x_stage_bytes;
   // filter box: only the rows that exist (8-row swizzle atoms); the UMMA reads 128 rows, the surplus lanes are
   // never stored
   int w_box_rows = d->w_rows < 128 ? ((d->w_rows + 7) / 8) * 8 : 128;
   if (p.m_blks > 1 || p.groups > 1) w_box_rows = 128;
   p.w_tap_bytes = w_box_rows * 128;
   // resident filter when it fits (conv1: 9 taps x 96 rows = 108 KB) and is the same for every tile
-  p.resident = (p.m_blks == 1 && p.groups == 1 && p.taps * p.cchunks * p.w_tap_bytes + (128 - w_box_rows) * 128 <= w_avail &&
-                !getenv("VL_FLAT_NO_RESIDENT"))
-                   ? 1
-                   : 0;
+  const int resident_bytes = p.taps * p.cchunks * p.w_tap_bytes + (128 - w_box_rows) * 128;
+  if (!p.direct && p.m_blks == 1 && p.groups == 1 && resident_bytes > w_avail &&
+      resident_bytes <= w_avail + STAGE_BYTES / 2) {
+    // the resident filter fits only next to single-buffered transposition stages (conv1 with four groups)
+    p.stage_bufs = 1;
+    STAGE_BYTES /= 2;
+    w_avail += STAGE_BYTES;
+  }
+  p.resident = (p.m_blks == 1 && p.groups == 1 && resident_bytes <= w_avail && !getenv("VL_FLAT_NO_RESIDENT")) ? 1 : 0;
   // taps per weight stage: a whole filter row if two such stages fit (one mbarrier hand-shake costs ~350 cycles, a
   // 128 x 240 x 16 UMMA 120), else as many taps as still allow double buffering
   p.tpg = d->kw;
@@ -625,6 +653,7 @@ extern "C" int vl_conv_flat(const vl_conv_flat_desc* d, const void* x, const voi
                         ((reinterpret_cast<uintptr_t>(out) & 15) == 0) && !p.direct && !(epi_env && !strcmp(epi_env, "stage"))
                     ? 1
                     : 0;
+  if (p.stage_bufs == 1) p.tma_store = 0;  // the TMA-store form relies on the double buffer
   {
     cuuint64_t dims[4] = {(cuuint64_t)d->c_ld, (cuuint64_t)p.Wo, (cuuint64_t)p.Ho, (cuuint64_t)d->n};
     cuuint64_t strides[3] = {(cuuint64_t)d->c_ld * 2, (cuuint64_t)d->c_ld * p.Wo * 2,
@@ -642,7 +671,7 @@ extern "C" int vl_conv_flat(const vl_conv_flat_desc* d, const void* x, const voi
   {
     cuuint64_t dims[4] = {(cuuint64_t)d->c, (cuuint64_t)d->w, (cuuint64_t)d->h, (cuuint64_t)d->n};
     cuuint64_t strides[3] = {(cuuint64_t)d->c * 2, (cuuint64_t)d->c * d->w * 2, (cuuint64_t)d->c * d->w * d->h * 2};
-    cuuint32_t box[4] = {64, (cuuint32_t)p.Wp, (cuuint32_t)box_rows, 1};
+    cuuint32_t box[4] = {64, (cuuint32_t)p.Wp, (cuuint32_t)p.x_load_rows, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = g_encode(&tmX, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

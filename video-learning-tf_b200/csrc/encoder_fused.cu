@@ -166,9 +166,11 @@ __global__ void __launch_bounds__(256)
   // crop window of this frame inside the stored (hr x wr) frame and horizontal mirror (dataset_.py:444-461,498-500)
   int y0 = 0, x0 = 0, mirror = 0;
   if (crops != nullptr) {
-    y0 = crops[nn * 3];
-    x0 = crops[nn * 3 + 1];
-    mirror = crops[nn * 3 + 2];
+    // clamped into the stored frame: offsets that arrive as device tensors cannot be validated on the host without a
+    // synchronisation, and an out-of-range window must never read outside the frame buffer
+    y0 = max(0, min(crops[nn * 3], hr - h));
+    x0 = max(0, min(crops[nn * 3 + 1], wr - w));
+    mirror = crops[nn * 3 + 2] != 0;
   }
   // one thread per image pixel x: its 3 channels of the S image rows go to block bx = (x+pad_left)/S, slot dx
   for (int x = threadIdx.x; x < w; x += blockDim.x) {

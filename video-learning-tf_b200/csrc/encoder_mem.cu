@@ -729,6 +729,26 @@ __global__ void cast_bf16_kernel(const float* __restrict__ src, bf16* __restrict
     for (long long i = n8 << 3; i < n; ++i) dst[i] = __float2bfloat16_rn(src[i]);
 }
 
+// dst[i] = bf16(src[table[i]]) (0 where table[i] < 0): every operand copy ("shadow") of the convolution filters is a
+// fixed permutation / zero padding of the fp32 master, so ONE launch over a precomputed index table refreshes all of
+// them after the optimiser step (Engine.refresh_shadows) instead of one pack kernel per layer and layout.
+// A thread produces 8 consecutive outputs: two 16-byte table loads, 8 gathers (the masters are L2 resident), one
+// 16-byte store.
+__global__ void __launch_bounds__(256)
+    gather_bf16_kernel(const float* __restrict__ src, const int32_t* __restrict__ table, bf16* __restrict__ dst,
+                       long long n8) {
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n8;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int4 t0 = __ldg(reinterpret_cast<const int4*>(table) + 2 * idx);
+    const int4 t1 = __ldg(reinterpret_cast<const int4*>(table) + 2 * idx + 1);
+    const int t[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = t[j] >= 0 ? __ldg(src + t[j]) : 0.f;
+    st8(reinterpret_cast<Bf16x8*>(dst) + idx, pack8(f));
+  }
+}
+
 // dst[c][r] = src[r][c]  (fp32, 32x32 smem tiles; used for the recurrent weights w_h -> w_h^T of the BPTT kernel)
 __global__ void transpose_f32_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols) {
   __shared__ float tile[32][33];
@@ -907,6 +927,16 @@ extern "C" int vl_cast_f32_to_bf16(const float* src, void* dst, int64_t n, vl_st
   VL_REQUIRE((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0,
              "vl_cast_f32_to_bf16: pointers must be 16B aligned");
   cast_bf16_kernel<<<sweep_grid((n + 7) / 8, 256), 256, 0, stream>>>(src, reinterpret_cast<bf16*>(dst), n);
+  VL_LAUNCHED();
+  return 0;
+}
+
+extern "C" int vl_gather_bf16(const float* src, const int32_t* table, void* dst, int64_t n, vl_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  VL_REQUIRE(src && table && dst && n > 0 && n % 8 == 0, "vl_gather_bf16: bad arguments (n must be a multiple of 8)");
+  VL_REQUIRE((reinterpret_cast<uintptr_t>(table) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0,
+             "vl_gather_bf16: table and dst must be 16-byte aligned");
+  gather_bf16_kernel<<<sweep_grid(n / 8, 256), 256, 0, stream>>>(src, table, reinterpret_cast<bf16*>(dst), n / 8);
   VL_LAUNCHED();
   return 0;
 }

@@ -176,15 +176,17 @@ __global__ void softmax_ce_kernel(const float* __restrict__ logits, const int32_
 }
 
 // deterministic in-order sums of the per-row results
+// out[0] = loss_scale * sum of the row losses: with loss_scale = 1 / (clips of the GLOBAL batch) the sum of out[0] over
+// the data-parallel ranks is the mean loss of the global batch (train.py:123), whatever the shard sizes are
 __global__ void ce_finalize_kernel(const float* __restrict__ row_loss, const float* __restrict__ row_correct, int rows,
-                                   float* __restrict__ out_scalars) {
+                                   float loss_scale, float* __restrict__ out_scalars) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     float l = 0.f, cor = 0.f;
     for (int r = 0; r < rows; ++r) {
       l += row_loss[r];
       cor += row_correct[r];
     }
-    out_scalars[0] = l / (float)rows;
+    out_scalars[0] = l * loss_scale;
     out_scalars[1] = cor;
   }
 }
@@ -258,7 +260,7 @@ extern "C" int vl_softmax_ce(const float* logits, const int32_t* labels, int32_t
                                                                row_loss + rows, dlogits,
                                                                reinterpret_cast<bf16*>(dlogits_bf16), dl_ld);
   VL_LAUNCHED();
-  ce_finalize_kernel<<<1, 32, 0, stream>>>(row_loss, row_loss + rows, rows, out_scalars);
+  ce_finalize_kernel<<<1, 32, 0, stream>>>(row_loss, row_loss + rows, rows, grad_scale, out_scalars);
   VL_LAUNCHED();
   return 0;
 }

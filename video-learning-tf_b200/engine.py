@@ -162,15 +162,26 @@ class Engine(object):
             offsets.append(off)
         self.arena_n = off
         self.params = torch.zeros(off, dtype=F32, device=self.dev)
-        # gradient arena + scratch for the filter gradient of the space-to-depth conv1 (zeroed together every step)
+        # [64-float header | gradient arena | scratch for the filter gradient of the space-to-depth conv1].  The header
+        # holds the step scalars ([0..2] clip scalars, [4] loss, [5] correct): [loss, correct] sit right in front of the
+        # convolution gradients, so the tail all-reduce of a data-parallel step is ONE collective over
+        # [header | conv1..conv5 gradients] instead of two
         s1s = self.sp["conv1_s2d"]
         self._dws_n = _align(s1s.taps * s1s.cin_g * s1s.cout)
-        self.grads_ext = torch.zeros(off + self._dws_n, dtype=F32, device=self.dev)
-        self.grads = self.grads_ext[:off]
-        self.dws1 = self.grads_ext[off:off + s1s.taps * s1s.cin_g * s1s.cout].view(s1s.taps * s1s.cin_g, s1s.cout)
+        self._hdr = 64
+        self.grads_ext = torch.zeros(self._hdr + off + self._dws_n, dtype=F32, device=self.dev)
+        self.grads = self.grads_ext[self._hdr:self._hdr + off]
+        self.dws1 = self.grads_ext[self._hdr + off:self._hdr + off + s1s.taps * s1s.cin_g * s1s.cout].view(
+            s1s.taps * s1s.cin_g, s1s.cout)
         self.seg_offsets = torch.tensor(offsets, dtype=torch.int64, device=self.dev)
+        # the variables from fc6W on (89 % of the arena) have their final gradients as soon as fc6's filter gradient is
+        # enqueued: their squared norms are taken on a side stream under the convolution backward
+        self._k_late = [n for n, _ in self.var_shapes].index("dcnn/fc6W")
+        off_late = offsets[self._k_late]
+        self._seg_early = torch.tensor(offsets[:self._k_late + 1], dtype=torch.int64, device=self.dev)
+        self._seg_late = torch.tensor([o - off_late for o in offsets[self._k_late:]], dtype=torch.int64, device=self.dev)
         self.sqnorms = torch.zeros(len(self.var_shapes), dtype=F32, device=self.dev)
-        self.scalars = torch.zeros(8, dtype=F32, device=self.dev)  # [0..2] clip scalars, [4] loss, [5] correct
+        self.scalars = self.grads_ext[:8]
         self.adam_m = self.adam_v = None
         if cfg.optimizer == "adam":
             self.adam_m = torch.zeros(off, dtype=F32, device=self.dev)
@@ -185,7 +196,9 @@ class Engine(object):
         self._rb_stream = torch.cuda.Stream(device=self.dev)
         self._scalars_host = torch.zeros(8, dtype=F32).pin_memory()
         self._scalars_ready = None
-        self._streams = (self._side, self._side2)
+        self._norm_stream = torch.cuda.Stream(device=self.dev)  # early gradient norms (+ the early all-reduce wait)
+        self._late_norms_ready = None
+        self._streams = (self._side, self._side2, self._norm_stream)
         self._alloc_shadows()
         self._alloc_activations()
         self.load_state_dict(params if params is not None else init_variables(cfg))
@@ -223,6 +236,38 @@ class Engine(object):
             self.global_step = int(sd["global_step"])
         self.refresh_shadows()
 
+    def optimizer_state_dict(self):
+        """Optimiser slots under the names tf.train.Saver gives them (the reference saves all global variables,
+        feeder.py:263-288): `<var>/Adam` (m), `<var>/Adam_1` (v), `beta1_power` / `beta2_power` (= beta^(t+1) after t
+        steps).  Empty for SGD."""
+        if self.cfg.optimizer != "adam":
+            return {}
+        out = {}
+        for name, _ in self.var_shapes:
+            out[name + "/Adam"] = self.var(name, self.adam_m).detach().cpu().numpy().copy()
+            out[name + "/Adam_1"] = self.var(name, self.adam_v).detach().cpu().numpy().copy()
+        out["beta1_power"] = np.float32(0.9 ** (self.adam_t + 1))
+        out["beta2_power"] = np.float32(0.999 ** (self.adam_t + 1))
+        return out
+
+    def load_optimizer_state_dict(self, sd):
+        """Inverse of optimizer_state_dict; slots that are absent keep their zero initialisation (a checkpoint written
+        by an SGD run, or by a version that did not save them)."""
+        if self.cfg.optimizer != "adam":
+            return 0
+        loaded = 0
+        for name, shape in self.var_shapes:
+            for suffix, arena in (("/Adam", self.adam_m), ("/Adam_1", self.adam_v)):
+                if name + suffix in sd:
+                    arr = np.asarray(sd[name + suffix], dtype=np.float32)
+                    if tuple(arr.shape) != tuple(shape):
+                        raise ValueError("optimizer slot %s: shape %s does not match %s" % (name + suffix, arr.shape, shape))
+                    self.var(name, arena).copy_(torch.from_numpy(arr))
+                    loaded += 1
+        if "beta1_power" in sd:
+            self.adam_t = max(0, int(round(math.log(float(sd["beta1_power"])) / math.log(0.9))) - 1)
+        return loaded
+
     def gradient_dict(self):
         return {name: self.var(name, self.grads).detach().cpu().numpy().copy() for name, _ in self.var_shapes}
 
@@ -230,31 +275,58 @@ class Engine(object):
     # bf16 operand copies of the weights
     # ------------------------------------------------------------------------------------------
     def _alloc_shadows(self):
+        """bf16 operand copies of the weights.  The permuted / padded copies of the convolution filters (and of the
+        narrow fc8 / output_fc matrices) live in ONE bf16 arena described by an index table (shadow_table.py): one
+        vl_gather_bf16 launch refreshes all of them.  The big same-layout copies (fc6, fc7, LSTM kernels) are separate
+        tensors written by the optimiser kernel itself (vl_sgd_update_shadow) or by vl_cast_f32_to_bf16."""
+        from . import shadow_table as ST
         cfg, sp, dev = self.cfg, self.sp, self.dev
-        sh = {}
-        s1s = sp["conv1_s2d"]
-        sh["conv1_fwd"] = torch.zeros(96, s1s.k_packed, dtype=BF16, device=dev)  # K-major
+        names = dict(self.var_shapes)
+        plan = []  # (key, shape, table of source indices relative to the master variable, master variable name)
+        s1, s1s = sp["conv1"], sp["conv1_s2d"]
+        plan.append(("conv1_fwd", (96, s1s.k_packed),
+                     ST.s2d_filter_kmajor(s1.kh, s1.kw, 3, 96, s1.stride, s1s.cchunks * 64), "dcnn/conv1W"))
         for name in ("conv2", "conv3", "conv4", "conv5"):
-            s = sp[name]
-            sh[name] = torch.zeros(s.taps * s.cin_g, s.cout, dtype=BF16, device=dev)  # HWIO as 2D (data gradient)
-            sh[name + "_fwd"] = torch.zeros(s.cout, s.k_packed, dtype=BF16, device=dev)  # K-major, taps padded to 64
+            sc = sp[name]
+            rows = sc.taps * sc.cin_g
+            plan.append((name, (rows, sc.cout), ST.identity(rows * sc.cout), "dcnn/%sW" % name))  # HWIO as 2D (dgrad)
+            plan.append((name + "_fwd", (sc.cout, sc.k_packed),
+                         ST.kmajor_padded(sc.taps, sc.cin_g, sc.cout, sc.cchunks * 64), "dcnn/%sW" % name))
         # conv2's data gradient runs as a stride-2 forward convolution over dy with a depth-to-space epilogue
         # (kernels.conv_dgrad_d2s): N = 2*2*48 = 192 columns per UMMA instead of 48
-        sh["conv2_d2s"] = torch.zeros(*K.d2s_filter_shape(sp["conv2"], 2, 2), dtype=BF16, device=dev)
+        s2 = sp["conv2"]
+        plan.append(("conv2_d2s", K.d2s_filter_shape(s2, 2, 2),
+                     ST.dgrad_d2s(s2.kh, s2.kw, s2.cin_g, s2.cout_g, s2.groups, 2, 2), "dcnn/conv2W"))
+        if "dcnn/fc8W" in names:
+            plan.append(("fc8", (4096, self.c_pad), ST.col_padded(4096, cfg.num_classes, self.c_pad), "dcnn/fc8W"))
+        for fc_name in ("output_fc", "fc_convert"):
+            if fc_name + "_w" in names:
+                rows = names[fc_name + "_w"][0]
+                plan.append((fc_name, (rows, self.c_pad), ST.col_padded(rows, cfg.num_classes, self.c_pad),
+                             fc_name + "_w"))
+        total = 0
+        offs = []
+        for key, shape, table, master in plan:
+            assert table.size == int(np.prod(shape)), key
+            offs.append(total)
+            total += _align(table.size)
+        table_all = np.full(total, -1, dtype=np.int32)
+        for (key, shape, table, master), o in zip(plan, offs):
+            table_all[o:o + table.size] = np.where(table >= 0, table + self.var_off[master], -1)
+        self._shadow_table = torch.from_numpy(table_all).to(dev)
+        self._shadow_arena = torch.zeros(total, dtype=BF16, device=dev)
+        sh = {}
+        for (key, shape, table, master), o in zip(plan, offs):
+            sh[key] = self._shadow_arena[o:o + table.size].view(*shape)
         sh["fc6"] = torch.zeros(sp["flat"], 4096, dtype=BF16, device=dev)
-        names = dict(self.var_shapes)
         if "dcnn/fc7W" in names:
             sh["fc7"] = torch.zeros(4096, 4096, dtype=BF16, device=dev)
-        if "dcnn/fc8W" in names:
-            sh["fc8"] = torch.zeros(4096, self.c_pad, dtype=BF16, device=dev)
         if cfg.workflow == "lrcn":
             for layer in range(cfg.lstm_layers):
                 kn = "rnn/multi_rnn_cell/cell_%d/basic_lstm_cell/kernel" % layer
                 rows, cols = names[kn]
                 sh["lstm%d" % layer] = torch.zeros(rows, cols, dtype=BF16, device=dev)
                 sh["lstm%d_wht" % layer] = torch.zeros(cols, cfg.lstm_hidden, dtype=F32, device=dev)
-            if "output_fc_w" in names:
-                sh["output_fc"] = torch.zeros(cfg.lstm_hidden, self.c_pad, dtype=BF16, device=dev)
         self.sh = sh
 
     def _plain_shadow_segments(self):
@@ -275,37 +347,21 @@ class Engine(object):
     def refresh_shadows(self, plain_done=False):
         """fp32 master -> bf16 tensor-core operands (after load and after every optimiser step).  plain_done: the
         same-layout copies (fc6, fc7, LSTM kernels) were already written by vl_sgd_update_shadow."""
-        sh, sp = self.sh, self.sp
-        s1 = sp["conv1"]
-        nv.call("vl_s2d_pack_filter", self.var("dcnn/conv1W"), sh["conv1_fwd"], s1.kh, s1.kw, 3, 96, s1.stride,
-                sp["conv1_s2d"].cchunks * 64, 1)
-        for name in ("conv2", "conv3", "conv4", "conv5"):
-            s = sp[name]
-            w = self.var2d("dcnn/%sW" % name)
-            nv.call("vl_cast_f32_to_bf16", w, sh[name], w.numel())
-            nv.call("vl_pack_bf16_t", w, s.taps * s.cin_g, s.cout, sh[name + "_fwd"], s.k_packed, s.cin_g,
-                    s.cchunks * 64)
-        s2 = sp["conv2"]
-        nv.call("vl_pack_dgrad_d2s", self.var("dcnn/conv2W"), sh["conv2_d2s"], s2.kh, s2.kw, s2.cin_g, s2.cout_g,
-                s2.groups, 2, 2)
+        sh = self.sh
+        nv.call("vl_gather_bf16", self.params, self._shadow_table, self._shadow_arena, self._shadow_arena.numel())
         for name in ("fc6", "fc7"):
             if name in sh and not plain_done:
                 w = self.var("dcnn/%sW" % name)
                 nv.call("vl_cast_f32_to_bf16", w, sh[name], w.numel())
-        if "fc8" in sh:
-            w = self.var("dcnn/fc8W")
-            nv.call("vl_pack_bf16", w, 4096, self.cfg.num_classes, sh["fc8"], 4096, self.c_pad, 4096, 4096)
         if self.cfg.workflow == "lrcn":
             hdim = self.cfg.lstm_hidden
             for layer in range(self.cfg.lstm_layers):
                 kern = self.var("rnn/multi_rnn_cell/cell_%d/basic_lstm_cell/kernel" % layer)
                 if not plain_done:
                     nv.call("vl_cast_f32_to_bf16", kern, sh["lstm%d" % layer], kern.numel())
-                d_in = kern.shape[0] - hdim
-                nv.call("vl_transpose_f32", kern[d_in:], sh["lstm%d_wht" % layer], hdim, 4 * hdim)
-            if "output_fc" in sh:
-                w = self.var("output_fc_w")
-                nv.call("vl_pack_bf16", w, hdim, self.cfg.num_classes, sh["output_fc"], hdim, self.c_pad, hdim, hdim)
+                if hdim != 256:  # the generic BPTT kernel reads w_h^T; the cluster kernel (H = 256) reads w_h itself
+                    d_in = kern.shape[0] - hdim
+                    nv.call("vl_transpose_f32", kern[d_in:], sh["lstm%d_wht" % layer], hdim, 4 * hdim)
 
     # ------------------------------------------------------------------------------------------
     # buffers
@@ -367,6 +423,7 @@ class Engine(object):
         self.A = A
         self.G = None  # gradient-side activation buffers, allocated on the first train_step
         self._pinned = {}
+        self._pinned_busy = {}  # pinned staging buffer -> event of the last asynchronous H2D copy that read it
 
     def _alloc_backward(self):
         sp, dev = self.sp, self.dev
@@ -408,6 +465,7 @@ class Engine(object):
         input (raw_image_shape) when crop offsets accompany them.  Returns (device tensor, is_u8, n_frames)."""
         if isinstance(frames, (list, tuple)):
             frames = np.stack([np.asarray(f) for f in frames], axis=0)
+        pinned_key = None
         if isinstance(frames, np.ndarray):
             if frames.dtype != np.uint8:
                 frames = np.ascontiguousarray(frames, dtype=np.float32)
@@ -419,8 +477,12 @@ class Engine(object):
                 self._pinned[key] = pin
             if host.shape[0] > self.max_frames:
                 raise ValueError("batch of %d frames exceeds the engine capacity %d" % (host.shape[0], self.max_frames))
+            ev = self._pinned_busy.get(key)
+            if ev is not None:
+                ev.synchronize()  # the previous asynchronous H2D copy out of this pinned buffer has finished
             pin[:host.shape[0]].copy_(host)
             frames = pin[:host.shape[0]]
+            pinned_key = key
         assert isinstance(frames, torch.Tensor) and frames.is_contiguous() and frames.dtype in (torch.uint8, F32)
         n = frames.shape[0]
         if n > self.max_frames:
@@ -429,6 +491,10 @@ class Engine(object):
             # host tensor (ideally pinned): one asynchronous H2D copy straight into the device staging buffer
             dst = self._frame_buffer(frames.shape[1:3], frames.dtype)
             dst[:n].copy_(frames, non_blocking=True)
+            if pinned_key is not None:
+                ev = torch.cuda.Event()
+                ev.record()
+                self._pinned_busy[pinned_key] = ev
             frames = dst[:n]
         if self.read_resize is not None and frames.dtype == torch.uint8 and \
                 tuple(int(x) for x in frames.shape[1:3]) != tuple(self.read_resize):
@@ -463,13 +529,16 @@ class Engine(object):
                 raise ValueError("crop window leaves the stored %dx%d frame" % (hr, wr))
             self._crops_dev[:n].copy_(crops, non_blocking=True)
             return self._crops_dev[:n]
+        # device-resident offsets: not validated here (that would synchronise); the staging kernel clamps them
+        # into the stored frame, so an out-of-range window cannot read outside the buffer
         return crops.to(torch.int32).contiguous()
 
     def prefetch(self, frames_pinned, onehot_pinned, slot):
         """Enqueue the H2D copy of one batch (pinned host tensors: uint8 frames [n,H,W,3], int32 one-hot [b,C]) on the
-        copy stream into device slot `slot` (0/1) and return (frames_dev, onehot_dev, event).  The compute stream
-        must wait for `event` before `train_step(frames_dev, onehot_dev, ...)`; with two slots the copy of batch
-        i+1 overlaps the step of batch i."""
+        copy stream into device slot `slot` (0/1) and return (frames_dev, onehot_dev, copied, consumed): the compute
+        stream must wait for the event `copied` before `train_step(frames_dev, onehot_dev, ...)` and record
+        `consumed` after it (the next copy into this slot waits for it); with two slots the copy of batch i+1
+        overlaps the step of batch i."""
         if not hasattr(self, "_copy_stream"):
             self._copy_stream = torch.cuda.Stream(device=self.dev)
             self._slots = {}
@@ -603,14 +672,15 @@ class Engine(object):
                 rows, cols = self.var2d(name).shape
                 if self._split_k(rows, cols, n) == 1:
                     skip.append((self.var_off[name], self.var_off[name] + rows * cols))
+        body = self.grads_ext[self._hdr:]  # the header (step scalars, written by vl_softmax_ce) is not touched
         lo = 0
-        total = self.grads_ext.numel()
+        total = body.numel()
         for b, e in sorted(skip):
             if b > lo:
-                nv.call("vl_zero", self.grads_ext[lo:b], (b - lo) * 4)
+                nv.call("vl_zero", body[lo:b], (b - lo) * 4)
             lo = e
         if total > lo:
-            nv.call("vl_zero", self.grads_ext[lo:], (total - lo) * 4)
+            nv.call("vl_zero", body[lo:], (total - lo) * 4)
 
     def _dense_bwd(self, x, dy, wname, bname, n_valid=None):
         """Filter / bias gradient of y = x @ W + b into the gradient arena."""
@@ -697,10 +767,20 @@ class Engine(object):
         df6 = G["df6"][:n]
         flat = A["p5"][:n].view(n, sp["flat"])
         self._dense_bwd(flat, df6, "dcnn/fc6W", "dcnn/fc6b")
-        if self.world > 1:
-            # fc6/fc7/LSTM/output gradients (89 % of the bytes) are final here: their all-reduce runs on NCCL's
-            # stream while the convolution gradients below are still being computed
-            self._early_reduce = parallel.allreduce_async(self.grads[self.var_off["dcnn/fc6W"]:], self.group)
+        # fc6/fc7/LSTM/output gradients (89 % of the bytes) are final here: their all-reduce (W > 1) runs on NCCL's
+        # stream and their squared norms on a side stream while the convolution gradients below are being computed
+        late = self.grads[self.var_off["dcnn/fc6W"]:]
+        final = torch.cuda.Event()
+        final.record()
+        self._norm_stream.wait_event(final)
+        with torch.cuda.stream(self._norm_stream):
+            if self.world > 1:
+                self._early_reduce = parallel.allreduce_async(late, self.group)
+                parallel.wait(self._early_reduce)
+            nv.call("vl_grad_sqnorms", late, late.numel(), self._seg_late, len(self.var_shapes) - self._k_late,
+                    self.sqnorms[self._k_late:])
+            self._late_norms_ready = torch.cuda.Event()
+            self._late_norms_ready.record()
         K.linear_dgrad(df6, sh["fc6"], G["dp5"][:n].view(n, sp["flat"]))
         nv.call("vl_maxpool_bwd", G["dp5"][:n], A["arg5"][:n], G["da5"][:n], A["a5"][:n], n, s3.p, s3.q, 256)
         self._conv_bwd("conv5", A["a4"][:n], G["da5"][:n], G["da4"][:n], A["a4"][:n])
@@ -757,14 +837,16 @@ class Engine(object):
         used by bench.py to time each contraction launch in isolation for the roofline."""
         if serial:
             cur = torch.cuda.current_stream()
-            self._side, self._side2 = cur, cur
+            self._side, self._side2, self._norm_stream = cur, cur, cur
         else:
-            self._side, self._side2 = self._streams
+            self._side, self._side2, self._norm_stream = self._streams
 
-    def train_step(self, frames, onehot, lr, dropout_mask=None, apply_update=True, crops=None):
+    def train_step(self, frames, onehot, lr, dropout_mask=None, apply_update=True, crops=None, global_clips=None):
         """One `sess.run([loss, lr, global_step, optimizer])` (run_task.py:44, train.py:199-222).
 
         frames: host/device frames of `clips * fpc` images; onehot: int32 [clips, C] (utils_.labels_to_one_hot).
+        global_clips: clips of the GLOBAL batch over all data-parallel ranks (default: local clips x world); the
+        loss is the mean over the global batch (train.py:123) whatever the shard sizes are.
         Returns (loss, lr, global_step, accuracy, grads_norm) with global_step already incremented."""
         cfg, A = self.cfg, self.A
         if self.G is None:
@@ -777,6 +859,8 @@ class Engine(object):
             raise ValueError("number of frames (%d) is not a multiple of num_frames_per_clip (%d)" % (n, cfg.fpc))
         b, c = n // cfg.fpc, cfg.num_classes
         if isinstance(onehot, torch.Tensor):
+            if tuple(onehot.shape) != (b, c):
+                raise ValueError("labels shape %s does not match [%d, %d]" % (tuple(onehot.shape), b, c))
             A["labels"][:b].copy_(onehot.to(torch.int32), non_blocking=True)
         else:
             lab = np.ascontiguousarray(np.asarray(onehot, dtype=np.int32))
@@ -785,15 +869,18 @@ class Engine(object):
             A["labels"][:b].copy_(torch.from_numpy(lab), non_blocking=True)
         feat = self._encoder_fwd(frames, is_u8, n, True, self._stage_crops(crops, frames, n))
         logits = self._head_fwd(feat, n, True)
-        nv.call("vl_softmax_ce", logits, A["labels"][:b], b, c, parallel.local_grad_scale(b, self.world), A["row_loss"],
+        self._global_clips = int(global_clips) if global_clips else b * self.world
+        nv.call("vl_softmax_ce", logits, A["labels"][:b], b, c, 1.0 / self._global_clips, A["row_loss"],
                 self.scalars[4:6], A["dlogits"][:b], A["dlogits_bf"][:b], self.c_pad)
         self._zero_grads(n)
         dfeat = self._head_bwd(n)
         self._encoder_bwd(dfeat, n)
         if self.world > 1:
-            parallel.allreduce_gradients(self.grads[:self.var_off["dcnn/fc6W"]], self.scalars[4:6], self.group)
-            parallel.wait(self._early_reduce)
-        nv.call("vl_grad_sqnorms", self.grads, self.arena_n, self.seg_offsets, len(self.var_shapes), self.sqnorms)
+            # ONE tail collective: [header with loss / correct | conv1..conv5 gradients] (contiguous by construction)
+            parallel.allreduce_gradients(self.grads_ext[:self._hdr + self.var_off["dcnn/fc6W"]], None, self.group)
+        early_n = self.var_off["dcnn/fc6W"]
+        nv.call("vl_grad_sqnorms", self.grads[:early_n], early_n, self._seg_early, self._k_late, self.sqnorms)
+        torch.cuda.current_stream().wait_event(self._late_norms_ready)  # implies the early all-reduce has completed
         clip = float(cfg.clip_norm) if cfg.clip_norm else 0.0
         nv.call("vl_clip_scalars", self.sqnorms, len(self.var_shapes), clip, 1.0, self.scalars)
         if os.environ.get("VL_EARLY_READ", "1") != "0":
@@ -834,7 +921,6 @@ class Engine(object):
             s = self._scalars_host.numpy().copy()
         else:
             s = self.scalars.cpu().numpy()
-        b = self._last_clips
-        loss = float(s[4]) / self.world
-        acc = float(s[5]) / (b * self.world)
+        loss = float(s[4])  # sum over ranks of (1 / global clips) * local row losses = mean over the global batch
+        acc = float(s[5]) / self._global_clips
         return loss, float(lr), self.global_step, acc, float(s[2])
