@@ -134,12 +134,40 @@ def stream_handle():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+# Measurement hook (bench.py, tests/bringup): an object with begin(name, args, meta) / end() brackets every launch that
+# goes through this module, on the stream the kernel is launched on.  `meta` is what the launch wrapper of kernels.py
+# declared just before the call (label + algorithmic FLOPs of a contraction).  None in normal operation.
+tracer = None
+pending_meta = None
+
+
+def declare(label, flops):
+    """Called by the launch wrappers of kernels.py: label and ALGORITHMIC FLOPs (real extents, no padding) of the
+    contraction launched next; consumed by the tracer (if any)."""
+    global pending_meta
+    pending_meta = (label, float(flops))
+
+
+def _traced(name, args, fn):
+    global pending_meta
+    meta, pending_meta = pending_meta, None
+    if tracer is None:
+        return fn()
+    tracer.begin(name, args, meta)
+    try:
+        return fn()
+    finally:
+        tracer.end()
+
+
 def gemm(desc, a, b, c, bias=None, relu_mask=None):
-    check(lib().vl_gemm(ctypes.byref(desc), ptr(a), ptr(b), ptr(c), ptr(bias), ptr(relu_mask), stream_handle()))
+    _traced("vl_gemm", (desc,), lambda: check(lib().vl_gemm(
+        ctypes.byref(desc), ptr(a), ptr(b), ptr(c), ptr(bias), ptr(relu_mask), stream_handle())))
 
 
 def conv_flat(desc, x, w, bias, out):
-    check(lib().vl_conv_flat(ctypes.byref(desc), ptr(x), ptr(w), ptr(bias), ptr(out), stream_handle()))
+    _traced("vl_conv_flat", (desc,), lambda: check(lib().vl_conv_flat(
+        ctypes.byref(desc), ptr(x), ptr(w), ptr(bias), ptr(out), stream_handle())))
 
 
 def call(name, *args):
@@ -152,4 +180,4 @@ def call(name, *args):
             conv.append(ctypes.c_void_p(a.data_ptr()))
         else:
             conv.append(a)
-    check(getattr(lib(), name)(*conv, stream_handle()))
+    _traced(name, args, lambda: check(getattr(lib(), name)(*conv, stream_handle())))

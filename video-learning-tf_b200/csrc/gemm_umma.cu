@@ -411,7 +411,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
       // stage this tile's bias slice in shared memory once (instead of one global load per element)
       if (p.bias != nullptr) {
         asm volatile("bar.sync 1, 128;" ::: "memory");  // previous tile's readers are done
-        for (int j = epi_tid; j < BN; j += 128) sbias[j] = (n0 + j < p.N) ? __ldg(p.bias + gcol0 + j) : 0.f;
+        // split-K (atomic fp32 output): only the split that owns the first k-block adds the bias
+        for (int j = epi_tid; j < BN; j += 128)
+          sbias[j] = (n0 + j < p.N && t.kb_begin == 0) ? __ldg(p.bias + gcol0 + j) : 0.f;
         asm volatile("bar.sync 1, 128;" ::: "memory");
       }
       mbar_wait(&tmem_full[acc], acc_phase);

@@ -14,7 +14,7 @@ extern std::atomic<long long> g_launches;
 namespace {
 
 constexpr int SQ_THREADS = 256;
-constexpr long long SQ_CHUNK = 1 << 16;  // elements per block
+constexpr long long SQ_CHUNK = 1 << 14;  // elements per block (64 per thread: the 9 MB conv slice still fills the GPU)
 
 __global__ void grad_sqnorms_kernel(const float* __restrict__ g, const int64_t* __restrict__ seg, int num_vars,
                                     float* __restrict__ sq) {

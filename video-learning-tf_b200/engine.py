@@ -577,7 +577,8 @@ class Engine(object):
                 int(frames.shape[2]), crops, self.cfg.height, self.cfg.width, s1.stride, s1.pad_top, s1.pad_left,
                 s1s.h, s1s.w)
         a1 = A["a1"][:n]
-        K.conv_fwd_flat(s1s, xs, sh["conv1_fwd"], self.var("dcnn/conv1b"), a1, relu=True)  # tap-shifted kernel
+        K.conv_fwd_flat(s1s, xs, sh["conv1_fwd"], self.var("dcnn/conv1b"), a1, relu=True,
+                        flops=K.conv_flops(s1, n))  # tap-shifted kernel; algorithmic FLOPs of the 11x11x3 layer
         nv.call("vl_lrn_pool_fwd", a1, A["p1"][:n], A["arg1"][:n], n, s1.p, s1.q, 96, LRN["radius"], LRN["alpha"],
                 LRN["beta"], LRN["bias"])
         s2 = sp["conv2"]
@@ -818,7 +819,8 @@ class Engine(object):
                 # row-shift form when an output row fits one k-block (q <= 64): the taps of a filter row share one
                 # staged input row (kernels.conv_wgrad_t); split-K atomics: halves add up
                 K.conv_wgrad_t(s1s, A["x_s2d"][lo:hi], G["da1"][lo:hi], self.dws1,
-                               row_shift=(s1s.q <= 64 and s1s.cin_g <= 64 and os.environ.get("VL_WGRAD_ROW", "1") != "0"))
+                               row_shift=(s1s.q <= 64 and s1s.cin_g <= 64 and os.environ.get("VL_WGRAD_ROW", "1") != "0"),
+                               flops=K.conv_flops(s1, m))
         for ev in da2_ready:
             self._side.wait_event(ev)
         with torch.cuda.stream(self._side):

@@ -80,9 +80,11 @@ def _ld(t):
 # ----------------------------------------------------------------------------------------------------
 # dense layers: tf.nn.relu_layer / tf.nn.xw_plus_b (alexnet.py:228,248,275; tf_util.py:56; lstm.py:141 x-part)
 # ----------------------------------------------------------------------------------------------------
-def linear_fwd(x, w, bias, out, relu=False, n=None, block_n=0, msub=0):
+def linear_fwd(x, w, bias, out, relu=False, n=None, block_n=0, msub=0, split_k=1):
     """out[M,N] = act(x[M,K] @ w[K,N] + bias).  x, w bf16 (w in TF [in,out] layout, row pitch % 8 == 0).
-    block_n / msub = 0: the library's tile choice."""
+    block_n / msub = 0: the library's tile choice.  split_k > 1 (fp32 output, no ReLU): the contraction is split over
+    split_k CTAs per tile that red.add into the zeroed output - for a tall-K, few-tile product (the LSTM input
+    projection: 32 tiles of 64 serial k-blocks on 148 SMs) the k-block chain, not the tensor pipe, is the bound."""
     m, k = x.shape
     n = out.shape[1] if n is None else n
     d = nv.GemmDesc()
@@ -93,8 +95,14 @@ def linear_fwd(x, w, bias, out, relu=False, n=None, block_n=0, msub=0):
     d.c_dtype = nv.DT_BF16 if out.dtype == BF16 else nv.DT_F32
     d.relu = 1 if relu else 0
     d.split_k = 1
+    if split_k > 1:
+        assert out.dtype == F32 and not relu and out.is_contiguous()
+        nv.call("vl_zero", out, out.numel() * 4)
+        d.c_atomic = 1
+        d.split_k = split_k
     d.block_n = block_n
     d.msub = msub
+    nv.declare("dense fwd %dx%dx%d" % (m, n, k), 2.0 * m * n * k)
     nv.gemm(d, x, w, out, bias)
     return out
 
@@ -114,6 +122,7 @@ def linear_dgrad(dy, w, dx, relu_mask=None, n_contract=None, block_n=0):
     d.block_n = block_n
     if relu_mask is not None:
         d.mask_ld = _ld(relu_mask)
+    nv.declare("dense dgrad %dx%dx%d" % (m, k, nn), 2.0 * m * k * nn)
     nv.gemm(d, dy, w, dx, None, relu_mask)
     return dx
 
@@ -133,8 +142,14 @@ def linear_wgrad(x, dy, dw, split_k=1, n=None, block_n=0):
     d.split_k = split_k
     d.block_n = block_n
     assert dw.dtype == F32
+    nv.declare("dense wgrad %dx%dx%d" % (dw.shape[0], n, m), 2.0 * dw.shape[0] * n * m)
     nv.gemm(d, x, dy, dw)
     return dw
+
+
+def conv_flops(spec, n):
+    """Algorithmic FLOPs of one pass (forward, data gradient or filter gradient) of the convolution over n frames."""
+    return 2.0 * n * spec.p * spec.q * spec.cout * spec.taps * spec.cin_g
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -158,11 +173,13 @@ def conv_fwd(spec, x, w_kmajor, bias, out, relu=True, block_n=0, msub=0):
     d.block_n = block_n
     d.msub = msub
     d.conv = spec.geom(n)
+    nv.declare("conv fwd (im2col) %dx%dx%d k%dx%d -> %d g%d" % (spec.h, spec.w, spec.cin, spec.kh, spec.kw, spec.cout,
+                                                               spec.groups), conv_flops(spec, n))
     nv.gemm(d, x, w_kmajor, out, bias)
     return out
 
 
-def conv_fwd_flat(spec, x, w_kmajor, bias, out, relu=True):
+def conv_fwd_flat(spec, x, w_kmajor, bias, out, relu=True, flops=None):
     """Same contract as conv_fwd for stride-1 convolutions with cout_g <= 128, through the tap-shifted kernel
     (csrc/conv_flat.cu): the input tile is staged once per row tile instead of once per tap."""
     assert spec.stride == 1 and out.dtype == BF16
@@ -176,6 +193,9 @@ def conv_fwd_flat(spec, x, w_kmajor, bias, out, relu=True):
     d.w_rows, d.w_ld = spec.cout, spec.k_packed
     d.c_ld = spec.cout
     d.relu = 1 if relu else 0
+    nv.declare("conv fwd (tap-shifted) %dx%dx%d k%dx%d -> %d g%d" % (spec.h, spec.w, spec.cin, spec.kh, spec.kw,
+                                                                    spec.cout, spec.groups),
+               conv_flops(spec, n) if flops is None else flops)  # flops: the layer's own count (conv1 runs as s2d)
     nv.conv_flat(d, x, w_kmajor, bias, out)
     return out
 
@@ -195,6 +215,8 @@ def conv_dgrad_flat(spec, dy, w_dgrad_kmajor, dx):
     d.w_rows, d.w_ld = spec.cin, spec.taps * (-(-spec.cout_g // 64) * 64)
     d.c_ld = spec.cin
     d.relu = 0
+    nv.declare("conv dgrad (tap-shifted) %dx%dx%d k%dx%d g%d" % (spec.h, spec.w, spec.cin, spec.kh, spec.kw, spec.groups),
+               conv_flops(spec, n))
     nv.conv_flat(d, dy, w_dgrad_kmajor, None, dx)
     return dx
 
@@ -237,6 +259,8 @@ def conv_dgrad_d2s(spec, dy, w_d2s, dx, sh=2, sw=2, block_n=0, msub=0):
     g.cin_g = spec.cout_g
     g.flip_taps = 0
     d.conv = g
+    nv.declare("conv dgrad (depth-to-space) %dx%dx%d k%dx%d g%d" % (spec.h, spec.w, spec.cin, spec.kh, spec.kw,
+                                                                   spec.groups), conv_flops(spec, n))
     nv.gemm(d, dy, w_d2s, dx, None, None)
     return dx
 
@@ -258,6 +282,8 @@ def conv_dgrad(spec, dy, w_hwio, dx, relu_mask=None, block_n=0, msub=0):
     d.conv = spec.geom_dgrad(n)
     if relu_mask is not None:
         d.mask_ld = spec.cin
+    nv.declare("conv dgrad (im2col) %dx%dx%d k%dx%d g%d" % (spec.h, spec.w, spec.cin, spec.kh, spec.kw, spec.groups),
+               conv_flops(spec, n))
     nv.gemm(d, dy, w_hwio, dx, None, relu_mask)
     return dx
 
@@ -278,11 +304,13 @@ def conv_wgrad(spec, x, dy, dw, split_k=0, block_n=0, msub=0):
     d.msub = msub
     d.conv = spec.geom(n)
     assert dw.dtype == F32
+    nv.declare("conv wgrad %dx%dx%d k%dx%d g%d" % (spec.h, spec.w, spec.cin, spec.kh, spec.kw, spec.groups),
+               conv_flops(spec, n))
     nv.gemm(d, x, dy, dw)
     return dw
 
 
-def conv_wgrad_t(spec, x, dy, dw, split_k=0, block_n=0, a_ld=0, row_shift=False):
+def conv_wgrad_t(spec, x, dy, dw, split_k=0, block_n=0, a_ld=0, row_shift=False, flops=None):
     """Same contract as conv_wgrad with the operands swapped: output channels (dy^T) on the M side, the (tap, channel
     chunk) axis of im2col(x)^T on the N side.  Every UMMA is 128 x block_n x 16 with block_n = 192 / 256 instead of
     a narrow cout-wide one, and the split-K red.adds of a warp coalesce."""
@@ -305,6 +333,9 @@ def conv_wgrad_t(spec, x, dy, dw, split_k=0, block_n=0, a_ld=0, row_shift=False)
         d.row_shift = 1
         d.block_n = spec.kw * 64
     assert dw.dtype == F32
+    nv.declare("conv wgrad (swapped%s) %dx%dx%d k%dx%d g%d" % (", row-shift" if row_shift else "", spec.h, spec.w,
+                                                              spec.cin, spec.kh, spec.kw, spec.groups),
+               conv_flops(spec, n) if flops is None else flops)
     nv.gemm(d, dy, x, dw)
     return dw
 
