@@ -271,6 +271,14 @@ int vl_segment_pool_fwd(const float* x, const int32_t* seg, int32_t fixed_len, i
 int vl_segment_pool_bwd(const float* dy, const int32_t* seg, int32_t fixed_len, int32_t num_seg, int32_t d,
                         int32_t mode, float* dx, vl_stream_t stream);
 
+/* Early frame fusion (models/model.py:103-108: aggregate_clip_vectors on the dcnn features, tf_util.py:126-133):
+ * x bf16 [num_seg * fixed_len][d] -> y fp32 / bf16 [num_seg][d], avg (rows added in order, one division) or last; and
+ * its gradient fused with the ReLU gradient of the producing layer: dx bf16 = (act > 0) ? pool'(dy) : 0. */
+int vl_segment_pool_fwd_bf16(const void* x, int32_t fixed_len, int32_t num_seg, int32_t d, int32_t mode, float* y,
+                             void* y_bf16, vl_stream_t stream);
+int vl_segment_pool_bwd_relu_bf16(const float* dy, const void* act, int32_t fixed_len, int32_t num_seg, int32_t d,
+                                  int32_t mode, void* dx, vl_stream_t stream);
+
 /* tf.nn.dropout (lstm.py:50-56): y = x * mask, mask in {0, 1/keep}.  The mask is generated on device from
  * (seed, offset) with Philox4x32-10 and returned so that the backward pass (and the oracle) can reuse it. */
 int vl_dropout_mask(float* mask, int64_t n, float keep_prob, uint64_t seed, uint64_t offset, vl_stream_t stream);
@@ -288,12 +296,15 @@ int vl_softmax_ce(const float* logits, const int32_t* labels, int32_t rows, int3
 /* ------------------------------------------------------------------------------------------------
  * Optimiser (train.py:199-222) on one flat fp32 parameter / gradient arena.
  * seg_offsets[num_vars+1] (DEVICE array) delimit the variables inside the arena of n floats.
- * vl_grad_sqnorms writes sum(g^2) per variable (fp32).
+ * vl_grad_sqnorms writes sum(g^2) per variable (fp32) through a deterministic two-stage reduction (no float atomics:
+ * every data-parallel rank must derive the same clip scale from the same reduced gradients); workspace = DEVICE
+ * scratch of vl_grad_sqnorms_workspace(n, num_vars) floats, private to the call while it runs.
  * vl_sgd_update / vl_adam_update apply  g' = g * clip_scale  where clip_scale = clip/max(gnorm, clip) is read
  * from DEVICE memory (scale_dev[0]) so the step needs no host sync.
  * ---------------------------------------------------------------------------------------------- */
+int64_t vl_grad_sqnorms_workspace(int64_t n, int32_t num_vars);
 int vl_grad_sqnorms(const float* grads, int64_t n, const int64_t* seg_offsets, int32_t num_vars, float* sqnorms,
-                    vl_stream_t stream);
+                    float* workspace, int64_t workspace_floats, vl_stream_t stream);
 /* scalars[0]=global norm, [1]=clip scale, [2]=mean_i ||g_i * scale||  (grads_norm summary). clip<=0: no clip. */
 int vl_clip_scalars(const float* sqnorms, int32_t num_vars, float clip_norm, float grad_prescale, float* scalars,
                     vl_stream_t stream);

@@ -53,14 +53,21 @@ if rank == 0:
         loss, rloss, acc, racc, gnorm, rgnorm, worst))
     ok = (abs(loss - rloss) < 1e-4 * max(1.0, abs(rloss)) and abs(acc - racc) < 1e-6 and
           abs(gnorm - rgnorm) < 2e-2 * rgnorm and worst < 5e-2)
-flag = torch.tensor([1 if ok else 0], device="cuda:%d" % local)
+# the verdict and the parameter digests travel on the backend's native device (gloo: host tensors; nccl: device tensors)
+xdev = "cpu" if dist.get_backend() == "gloo" else "cuda:%d" % local
+torch.cuda.synchronize()
+flag = torch.tensor([1 if ok else 0], device=xdev)
 dist.broadcast(flag, 0)
 # both ranks must hold identical parameters after the step
-digest = torch.tensor([float(sum(np.float64(v).sum() for k, v in sd.items() if k != "global_step"))], device="cuda:%d" % local,
-                      dtype=torch.float64)
-# (all_reduce only: gloo moves CUDA tensors for broadcast / all_reduce, not for all_gather)
+per_var = [float(np.float64(v).sum()) for k, v in sorted(sd.items()) if k != "global_step"]
+digest = torch.tensor(per_var, device=xdev, dtype=torch.float64)
 both = torch.cat([digest, -digest])
-dist.all_reduce(both, op=dist.ReduceOp.MAX)
-same = (both[0].item() == -both[1].item())
+dist.all_reduce(both, op=dist.ReduceOp.MAX)  # max(d) == -max(-d) = min(d) on every variable <=> all ranks agree
+k = digest.numel()
+same = bool(torch.equal(both[:k], -both[k:]))
+if not same or flag.item() != 1:
+    print("rank %d: verdict %d, parameters identical across ranks: %s\n  max %s\n  min %s" % (
+        rank, int(flag.item()), same, both[:k].tolist(), (-both[k:]).tolist()), flush=True)
+dist.barrier()
 dist.destroy_process_group()
 sys.exit(0 if (flag.item() == 1 and same) else 1)

@@ -49,7 +49,8 @@ def test_run_task_train_then_resume_then_validate(tmp_path):
         run["train"]["epochs"] = 1
     run_task.main(_cfg("config2_lrcn_train.yml", tmp_path, small_train))
     folder = tmp_path / "run" / "checkpoints"
-    names = [l.strip() for l in open(folder / "checkpoint") if l.strip()]
+    from vlb200 import checkpoint
+    names = checkpoint.read_index(str(folder))
     assert len(names) == 1 and names[0].endswith("ep_1_btch_3_gs_3.graph-3")
     assert os.path.exists(tmp_path / "run" / "config2_train_scratch_lr_decay_schedule.txt")
 
@@ -103,7 +104,8 @@ def test_run_task_on_a_serialized_tfrecord_dataset(tmp_path):
         run["train"]["batch_size"] = 2
         run["train"]["epochs"] = 1
     run_task.main(_cfg("config2_lrcn_train.yml", tmp_path, mutate))
-    names = [l.strip() for l in open(tmp_path / "run" / "checkpoints" / "checkpoint") if l.strip()]
+    from vlb200 import checkpoint
+    names = checkpoint.read_index(str(tmp_path / "run" / "checkpoints"))
     assert names and names[-1].endswith("ep_1_btch_2_gs_2.graph-2")
 
     # device preprocessing == numpy preprocessing on the same draws
@@ -174,5 +176,6 @@ def test_raw_resize_on_the_device_equals_pil_then_crop(tmp_path):
         run["train"]["batch_size"] = 2
         run["train"]["epochs"] = 1
     run_task.main(_cfg("config2_lrcn_train.yml", tmp_path, mutate))
-    names = [l.strip() for l in open(tmp_path / "run" / "checkpoints" / "checkpoint") if l.strip()]
+    from vlb200 import checkpoint
+    names = checkpoint.read_index(str(tmp_path / "run" / "checkpoints"))
     assert names and names[-1].endswith("gs_2.graph-2")

@@ -94,11 +94,11 @@ def test_pipeline_validation_errors(tmp_path):
         run["network"]["pipelines"][0]["lrcn"]["frame_fusion"] = ["defs.fusion_type.early", "defs.fusion_method.avg"]
     st = Settings()
     fd = st.initialize(_load("config2_lrcn_train.yml", tmp_path, fusion_with_lstm))
-    with pytest.raises(Exception, match="fusion type none"):
+    with pytest.raises(Exception, match=r"only with \[none\] fusion"):  # the reference's own text (model.py:125)
         st.engine_config(16)
     st = Settings()
     fd = st.initialize(_load("config2_lrcn_train.yml", tmp_path))
-    with pytest.raises(Exception, match="more than one frame"):
+    with pytest.raises(Exception, match="requires an fpc greater than 1"):  # model.py:121
         st.engine_config(1)
 
 
@@ -141,6 +141,14 @@ class _FakeEngine(object):
         if "global_step" in sd:
             self.global_step = int(sd["global_step"])
 
+    cfg = types.SimpleNamespace(optimizer="sgd")
+
+    def optimizer_state_dict(self):
+        return {}
+
+    def load_optimizer_state_dict(self, sd):
+        return 0
+
 
 def test_checkpoint_roundtrip_and_snap_format(tmp_path):
     eng = _FakeEngine()
@@ -164,5 +172,8 @@ def test_checkpoint_roundtrip_and_snap_format(tmp_path):
     for i in range(3):
         eng.global_step = 18 + i
         checkpoint.save(eng, str(tmp_path), "ep_1_btch_%d_gs_%d" % (5 + i, 18 + i), 5 + i, 0, max_to_keep=2)
+    kept = checkpoint.read_index(os.path.join(str(tmp_path), "checkpoints"))
+    assert len(kept) == 2 and all(os.path.exists(k + ".npz") for k in kept)
     with open(os.path.join(str(tmp_path), "checkpoints", "checkpoint")) as f:
-        assert len([l for l in f if l.strip()]) == 2
+        first = f.readline().strip()  # TensorFlow's layout: the reference's resume_snap reads this line (feeder.py:148-156)
+    assert first == 'model_checkpoint_path: "%s"' % kept[-1]

@@ -62,6 +62,8 @@ def _declare(L):
     L.vl_version.restype = i32
     L.vl_device_sm_count.restype = i32
     L.vl_launch_count.restype = i64
+    L.vl_grad_sqnorms_workspace.restype = i64
+    L.vl_grad_sqnorms_workspace.argtypes = [i64, i32]
     u64 = ctypes.c_uint64
     sigs = {
         "vl_gemm": [ctypes.POINTER(GemmDesc), vp, vp, vp, vp, vp, vp],
@@ -94,10 +96,12 @@ def _declare(L):
         "vl_lstm_bwd": [vp, vp, vp, vp, vp, i32, i32, i32, vp],
         "vl_segment_pool_fwd": [vp, vp, i32, i32, i32, i32, vp, vp, vp],
         "vl_segment_pool_bwd": [vp, vp, i32, i32, i32, i32, vp, vp],
+        "vl_segment_pool_fwd_bf16": [vp, i32, i32, i32, i32, vp, vp, vp],
+        "vl_segment_pool_bwd_relu_bf16": [vp, vp, i32, i32, i32, i32, vp, vp],
         "vl_dropout_mask": [vp, i64, f32, u64, u64, vp],
         "vl_mul": [vp, vp, vp, vp, i64, vp],
         "vl_softmax_ce": [vp, vp, i32, i32, f32, vp, vp, vp, vp, i32, vp],
-        "vl_grad_sqnorms": [vp, i64, vp, i32, vp, vp],
+        "vl_grad_sqnorms": [vp, i64, vp, i32, vp, vp, i64, vp],
         "vl_clip_scalars": [vp, i32, f32, f32, vp, vp],
         "vl_resize_bilinear_u8": [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, i32, vp, vp, i32, vp],
         "vl_sgd_update": [vp, vp, i64, f32, vp, f32, vp],
@@ -115,7 +119,7 @@ EXPORTS = ["vl_last_error", "vl_version", "vl_device_sm_count", "vl_launch_count
            "vl_cast_f32_to_bf16", "vl_transpose_f32", "vl_gather_bf16", "vl_lstm_fwd", "vl_lstm_bwd", "vl_lrn_pool_fwd", "vl_pool_lrn_bwd",
            "vl_lstm_fwd_cluster", "vl_lstm_bwd_cluster", "vl_frames_s2d", "vl_frames_s2d_crop", "vl_pack_bf16_t", "vl_s2d_pack_filter", "vl_s2d_unpack_grad",
            "vl_lrn_pool_fwd_generic", "vl_pool_lrn_bwd_generic", "vl_segment_pool_fwd",
-           "vl_segment_pool_bwd", "vl_dropout_mask", "vl_mul", "vl_softmax_ce", "vl_grad_sqnorms",
+           "vl_segment_pool_bwd", "vl_segment_pool_fwd_bf16", "vl_segment_pool_bwd_relu_bf16", "vl_dropout_mask", "vl_mul", "vl_softmax_ce", "vl_grad_sqnorms", "vl_grad_sqnorms_workspace",
            "vl_clip_scalars", "vl_resize_bilinear_u8", "vl_sgd_update", "vl_sgd_update_shadow", "vl_adam_update"]
 
 

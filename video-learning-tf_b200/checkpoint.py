@@ -38,6 +38,63 @@ def _write_atomic(path, writer, mode="wb"):
     os.replace(tmp, path)
 
 
+def _write_variables(engine, prefix):
+    sd = dict(engine.state_dict())
+    sd.update(engine.optimizer_state_dict())
+    _write_atomic(prefix + ".npz", lambda f: np.savez(f, **{k.replace("/", "|"): v for k, v in sd.items()}))
+
+
+def read_index(folder):
+    """Checkpoint prefixes named by `<folder>/checkpoint`, oldest first.  The file has TensorFlow's layout, which the
+    reference's own reader expects (feeder.py:148-156 takes the quoted path of the FIRST line):
+        model_checkpoint_path: "<latest prefix>"
+        all_model_checkpoint_paths: "<prefix>"      (one line per kept checkpoint, oldest first)
+    Plain one-name-per-line files (written by round 1 of this package) are still understood."""
+    index = os.path.join(folder, "checkpoint")
+    if not os.path.exists(index):
+        return []
+    latest, kept, plain = None, [], []
+    with open(index) as f:
+        for line in f:
+            line = line.strip()
+            if not line:
+                continue
+            if line.startswith("model_checkpoint_path:"):
+                latest = line.split(":", 1)[1].strip().strip('"')
+            elif line.startswith("all_model_checkpoint_paths:"):
+                kept.append(line.split(":", 1)[1].strip().strip('"'))
+            else:
+                plain.append(os.path.join(folder, line))
+    if latest is None:
+        return plain
+    if latest not in kept:
+        kept.append(latest)
+    return kept
+
+
+def _update_index(folder, prefix, max_to_keep=None):
+    prefix = os.path.abspath(prefix)
+    names = [n for n in read_index(folder) if n != prefix] + [prefix]
+    stale = names[:-max_to_keep] if max_to_keep else []
+    if max_to_keep:
+        names = names[-max_to_keep:]
+    lines = ['model_checkpoint_path: "%s"' % names[-1]] + ['all_model_checkpoint_paths: "%s"' % n for n in names]
+    _write_atomic(os.path.join(folder, "checkpoint"), lambda f: f.write("\n".join(lines) + "\n"), mode="w")
+    for old in stale:  # only after the index stopped naming them
+        for ext in (".npz", ".snap", ".meta", ".index"):
+            if os.path.exists(old + ext):
+                os.remove(old + ext)
+
+
+def save_prefix(engine, prefix, max_to_keep=None):
+    """`tf.train.Saver.save` of the shim (tfshim.py): variables + optimiser slots to `<prefix>.npz`, then the index.
+    The reference's feeder.save writes the `.snap` itself afterwards (feeder.py:263-288)."""
+    os.makedirs(os.path.dirname(prefix), exist_ok=True)
+    _write_variables(engine, prefix)
+    _update_index(os.path.dirname(prefix), prefix, max_to_keep)
+    return prefix
+
+
 def save(engine, run_folder, progress_str, batch_index, epoch_index, max_to_keep=None):
     """Variables + optimiser slots (tf.train.Saver saves all global variables: feeder.py:263-288) + the `.snap`
     progress pickle.  Order: weights, snap, and only then the `checkpoint` index, each through an atomic rename, so
@@ -45,26 +102,10 @@ def save(engine, run_folder, progress_str, batch_index, epoch_index, max_to_keep
     folder = checkpoint_folder(run_folder)
     os.makedirs(folder, exist_ok=True)
     gs = engine.global_step
-    prefix = os.path.join(folder, "%s_%s.graph-%d" % (time.strftime("%d%m%y_%H%M%S"), progress_str, gs))
-    sd = dict(engine.state_dict())
-    sd.update(engine.optimizer_state_dict())
-    _write_atomic(prefix + ".npz", lambda f: np.savez(f, **{k.replace("/", "|"): v for k, v in sd.items()}))
+    prefix = os.path.abspath(os.path.join(folder, "%s_%s.graph-%d" % (time.strftime("%d%m%y_%H%M%S"), progress_str, gs)))
+    _write_variables(engine, prefix)
     _write_atomic(prefix + ".snap", lambda f: pickle.dump([batch_index, epoch_index, gs], f))
-    index = os.path.join(folder, "checkpoint")
-    names = []
-    if os.path.exists(index):
-        with open(index) as f:
-            names = [l.strip() for l in f if l.strip()]
-    names.append(os.path.basename(prefix))
-    stale = names[:-max_to_keep] if max_to_keep else []
-    if max_to_keep:
-        names = names[-max_to_keep:]
-    _write_atomic(index, lambda f: f.write("\n".join(names) + "\n"), mode="w")
-    for old in stale:  # only after the index stopped naming them
-        for ext in (".npz", ".snap"):
-            p = os.path.join(folder, old + ext)
-            if os.path.exists(p):
-                os.remove(p)
+    _update_index(folder, prefix, max_to_keep)
     info("Saved checkpoint %s" % prefix)
     return prefix
 
@@ -72,14 +113,12 @@ def save(engine, run_folder, progress_str, batch_index, epoch_index, max_to_keep
 def resolve(run_folder, resume_file):
     folder = checkpoint_folder(run_folder)
     if resume_file == "latest":
-        index = os.path.join(folder, "checkpoint")
-        if not os.path.exists(index):
+        if not os.path.exists(os.path.join(folder, "checkpoint")):
             error("No checkpoint index in %s to resume `latest` from" % folder)
-        with open(index) as f:
-            names = [l.strip() for l in f if l.strip()]
+        names = read_index(folder)
         if not names:
-            error("Empty checkpoint index %s" % index)
-        return os.path.join(folder, names[-1])
+            error("Empty checkpoint index %s" % os.path.join(folder, "checkpoint"))
+        return names[-1]
     cand = resume_file if os.path.isabs(resume_file) else os.path.join(folder, resume_file)
     for ext in (".npz", ".snap"):
         if cand.endswith(ext):
@@ -92,7 +131,7 @@ def resolve(run_folder, resume_file):
     return cand
 
 
-def restore(engine, prefix, ignorable=("global_step",), is_validation=False):
+def restore(engine, prefix, ignorable=("global_step",), is_validation=False, read_snap=True):
     """Load variables (name-diff check like feeder.py:229-249) and return (batch_index, epoch_index, global_step)."""
     blob = np.load(prefix + ".npz")
     sd = {k.replace("|", "/"): blob[k] for k in blob.files}
@@ -112,7 +151,7 @@ def restore(engine, prefix, ignorable=("global_step",), is_validation=False):
         if engine.cfg.optimizer == "adam" and n_slots == 0:
             warning("Checkpoint %s holds no Adam slots: the moments restart from zero" % prefix)
     snap = [0, 0, int(sd.get("global_step", 0))]
-    if os.path.exists(prefix + ".snap"):
+    if read_snap and os.path.exists(prefix + ".snap"):
         with open(prefix + ".snap", "rb") as f:
             snap = pickle.load(f)
     info("Restored %s: batch %d, epoch %d, global step %d" % (prefix, snap[0], snap[1], snap[2]))

@@ -63,6 +63,48 @@ __global__ void segment_pool_bwd_kernel(const float* __restrict__ dy, const int3
   }
 }
 
+// Early frame fusion (model.py:103-108: aggregate_clip_vectors on the dcnn FEATURES): the same pooling over bf16 rows
+// (the encoder stores its activations in bf16), fp32 accumulation in row order.
+__global__ void segment_pool_fwd_bf16_kernel(const bf16* __restrict__ x, int fixed_len, int num_seg, int d, int mode,
+                                             float* __restrict__ y, bf16* __restrict__ y_bf16) {
+  const long long total = (long long)num_seg * d;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int s = (int)(idx / d);
+    const int col = (int)(idx - (long long)s * d);
+    const long long lo = (long long)s * fixed_len, hi = lo + fixed_len;
+    float out;
+    if (mode == VL_POOL_LAST) {
+      out = __bfloat162float(x[(hi - 1) * d + col]);
+    } else {
+      float acc = __bfloat162float(x[lo * d + col]);
+      for (long long r = lo + 1; r < hi; ++r) acc = __fadd_rn(acc, __bfloat162float(x[r * d + col]));
+      out = __fdiv_rn(acc, (float)fixed_len);
+    }
+    if (y) y[idx] = out;
+    if (y_bf16) y_bf16[idx] = __float2bfloat16_rn(out);
+  }
+}
+
+// ... and its gradient fused with the ReLU gradient of the layer that produced the features:
+// dx[r][col] = (act[r][col] > 0) ? pool'(dy[s][col]) : 0, stored in bf16 (the operand of the fc filter gradient).
+__global__ void segment_pool_bwd_relu_bf16_kernel(const float* __restrict__ dy, const bf16* __restrict__ act,
+                                                  int fixed_len, int num_seg, int d, int mode, bf16* __restrict__ dx) {
+  const long long total = (long long)num_seg * fixed_len * d;
+  const float inv = 1.0f / (float)fixed_len;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long r = idx / d;
+    const int col = (int)(idx - r * d);
+    const int s = (int)(r / fixed_len);
+    const int t = (int)(r - (long long)s * fixed_len);
+    float g = dy[(long long)s * d + col];
+    g = (mode == VL_POOL_LAST) ? (t == fixed_len - 1 ? g : 0.f) : g * inv;
+    if (!(__bfloat162float(act[idx]) > 0.f)) g = 0.f;
+    dx[idx] = __float2bfloat16_rn(g);
+  }
+}
+
 // ---- Philox4x32-10 ----
 __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
   const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
@@ -226,6 +268,28 @@ extern "C" int vl_segment_pool_bwd(const float* dy, const int32_t* seg, int32_t 
   VL_REQUIRE(dy && dx && num_seg > 0 && d > 0, "vl_segment_pool_bwd: bad arguments");
   VL_REQUIRE(mode == VL_POOL_AVG || mode == VL_POOL_LAST, "vl_segment_pool_bwd: only avg/last have gradients");
   segment_pool_bwd_kernel<<<num_seg, 256, 0, stream>>>(dy, seg, fixed_len, num_seg, d, mode, dx);
+  VL_LAUNCHED();
+  return 0;
+}
+
+extern "C" int vl_segment_pool_fwd_bf16(const void* x, int32_t fixed_len, int32_t num_seg, int32_t d, int32_t mode,
+                                        float* y, void* y_bf16, vl_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  VL_REQUIRE(x && (y || y_bf16) && num_seg > 0 && d > 0 && fixed_len > 0, "vl_segment_pool_fwd_bf16: bad arguments");
+  VL_REQUIRE(mode == VL_POOL_AVG || mode == VL_POOL_LAST, "Undefined frame fusion type : %d", mode);
+  segment_pool_fwd_bf16_kernel<<<sweep_grid((long long)num_seg * d, 256), 256, 0, stream>>>(
+      reinterpret_cast<const bf16*>(x), fixed_len, num_seg, d, mode, y, reinterpret_cast<bf16*>(y_bf16));
+  VL_LAUNCHED();
+  return 0;
+}
+
+extern "C" int vl_segment_pool_bwd_relu_bf16(const float* dy, const void* act, int32_t fixed_len, int32_t num_seg,
+                                             int32_t d, int32_t mode, void* dx, vl_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  VL_REQUIRE(dy && act && dx && num_seg > 0 && d > 0 && fixed_len > 0, "vl_segment_pool_bwd_relu_bf16: bad arguments");
+  VL_REQUIRE(mode == VL_POOL_AVG || mode == VL_POOL_LAST, "vl_segment_pool_bwd_relu_bf16: only avg/last have gradients");
+  segment_pool_bwd_relu_bf16_kernel<<<sweep_grid((long long)num_seg * fixed_len * d, 256), 256, 0, stream>>>(
+      dy, reinterpret_cast<const bf16*>(act), fixed_len, num_seg, d, mode, reinterpret_cast<bf16*>(dx));
   VL_LAUNCHED();
   return 0;
 }

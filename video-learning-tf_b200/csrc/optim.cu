@@ -16,15 +16,21 @@ namespace {
 constexpr int SQ_THREADS = 256;
 constexpr long long SQ_CHUNK = 1 << 14;  // elements per block (64 per thread: the 9 MB conv slice still fills the GPU)
 
-__global__ void grad_sqnorms_kernel(const float* __restrict__ g, const int64_t* __restrict__ seg, int num_vars,
-                                    float* __restrict__ sq) {
+// Deterministic two-stage reduction (no floating-point atomics): every data-parallel rank must derive the SAME clip
+// scale from the same all-reduced gradients, or the replicas drift apart by an ulp per step.
+// stage 1: block b owns elements [b * SQ_CHUNK, (b+1) * SQ_CHUNK) and writes partial[b][v] for every variable v.
+__global__ void grad_sqnorms_partial_kernel(const float* __restrict__ g, const int64_t* __restrict__ seg, int num_vars,
+                                            float* __restrict__ partial) {
   __shared__ float red[SQ_THREADS / 32];
   const long long c0 = (long long)blockIdx.x * SQ_CHUNK;
   const long long c1 = c0 + SQ_CHUNK;
   for (int v = 0; v < num_vars; ++v) {
     const long long lo = max((long long)seg[v], c0);
     const long long hi = min((long long)seg[v + 1], c1);
-    if (hi <= lo) continue;  // block-uniform
+    if (hi <= lo) {  // block-uniform
+      if (threadIdx.x == 0) partial[(long long)blockIdx.x * num_vars + v] = 0.f;
+      continue;
+    }
     float acc = 0.f;
     for (long long i = lo + threadIdx.x; i < hi; i += SQ_THREADS) {
       const float x = g[i];
@@ -36,10 +42,26 @@ __global__ void grad_sqnorms_kernel(const float* __restrict__ g, const int64_t* 
     if (threadIdx.x == 0) {
       float s = 0.f;
       for (int w = 0; w < SQ_THREADS / 32; ++w) s += red[w];
-      atomicAdd(sq + v, s);
+      partial[(long long)blockIdx.x * num_vars + v] = s;
     }
     __syncthreads();
   }
+}
+
+// stage 2: block v sums partial[0..nblocks)[v] in a fixed order (strided per thread, then a shared-memory tree).
+__global__ void grad_sqnorms_final_kernel(const float* __restrict__ partial, int nblocks, int num_vars,
+                                          float* __restrict__ sq) {
+  __shared__ float red[SQ_THREADS];
+  const int v = blockIdx.x;
+  float acc = 0.f;
+  for (int b = threadIdx.x; b < nblocks; b += SQ_THREADS) acc += partial[(long long)b * num_vars + v];
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = SQ_THREADS / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) sq[v] = red[0];
 }
 
 __global__ void clip_scalars_kernel(const float* __restrict__ sq, int num_vars, float clip, float prescale,
@@ -141,13 +163,21 @@ int sweep_grid(long long work, int block) {
     VL_CHECK_CUDA(cudaGetLastError()); \
   } while (0)
 
+extern "C" int64_t vl_grad_sqnorms_workspace(int64_t n, int32_t num_vars) {
+  return ((n + SQ_CHUNK - 1) / SQ_CHUNK) * (int64_t)num_vars;
+}
+
 extern "C" int vl_grad_sqnorms(const float* grads, int64_t n, const int64_t* seg_offsets, int32_t num_vars,
-                                 float* sqnorms, vl_stream_t stream_) {
+                               float* sqnorms, float* workspace, int64_t workspace_floats, vl_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  VL_REQUIRE(grads && seg_offsets && sqnorms && num_vars > 0 && n > 0, "vl_grad_sqnorms: bad arguments");
-  VL_CHECK_CUDA(cudaMemsetAsync(sqnorms, 0, sizeof(float) * num_vars, stream));
+  VL_REQUIRE(grads && seg_offsets && sqnorms && workspace && num_vars > 0 && n > 0, "vl_grad_sqnorms: bad arguments");
   const int grid = (int)((n + SQ_CHUNK - 1) / SQ_CHUNK);
-  grad_sqnorms_kernel<<<grid, SQ_THREADS, 0, stream>>>(grads, seg_offsets, num_vars, sqnorms);
+  VL_REQUIRE(workspace_floats >= (int64_t)grid * num_vars,
+             "vl_grad_sqnorms: workspace of %lld floats, %lld needed (vl_grad_sqnorms_workspace)",
+             (long long)workspace_floats, (long long)grid * num_vars);
+  grad_sqnorms_partial_kernel<<<grid, SQ_THREADS, 0, stream>>>(grads, seg_offsets, num_vars, workspace);
+  VL_LAUNCHED();
+  grad_sqnorms_final_kernel<<<num_vars, SQ_THREADS, 0, stream>>>(workspace, grid, num_vars, sqnorms);
   VL_LAUNCHED();
   return 0;
 }

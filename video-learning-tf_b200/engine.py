@@ -30,14 +30,25 @@ def _align(n, a=64):
 class EngineConfig(object):
     """The subset of `Settings` (settings_.py) the device path depends on."""
 
+    """workflow:
+      lrcn         dcnn(fc6|fc7) -> LSTM -> temporal fusion (avg | last | state) -> dropout -> output fc  (lstm.py:59-99)
+      singleframe  dcnn(fc8 logits per frame) -> late fusion over fpc                                    (model.py:149-151)
+      fc           dcnn(fc6|fc7) -> [early fusion over fpc] -> convert_dim_fc "fc_convert" -> [late fusion]
+                   (classifier fc, model.py:103-117,149-151); early_fusion selects which of the two fusions applies
+    fusion `state` (lstm.py:81,91-93; model.py:137-143): the logits come from the final hidden state h of the top
+    layer through convert_dim_fc under its default name (fc_convert), without temporal fusion, dropout or output_fc."""
+
     def __init__(self, num_classes=101, fpc=16, workflow="lrcn", frame_encoding_layer="fc7", lstm_hidden=256,
                  lstm_layers=1, fusion="avg", optimizer="sgd", clip_norm=None, dropout_keep_prob=0.0,
-                 height=227, width=227, mean=None, seed=1234):
-        assert workflow in ("lrcn", "singleframe")
+                 height=227, width=227, mean=None, seed=1234, early_fusion=False):
+        assert workflow in ("lrcn", "singleframe", "fc")
         self.num_classes = int(num_classes)
         self.fpc = int(fpc)
         self.workflow = workflow
-        self.frame_encoding_layer = frame_encoding_layer if workflow == "lrcn" else "fc8"
+        self.early_fusion = bool(early_fusion) and workflow == "fc"
+        self.frame_encoding_layer = frame_encoding_layer if workflow in ("lrcn", "fc") else "fc8"
+        if workflow == "fc" and self.frame_encoding_layer not in ("fc6", "fc7"):
+            raise ValueError("the fc workflow classifies fc6 / fc7 features (fc8 logits: workflow singleframe)")
         self.lstm_hidden = int(lstm_hidden)
         self.lstm_layers = int(lstm_layers)
         self.fusion = fusion
@@ -47,7 +58,9 @@ class EngineConfig(object):
         self.height, self.width = int(height), int(width)
         self.mean = tuple(mean) if mean is not None else None
         self.seed = int(seed)
-        if fusion not in ("avg", "last"):
+        if fusion not in ("avg", "last") and not (fusion == "state" and workflow == "lrcn"):
+            # `reshape` (tf_util.py:24-27) leaves one row per FRAME, which no label layout of the feeder matches
+            # (dataset_.py:400-408: one label row per clip); anything else is undefined in the reference too
             raise ValueError("Undefined frame fusion type : %s" % fusion)
         if optimizer not in ("sgd", "adam"):
             raise ValueError("Undefined optimizer %s" % optimizer)
@@ -80,8 +93,14 @@ def variable_shapes(cfg):
             out.append(("rnn/multi_rnn_cell/cell_%d/basic_lstm_cell/bias" % layer, (4 * cfg.lstm_hidden,)))
             d_in = cfg.lstm_hidden
         if cfg.lstm_hidden != cfg.num_classes:
-            out.append(("output_fc_w", (cfg.lstm_hidden, cfg.num_classes)))
-            out.append(("output_fc_b", (cfg.num_classes,)))
+            # tf.get_variable ignores name scopes: "output_fc_{w,b}" (lstm.py:90), or convert_dim_fc's default name
+            # "fc_convert_{w,b}" when the logits come from the LSTM state (model.py:137-143)
+            fc = "fc_convert" if cfg.fusion == "state" else "output_fc"
+            out.append((fc + "_w", (cfg.lstm_hidden, cfg.num_classes)))
+            out.append((fc + "_b", (cfg.num_classes,)))
+    elif cfg.workflow == "fc" and feat != cfg.num_classes:
+        out.append(("fc_convert_w", (feat, cfg.num_classes)))  # model.py:115-117 convert_dim_fc(feature_vectors, C)
+        out.append(("fc_convert_b", (cfg.num_classes,)))
     return out
 
 
@@ -180,6 +199,12 @@ class Engine(object):
         off_late = offsets[self._k_late]
         self._seg_early = torch.tensor(offsets[:self._k_late + 1], dtype=torch.int64, device=self.dev)
         self._seg_late = torch.tensor([o - off_late for o in offsets[self._k_late:]], dtype=torch.int64, device=self.dev)
+        # scratch of the two (possibly concurrent) deterministic norm reductions
+        n_late_vars = len(self.var_shapes) - self._k_late
+        self._ws_late = torch.empty(int(nv.lib().vl_grad_sqnorms_workspace(off - off_late, n_late_vars)), dtype=F32,
+                                    device=self.dev)
+        self._ws_early = torch.empty(int(nv.lib().vl_grad_sqnorms_workspace(off_late, self._k_late)), dtype=F32,
+                                     device=self.dev)
         self.sqnorms = torch.zeros(len(self.var_shapes), dtype=F32, device=self.dev)
         self.scalars = self.grads_ext[:8]
         self.adam_m = self.adam_v = None
@@ -394,7 +419,11 @@ class Engine(object):
         A["f6"] = act(n, 4096)
         A["f7"] = act(n, 4096)
         c, cp, hd = cfg.num_classes, self.c_pad, cfg.lstm_hidden
-        if cfg.workflow == "singleframe":
+        if cfg.workflow == "fc" and cfg.early_fusion:
+            A["pooled"] = act(b, 4096, dtype=F32)
+            A["pooled_bf"] = act(b, 4096)
+            A["dpooled"] = act(b, 4096, dtype=F32)
+        elif cfg.workflow in ("singleframe", "fc"):
             A["frame_logits"] = act(n, c, dtype=F32)
             A["d_frame_logits"] = act(n, cp, dtype=F32)
             A["d_frame_logits_bf16"] = act(n, cp)
@@ -603,9 +632,17 @@ class Engine(object):
         b = n // cfg.fpc
         c = cfg.num_classes
         logits = A["logits"][:b]
-        if cfg.workflow == "singleframe":
+        if cfg.workflow == "fc" and cfg.early_fusion:
+            # aggregate_clip_vectors on the features (model.py:103-108), then convert_dim_fc (model.py:115-117)
+            dim = feat.shape[1]
+            nv.call("vl_segment_pool_fwd_bf16", feat, cfg.fpc, b, dim, POOL[cfg.fusion], A["pooled"][:b],
+                    A["pooled_bf"][:b])
+            K.linear_fwd(A["pooled_bf"][:b], sh["fc_convert"], self.var("fc_convert_b"), logits, relu=False, n=c)
+            return logits
+        if cfg.workflow in ("singleframe", "fc"):
+            key, bname = self._frame_classifier()
             fl = A["frame_logits"][:n]
-            K.linear_fwd(feat, sh["fc8"], self.var("dcnn/fc8b"), fl, relu=False, n=c)
+            K.linear_fwd(feat, sh[key], self.var(bname), fl, relu=False, n=c)
             nv.call("vl_segment_pool_fwd", fl, None, cfg.fpc, b, c, POOL[cfg.fusion], logits, None)
             return logits
         hd, t_len = cfg.lstm_hidden, cfg.fpc
@@ -621,9 +658,12 @@ class Engine(object):
                     A["hprev_bf%d" % layer][:n], b, t_len, hd, 1.0)
             x = A["hseq_bf%d" % layer][:n]
         hseq = A["hseq%d" % (cfg.lstm_layers - 1)][:n]
-        nv.call("vl_segment_pool_fwd", hseq, None, t_len, b, hd, POOL[cfg.fusion], A["fused"][:b], A["fused_bf"][:b])
+        # fusion `state`: the final hidden state of the top layer = its output at the last step (full-length sequences)
+        state = cfg.fusion == "state"
+        nv.call("vl_segment_pool_fwd", hseq, None, t_len, b, hd, POOL["last" if state else cfg.fusion], A["fused"][:b],
+                A["fused_bf"][:b])
         top, top_bf = A["fused"][:b], A["fused_bf"][:b]
-        self._dropout_on = bool(training and cfg.dropout_keep_prob > 0)  # lstm.py:52
+        self._dropout_on = bool(training and cfg.dropout_keep_prob > 0 and not state)  # lstm.py:52; no dropout on state
         if self._dropout_on:
             if self._injected_mask is not None:
                 A["mask"][:b].copy_(self._injected_mask)
@@ -633,11 +673,17 @@ class Engine(object):
             nv.call("vl_mul", top, A["mask"][:b], A["dropped"][:b], A["dropped_bf"][:b], b * hd)
             top, top_bf = A["dropped"][:b], A["dropped_bf"][:b]
         self._top_bf = top_bf
-        if "output_fc" in sh:
-            K.linear_fwd(top_bf, sh["output_fc"], self.var("output_fc_b"), logits, relu=False, n=c)
+        fc = "fc_convert" if state else "output_fc"
+        if fc in sh:
+            K.linear_fwd(top_bf, sh[fc], self.var(fc + "_b"), logits, relu=False, n=c)
         else:
             logits.copy_(top)
         return logits
+
+    def _frame_classifier(self):
+        """(operand key, bias variable) of the per-frame classifier: fc8 inside the dcnn (single-frame workflow) or
+        convert_dim_fc on top of fc6 / fc7 features (classifier fc with late fusion)."""
+        return ("fc8", "dcnn/fc8b") if self.cfg.workflow == "singleframe" else ("fc_convert", "fc_convert_b")
 
     _injected_mask = None
 
@@ -715,19 +761,30 @@ class Engine(object):
         feat_name = "f7" if "fc7" in sh else "f6"
         feat = A[feat_name][:n]
         dfeat = G["d" + feat_name][:n]
-        if cfg.workflow == "singleframe":
+        if cfg.workflow == "fc" and cfg.early_fusion:
+            dim = feat.shape[1]
+            dl_bf = A["dlogits_bf"][:b]
+            self._dense_bwd(A["pooled_bf"][:b], dl_bf, "fc_convert_w", "fc_convert_b")
+            K.linear_dgrad(dl_bf, sh["fc_convert"], A["dpooled"][:b], n_contract=c)
+            nv.call("vl_segment_pool_bwd_relu_bf16", A["dpooled"][:b], feat, cfg.fpc, b, dim, POOL[cfg.fusion], dfeat)
+            return dfeat
+        if cfg.workflow in ("singleframe", "fc"):
+            key, bname = self._frame_classifier()
+            wname = bname[:-1] + "W" if key == "fc8" else "fc_convert_w"
             dfl = A["d_frame_logits"][:n]
             nv.call("vl_segment_pool_bwd", A["dlogits"][:b], None, cfg.fpc, b, self.c_pad, POOL[cfg.fusion], dfl)
             nv.call("vl_mul", dfl, None, None, A["d_frame_logits_bf16"][:n], n * self.c_pad)
             dfl_bf = A["d_frame_logits_bf16"][:n]
-            self._dense_bwd(feat, dfl_bf, "dcnn/fc8W", "dcnn/fc8b")
-            K.linear_dgrad(dfl_bf, sh["fc8"], dfeat, relu_mask=feat, n_contract=c)
+            self._dense_bwd(feat, dfl_bf, wname, bname)
+            K.linear_dgrad(dfl_bf, sh[key], dfeat, relu_mask=feat, n_contract=c)
             return dfeat
         hd, t_len = cfg.lstm_hidden, cfg.fpc
         dl_bf = A["dlogits_bf"][:b]
-        if "output_fc" in sh:
-            self._dense_bwd(self._top_bf, dl_bf, "output_fc_w", "output_fc_b")
-            K.linear_dgrad(dl_bf, sh["output_fc"], A["ddropped"][:b], n_contract=c)
+        state = cfg.fusion == "state"
+        fc = "fc_convert" if state else "output_fc"
+        if fc in sh:
+            self._dense_bwd(self._top_bf, dl_bf, fc + "_w", fc + "_b")
+            K.linear_dgrad(dl_bf, sh[fc], A["ddropped"][:b], n_contract=c)
             dtop = A["ddropped"][:b]
         else:
             dtop = A["dlogits"][:b, :c].contiguous()
@@ -735,7 +792,8 @@ class Engine(object):
             nv.call("vl_mul", dtop, A["mask"][:b], A["dfused"][:b], None, b * hd)
             dtop = A["dfused"][:b]
         top = cfg.lstm_layers - 1
-        nv.call("vl_segment_pool_bwd", dtop, None, t_len, b, hd, POOL[cfg.fusion], A["dhseq%d" % top][:n])
+        nv.call("vl_segment_pool_bwd", dtop, None, t_len, b, hd, POOL["last" if state else cfg.fusion],
+                A["dhseq%d" % top][:n])
         for layer in range(top, -1, -1):
             kn = "rnn/multi_rnn_cell/cell_%d/basic_lstm_cell/kernel" % layer
             bn = "rnn/multi_rnn_cell/cell_%d/basic_lstm_cell/bias" % layer
@@ -759,17 +817,10 @@ class Engine(object):
                 K.linear_dgrad(dg, sh["lstm0"][:d_in], dfeat, relu_mask=feat)
         return dfeat
 
-    def _encoder_bwd(self, dfeat, n):
-        A, G, sp, sh = self.A, self.G, self.sp, self.sh
-        s1, s2, s3 = sp["conv1"], sp["conv2"], sp["conv3"]
-        if "fc7" in sh:
-            self._dense_bwd(A["f6"][:n], dfeat, "dcnn/fc7W", "dcnn/fc7b")
-            K.linear_dgrad(dfeat, sh["fc7"], G["df6"][:n], relu_mask=A["f6"][:n])
-        df6 = G["df6"][:n]
-        flat = A["p5"][:n].view(n, sp["flat"])
-        self._dense_bwd(flat, df6, "dcnn/fc6W", "dcnn/fc6b")
-        # fc6/fc7/LSTM/output gradients (89 % of the bytes) are final here: their all-reduce (W > 1) runs on NCCL's
-        # stream and their squared norms on a side stream while the convolution gradients below are being computed
+    def _reduce_late_gradients(self):
+        """fc6/fc7/LSTM/output gradients (89 % of the bytes) are final once fc6's filter gradient is enqueued: their
+        all-reduce (W > 1) runs on NCCL's stream and their squared norms on a side stream while the convolution
+        gradients are still being computed."""
         late = self.grads[self.var_off["dcnn/fc6W"]:]
         final = torch.cuda.Event()
         final.record()
@@ -779,9 +830,20 @@ class Engine(object):
                 self._early_reduce = parallel.allreduce_async(late, self.group)
                 parallel.wait(self._early_reduce)
             nv.call("vl_grad_sqnorms", late, late.numel(), self._seg_late, len(self.var_shapes) - self._k_late,
-                    self.sqnorms[self._k_late:])
+                    self.sqnorms[self._k_late:], self._ws_late, self._ws_late.numel())
             self._late_norms_ready = torch.cuda.Event()
             self._late_norms_ready.record()
+
+    def _encoder_bwd(self, dfeat, n):
+        A, G, sp, sh = self.A, self.G, self.sp, self.sh
+        s1, s2, s3 = sp["conv1"], sp["conv2"], sp["conv3"]
+        if "fc7" in sh:
+            self._dense_bwd(A["f6"][:n], dfeat, "dcnn/fc7W", "dcnn/fc7b")
+            K.linear_dgrad(dfeat, sh["fc7"], G["df6"][:n], relu_mask=A["f6"][:n])
+        df6 = G["df6"][:n]
+        flat = A["p5"][:n].view(n, sp["flat"])
+        self._dense_bwd(flat, df6, "dcnn/fc6W", "dcnn/fc6b")
+        self._reduce_late_gradients()
         K.linear_dgrad(df6, sh["fc6"], G["dp5"][:n].view(n, sp["flat"]))
         nv.call("vl_maxpool_bwd", G["dp5"][:n], A["arg5"][:n], G["da5"][:n], A["a5"][:n], n, s3.p, s3.q, 256)
         self._conv_bwd("conv5", A["a4"][:n], G["da5"][:n], G["da4"][:n], A["a4"][:n])
@@ -856,6 +918,15 @@ class Engine(object):
         self._injected_mask = None
         if dropout_mask is not None:
             self._injected_mask = torch.as_tensor(np.asarray(dropout_mask, dtype=np.float32)).to(self.dev)
+        if len(frames) == 0:
+            # a data-parallel rank whose share of this batch is empty (fewer videos than ranks): zero gradients, zero
+            # loss / correct count, and the same collectives as every other rank
+            if self.world <= 1 or not global_clips:
+                raise ValueError("empty batch")
+            self._global_clips = int(global_clips)
+            nv.call("vl_zero", self.grads_ext, self.grads_ext.numel() * 4)
+            self._reduce_late_gradients()
+            return self._finish_step(lr, apply_update)
         frames, is_u8, n = self._stage_frames(frames)
         if n % cfg.fpc != 0:
             raise ValueError("number of frames (%d) is not a multiple of num_frames_per_clip (%d)" % (n, cfg.fpc))
@@ -877,11 +948,17 @@ class Engine(object):
         self._zero_grads(n)
         dfeat = self._head_bwd(n)
         self._encoder_bwd(dfeat, n)
+        return self._finish_step(lr, apply_update)
+
+    def _finish_step(self, lr, apply_update):
+        """Tail of a train step: the remaining all-reduce, global-norm clip, optimiser, operand refresh, read-back."""
+        cfg = self.cfg
         if self.world > 1:
             # ONE tail collective: [header with loss / correct | conv1..conv5 gradients] (contiguous by construction)
             parallel.allreduce_gradients(self.grads_ext[:self._hdr + self.var_off["dcnn/fc6W"]], None, self.group)
         early_n = self.var_off["dcnn/fc6W"]
-        nv.call("vl_grad_sqnorms", self.grads[:early_n], early_n, self._seg_early, self._k_late, self.sqnorms)
+        nv.call("vl_grad_sqnorms", self.grads[:early_n], early_n, self._seg_early, self._k_late, self.sqnorms,
+                self._ws_early, self._ws_early.numel())
         torch.cuda.current_stream().wait_event(self._late_norms_ready)  # implies the early all-reduce has completed
         clip = float(cfg.clip_norm) if cfg.clip_norm else 0.0
         nv.call("vl_clip_scalars", self.sqnorms, len(self.var_shapes), clip, 1.0, self.scalars)
@@ -909,7 +986,6 @@ class Engine(object):
                         0.9, 0.999, 1e-8, self.adam_t, self.scalars, 1.0)
             self.refresh_shadows(plain_done=fused)
             self.global_step += 1
-        self._last_clips = b
         return self.read_step_scalars(lr)
 
     def read_step_scalars(self, lr):

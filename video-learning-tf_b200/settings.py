@@ -135,7 +135,7 @@ class Settings(object):
         self.run_id = "_".join([self.run_id if self.run_id else os.path.basename(init_file), tag])
         if not os.path.exists(self.run_folder):
             warning("Non existent run folder %s - creating." % self.run_folder)
-            os.makedirs(self.run_folder)
+            os.makedirs(self.run_folder, exist_ok=True)  # (several data-parallel ranks may get here at once)
 
         log = config.get("logging", {}) or {}
         self.save_freq_per_epoch = log.get("save_freq_per_epoch", 1)
@@ -200,38 +200,17 @@ class Settings(object):
             self.data.append(o)
 
     # ------------------------------------------------------------------------------------------------
-    def engine_config(self, fpc):
+    def engine_config(self, fpc, image_shape=None):
         """Validity rules of Model.build_pipeline (models/model.py:18-155) for the pipelines the hot path covers,
-        and the EngineConfig they map to."""
+        and the EngineConfig they map to.  image_shape: the dataset's (h, w, 3) network input (model.py:54 takes it
+        from the dataset as well)."""
         if len(self.pipeline_names) != 1:
             error("Only single-pipeline models (the LRCN / single-frame hot path) are built; multi-input fusion "
                   "pipelines are outside the hot path (SURVEY 8f #4)")
         net = self.pipelines[self.pipeline_names[0]]
-        if net.representation != defs.representation.dcnn:
-            error("Only the dcnn representation is built for the hot path (got %s)" % net.representation)
-        if net.weights_file is not None and not os.path.exists(net.weights_file):
-            error("Weights file %s does not exist" % net.weights_file)
         opt = self.train.optimizer if self.train else defs.optim.sgd
         clip = self.train.clip_norm if self.train else None
-        common = dict(num_classes=self.num_classes, fpc=fpc, optimizer=opt, clip_norm=clip,
-                      dropout_keep_prob=self.get_dropout())
-        if net.classifier == defs.classifier.lstm:
-            if fpc <= 1:
-                error("LSTM classifier requires more than one frame per clip")  # model.py:121
-            if net.frame_fusion is not None and net.frame_fusion[0] != defs.fusion_type.none:
-                error("LSTM classifier requires frame fusion type none")  # model.py:125
-            hidden, layers, fusion = net.lstm_params
-            if fusion == defs.fusion_method.state:
-                error("lstm fusion `state` is not built for the hot path")
-            return EngineConfig(workflow="lrcn", frame_encoding_layer=net.frame_encoding_layer, lstm_hidden=hidden,
-                                lstm_layers=layers, fusion=fusion, **common)
-        # single-frame: fc8 logits per frame, classifier fc is the identity when dims agree, late fusion over fpc
-        if net.frame_encoding_layer in ("fc6", "fc7"):
-            error("frame_encoding_layer %s needs a classifier; use an fc8 encoding for single-frame runs" %
-                  net.frame_encoding_layer)
-        if net.frame_fusion is None or net.frame_fusion[0] != defs.fusion_type.late:
-            error("Single-frame pipelines need frame_fusion [late, avg|last] (labels are per clip, dataset_.py:400-408)")
-        return EngineConfig(workflow="singleframe", fusion=net.frame_fusion[1], **common)
+        return pipeline_engine_config(net, self.num_classes, fpc, opt, clip, self.get_dropout(), image_shape)
 
     def initialize(self, init_file):
         if init_file.endswith(".ini"):
@@ -245,3 +224,48 @@ class Settings(object):
         from .feeder import Feeder
         feeder = Feeder(self)
         return feeder
+
+
+def pipeline_engine_config(net, num_classes, fpc, optimizer, clip_norm, dropout_keep_prob, image_shape=None):
+    """One pipeline description (this package's Network or the reference's settings_.Network: same fields) -> the
+    EngineConfig of the device path, under the validity rules of Model.build_pipeline (models/model.py:18-155)."""
+    if len(net.input) != 1 or net.input_fusion is not None:
+        error("Multi-input pipelines (input_fusion %s) are outside the hot path (SURVEY 8f #4)" % str(net.input_fusion))
+    if net.representation != defs.representation.dcnn:
+        error("Only the dcnn representation is built for the hot path (got %s)" % net.representation)
+    if net.weights_file is not None and not os.path.exists(net.weights_file):
+        error("Weights file %s does not exist" % net.weights_file)
+    common = dict(num_classes=num_classes, fpc=fpc, optimizer=optimizer, clip_norm=clip_norm,
+                  dropout_keep_prob=dropout_keep_prob)
+    if image_shape is not None:
+        if len(image_shape) != 3 or int(image_shape[2]) != 3:
+            error("image_shape %s: the dcnn input is [h, w, 3] (model.py:54)" % str(tuple(image_shape)))
+        if min(int(image_shape[0]), int(image_shape[1])) < 67:
+            error("image_shape %s is too small for the AlexNet encoder (pool5 would be empty)" % str(tuple(image_shape)))
+        common.update(height=int(image_shape[0]), width=int(image_shape[1]))
+    fusion_type, fusion_method = net.frame_fusion if net.frame_fusion else (None, None)
+    if net.classifier is None and fusion_type == defs.fusion_type.late:
+        error("Specified late fusion with no classifier selected")  # model.py:37-38
+    if net.classifier == defs.classifier.lstm:
+        if fpc <= 1:
+            error("The LSTM classifier requires an fpc greater than 1")  # model.py:121
+        if fusion_type is not None and fusion_type != defs.fusion_type.none:
+            error("The LSTM classifier should be used only with [%s] fusion, but it's [%s]" % (
+                defs.fusion_type.none, fusion_type))  # model.py:125
+        hidden, layers, fusion = net.lstm_params[:3]
+        return EngineConfig(workflow="lrcn", frame_encoding_layer=net.frame_encoding_layer, lstm_hidden=hidden,
+                            lstm_layers=layers, fusion=fusion, **common)
+    if net.classifier != defs.classifier.fc:
+        error("A classifier (fc or lstm) is required: feature-only pipelines feed other pipelines (SURVEY 8f #4)")
+    # classifier fc (model.py:103-117,149-151): optional EARLY fusion of the frame features, convert_dim_fc to the class
+    # count when the widths differ, optional LATE fusion of the logits
+    early = fusion_method if (fusion_type == defs.fusion_type.early and fpc > 1) else None
+    late = fusion_method if (fusion_type == defs.fusion_type.late and fpc > 1) else None
+    if early is None and late is None and fpc > 1:
+        error("A pipeline with an fc classifier and fpc %d needs frame_fusion [early|late, avg|last]: labels are per "
+              "clip (dataset_.py:400-408)" % fpc)
+    layer = net.frame_encoding_layer if net.frame_encoding_layer in ("fc6", "fc7") else "fc8"
+    if layer == "fc8" and early is None:
+        return EngineConfig(workflow="singleframe", fusion=late or defs.fusion_method.avg, **common)
+    return EngineConfig(workflow="fc", frame_encoding_layer=layer, fusion=late or early, early_fusion=early is not None,
+                        **common)

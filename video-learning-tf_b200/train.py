@@ -82,6 +82,6 @@ class Train(object):
             error("global step %d exceeds the learning rate table (%d)" % (step, len(self.learning_rates)))
         return float(self.learning_rates[step])
 
-    def step(self, frames, onehot, crops=None):
+    def step(self, frames, onehot, crops=None, global_clips=None):
         """(loss, lr, global_step, accuracyTrain, grads_norm) -- the fetches of run_task.py:29,44."""
-        return self.engine.train_step(frames, onehot, self.current_lr(), crops=crops)
+        return self.engine.train_step(frames, onehot, self.current_lr(), crops=crops, global_clips=global_clips)
