@@ -179,3 +179,57 @@ def test_raw_resize_on_the_device_equals_pil_then_crop(tmp_path):
     from vlb200 import checkpoint
     names = checkpoint.read_index(str(tmp_path / "run" / "checkpoints"))
     assert names and names[-1].endswith("gs_2.graph-2")
+
+
+def test_tfshim_session_drives_the_real_engine(tmp_path):
+    """The reference-facing seam (tfshim.Session / compat.Model / compat.Train / tf.train.Saver) over the CUDA engine:
+    `sess.run([summaries, loss, lr, global_step, optimizer], feed_dict)` and `sess.run(model.logits, feed_dict)` give
+    what direct Engine calls give on the same inputs, and a Saver round trip restores the variables bit for bit.
+    (tests/test_reference_dropin.py runs the reference's own run_task.main through the same objects.)"""
+    import vlb200  # noqa: F401
+    from vlb200 import compat, tfshim
+    from vlb200 import engine as E
+    fpc, clips, classes = 2, 3, 11
+    ds = types.SimpleNamespace(num_frames_per_clip=fpc, clips_per_video=[1] * 6, num_items=6,
+                               get_image_shape=lambda: (227, 227, 3))
+    pipe = types.SimpleNamespace(input=["main"], input_shape=[None], input_fusion=None, representation="dcnn",
+                                 frame_encoding_layer="fc7", classifier="lstm", lstm_params=[64, 1, "avg"],
+                                 frame_fusion=None, weights_file=None, fc_output_dim=None)
+    tr = types.SimpleNamespace(optimizer="sgd", clip_norm=10, lr_mult=None, base_lr=0.01,
+                               lr_decay=["exp", "interval", 1, 0.5], epochs=2, dropout_keep_prob=0.0)
+    settings = types.SimpleNamespace(
+        pipeline_names=["lrcn"], pipelines={"lrcn": pipe}, num_classes=classes, train=tr, val=None, global_step=0,
+        run_folder=str(tmp_path), run_id="shim", get_dropout=lambda: 0.0, get_batch_size=lambda: clips,
+        feeder=types.SimpleNamespace(get_dataset_by_tag=lambda tag: [ds], get_num_batches=lambda: 2))
+    model = compat.Model(settings)
+    summaries = types.SimpleNamespace(train=[], val=[])
+    train = compat.Train(settings, settings.feeder, model.get_output(), summaries)
+    sess = tfshim.Session()
+    sess.run(tfshim.global_variables_initializer())
+    rng = np.random.default_rng(3)
+    frames = [rng.uniform(-1, 1, size=(227, 227, 3)).astype(np.float32) for _ in range(clips * fpc)]  # feeder.py:97-100
+    onehot = np.zeros((clips, classes), np.int32)
+    onehot[np.arange(clips), [1, 4, 7]] = 1
+    fdict = {model.required_input[0][0]: frames, train.required_input[0][0]: list(onehot)}
+    logits0 = sess.run(model.logits, feed_dict=fdict)
+    # the same engine configuration built directly
+    ref = E.Engine(model.cfg, max_clips=clips, params=E.init_variables(model.cfg))
+    assert np.array_equal(logits0, ref.forward(np.stack(frames)))
+    merged = tfshim.summary.merge(summaries.train)
+    for step in range(2):
+        _, loss, lr, gstep, _ = sess.run([merged, train.loss, train.current_lr, train.global_step, train.optimizer],
+                                         feed_dict=fdict)
+        rloss, rlr, rstep, _, _ = ref.train_step(np.stack(frames), onehot, [0.01, 0.005][step])
+        assert gstep == rstep == step + 1 and abs(lr - rlr) < 1e-9 and abs(loss - rloss) < 1e-6 * max(1.0, abs(rloss))
+    assert sess.run(train.global_step) == 2
+    saver = tfshim.train.Saver(max_to_keep=3)
+    prefix = saver.save(sess, str(tmp_path / "checkpoints" / "x.graph"), global_step=2)
+    assert prefix.endswith("x.graph-2") and all(os.path.exists(prefix + e) for e in (".npz", ".meta", ".index"))
+    names = tfshim._checkpoint_tensor_names(prefix)
+    assert {v.name[:-2] for v in tfshim.global_variables()} <= set(names)  # the name diff of feeder.py:229-249 is empty
+    before = sess.engine.state_dict()
+    sess.run([train.loss, train.optimizer], feed_dict=dict(fdict))  # a third step moves the variables
+    assert not np.array_equal(before["output_fc_w"], sess.engine.state_dict()["output_fc_w"])
+    saver.restore(sess, prefix)
+    after = sess.engine.state_dict()
+    assert all(np.array_equal(before[k], after[k]) for k in before)

@@ -48,9 +48,12 @@ class Dataset(object):
             self.tfr_path = base + ".tfrecord"
             if not os.path.exists(self.tfr_path):
                 error("TFRecord file path does not exist: %s" % self.tfr_path)
-            if not os.path.exists(base + ".size"):
-                error("Could not file data size file: %s" % (base + ".size"))
-            meta = tfrecord.read_size_file(base + ".size")
+            # serialize.py:138-151,664: the side file of `<inp>.tfrecord` is `<inp>.tfrecord.size` (dataset_.py:703 reads
+            # `self.path + ".size"` after appending ".tfrecord"); `<inp>.size` is accepted as well
+            size_file = self.tfr_path + ".size" if os.path.exists(self.tfr_path + ".size") else base + ".size"
+            if not os.path.exists(size_file):
+                error("Could not file data size file: %s" % (self.tfr_path + ".size"))
+            meta = tfrecord.read_size_file(size_file)
             if meta["type"] != defs.input_mode.video:
                 error("Specified input mode is [%s] but the size file contains [%s]" % (defs.input_mode.video, meta["type"]))
             self.num_items = meta["items"]
