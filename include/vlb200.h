@@ -139,14 +139,6 @@ int vl_pack_dgrad_d2s(const float* src, void* dst, int32_t kh, int32_t kw, int32
  * Memory-bound kernels of the AlexNet encoder (HBM roofline).
  * ---------------------------------------------------------------------------------------------- */
 
-/* Input staging for conv1 (alexnet.py:76): frames [n][h][w][3] (uint8 with the per-channel mean subtracted
- * here -- dataset_.py:521-530 -- when `is_u8`, else fp32 already mean-subtracted as fed by feeder.py:97-100)
- * -> bf16 patch matrix col[n*p*q][k_ld], column (r*kw+s)*3+c, zero filled up to k_ld and outside the image
- * (TF SAME padding). */
-int vl_conv1_patches(const void* frames, int is_u8, const float* mean3, void* col, int32_t n, int32_t h,
-                     int32_t w, int32_t kh, int32_t kw, int32_t stride, int32_t pad_top, int32_t pad_left,
-                     int32_t p, int32_t q, int32_t k_ld, vl_stream_t stream);
-
 /* Space-to-depth staging of the conv1 input (alexnet.py:60-77, dataset_.py:521-530): frames [n][h][w][3] (uint8,
  * mean subtracted here, or fp32 as fed by feeder.py:97-100) -> bf16 out[n][hb][wb][s*s*3] with
  * out[n][by][bx][(dy*s+dx)*3+c] = frame[n][s*by-pad_top+dy][s*bx-pad_left+dx][c] (0 outside the image), so that the

@@ -74,7 +74,7 @@ def config(work, phase, shape, classes):
         "network": {"num_classes": classes, "pipelines": [{"lrcn": {
             "input": "defs.dataset_tag.main", "representation": "defs.representation.dcnn", "frame_encoding_layer": "fc7",
             "classifier": "defs.classifier.lstm", "lstm_params": [64, 1, "defs.fusion_method.avg"]}}]},
-        "train": {"batch_size": 2, "epochs": 2 if phase == "train" else 3, "optimizer": "defs.optim.sgd", "base_lr": 0.001,
+        "train": {"batch_size": 2, "epochs": 1 if phase == "train" else 3, "optimizer": "defs.optim.sgd", "base_lr": 0.001,
                   "lr_mult": "None", "lr_decay": ["defs.decay.exp", "defs.periodicity.interval", 2, 0.5], "clip_norm": 10,
                   "dropout_keep_prob": 0.5},
         "val": {"batch_size": 2, "logits_save_interval": 0, "clip_fusion": ["defs.fusion_type.late", "defs.fusion_method.avg"]},

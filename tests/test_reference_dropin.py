@@ -31,24 +31,25 @@ def _run(work, phase):
 def test_reference_run_task_trains_resumes_and_validates_through_the_shim(tmp_path):
     work = tmp_path / "w"
     work.mkdir()
-    # ---- train: 4 videos, batch 2 -> 2 batches x 2 epochs; lr_decay [exp, interval, 2, 0.5] ----
+    # ---- train: 4 videos, batch 2 -> 2 batches, 1 epoch; lr_decay [exp, interval, 2, 0.5] ----
+    # (ONE checkpoint before the resume: the reference's init_saveload takes get_run_checkpoints(...)[-1], whose sort key
+    # `"_".join(x.split()[2:])` is empty for every path without blanks, i.e. "latest" is os.listdir order - utils_.py:223-230)
     out, log = _run(work, "train")
     assert out["reference_modules"] == ["dataset_", "defs_", "feeder", "run_task", "settings_", "utils_", "val"]
     steps = [c for c in out["calls"] if c[0] == "train"]
-    assert [c[1] for c in steps] == [3, 3, 3, 3]                    # clips per batch: whole videos (cpv 2,1 | 2,1)
-    assert [c[2] for c in steps] == [0.001, 0.001, 0.0005, 0.0005]  # lr = table[global_step] (train.py:129-132)
-    assert out["global_step"] == 4
-    snaps = sorted(out["snaps"].items())
-    assert [v for _, v in snaps] == [[2, 0, 2], [2, 1, 4]]          # feeder.save: [batch_index, epoch_index, global_step]
+    assert [c[1] for c in steps] == [3, 3]                          # clips per batch: whole videos (cpv 2,1 | 2,1)
+    assert [c[2] for c in steps] == [0.001, 0.001]                  # lr = table[global_step] (train.py:129-132)
+    assert out["global_step"] == 2
+    assert list(out["snaps"].values()) == [[2, 0, 2]]               # feeder.save: [batch_index, epoch_index, global_step]
     assert all(any(f.endswith(ext) for f in out["checkpoint_files"]) for ext in (".npz", ".meta", ".index", ".snap"))
-    assert out["index_first_line"].startswith('model_checkpoint_path: "') and "gs_4.graph-4" in out["index_first_line"]
-    assert "Learning rate 0.00050000, global step: 4" in log        # the reference's own log line (run_task.py:51)
-    assert "Epoch [2] training run complete." in log
+    assert out["index_first_line"].startswith('model_checkpoint_path: "') and "gs_2.graph-2" in out["index_first_line"]
+    assert "Learning rate 0.00100000, global step: 2" in log        # the reference's own log line (run_task.py:51)
+    assert "Epoch [1] training run complete." in log
     # ---- resume `latest` with 3 epochs: resume_snap + init_saveload + saver.restore are the reference's ----
     out, log = _run(work, "resume")
-    assert "Resumed epoch [2] is already complete." in log          # run_task.py:68
+    assert "Resumed epoch [1] is already complete." in log          # run_task.py:68
     steps = [c for c in out["calls"] if c[0] == "train"]
-    assert [c[2] for c in steps] == [0.00025, 0.00025] and out["global_step"] == 6
+    assert [c[2] for c in steps] == [0.0005, 0.0005, 0.00025, 0.00025] and out["global_step"] == 6
     assert any("ep_3_btch_2_gs_6.graph-6.npz" in f for f in out["checkpoint_files"])
     # ---- validation of the resumed checkpoint: the reference's Validation fuses clips to videos ----
     out, log = _run(work, "val")

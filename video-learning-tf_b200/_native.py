@@ -71,7 +71,6 @@ def _declare(L):
         "vl_conv_flat": [ctypes.POINTER(ConvFlatDesc), vp, vp, vp, vp, vp],
         "vl_pack_dgrad_kmajor": [vp, vp, i32, i32, i32, i32, vp],
         "vl_pack_dgrad_d2s": [vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],
-        "vl_conv1_patches": [vp, i32, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp],
         "vl_lrn_fwd": [vp, vp, i64, i32, i32, f32, f32, f32, vp],
         "vl_lrn_bwd": [vp, vp, vp, i64, i32, i32, f32, f32, f32, i32, vp],
         "vl_maxpool_fwd": [vp, vp, vp, i32, i32, i32, i32, vp],
@@ -114,7 +113,7 @@ def _declare(L):
         fn.argtypes = argtypes
 
 
-EXPORTS = ["vl_last_error", "vl_version", "vl_device_sm_count", "vl_launch_count", "vl_zero", "vl_gemm", "vl_conv_flat", "vl_pack_dgrad_kmajor", "vl_pack_dgrad_d2s", "vl_conv1_patches",
+EXPORTS = ["vl_last_error", "vl_version", "vl_device_sm_count", "vl_launch_count", "vl_zero", "vl_gemm", "vl_conv_flat", "vl_pack_dgrad_kmajor", "vl_pack_dgrad_d2s",
            "vl_lrn_fwd", "vl_lrn_bwd", "vl_maxpool_fwd", "vl_maxpool_bwd", "vl_colsum", "vl_pack_bf16",
            "vl_cast_f32_to_bf16", "vl_transpose_f32", "vl_gather_bf16", "vl_lstm_fwd", "vl_lstm_bwd", "vl_lrn_pool_fwd", "vl_pool_lrn_bwd",
            "vl_lstm_fwd_cluster", "vl_lstm_bwd_cluster", "vl_frames_s2d", "vl_frames_s2d_crop", "vl_pack_bf16_t", "vl_s2d_pack_filter", "vl_s2d_unpack_grad",

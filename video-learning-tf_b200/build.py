@@ -24,8 +24,15 @@ NVCC_FLAGS = [
 ]
 
 
+# development probes (TMA feed / mbarrier / shifted-descriptor micro-benchmarks behind tests/bringup/*_bench.py):
+# built only with VL_BUILD_PROBES=1, never part of the product library
+PROBE_SOURCES = ("dev_probes.cu",)
+
+
 def _sources():
-    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
+    probes = os.environ.get("VL_BUILD_PROBES", "0") == "1"
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC)
+                  if f.endswith(".cu") and (probes or f not in PROBE_SOURCES))
 
 
 def _digest():
@@ -36,7 +43,7 @@ def _digest():
         h.update(f.encode())
         with open(f, "rb") as fh:
             h.update(fh.read())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update((" ".join(NVCC_FLAGS) + os.environ.get("VL_BUILD_PROBES", "0")).encode())
     return h.hexdigest()
 
 

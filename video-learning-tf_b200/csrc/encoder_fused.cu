@@ -206,102 +206,11 @@ __global__ void __launch_bounds__(256)
 
 // ------------------------------------------------------------------------------------------------
 // Fast path of the staging for uint8 frames without crop / mirror and a block-aligned left padding (the bench and
-// config-2 feed): with pad_left % 4 == 0 the 12 source bytes of the 4 pixels of a (block column, dy) pair are
-// CONTIGUOUS in the frame row and land on 12 CONTIGUOUS bf16 of the output row, so one thread moves 12 bytes -> 24
-// bytes: four aligned 32-bit loads + funnel shifts (the frame rows are 681 bytes, i.e. unaligned), the exact
-// uint8 -> fp32 conversion through the 2^23 mantissa trick (no I2F), mean subtraction, three 8-byte shared-memory
-// stores; the finished rows leave with 16-byte stores as before.  Two block rows per CTA.
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-    frames_s2d_fast_kernel(const uint8_t* __restrict__ frames, const float* __restrict__ mean3, bf16* __restrict__ out,
-                           int h, int w, int pad_top, int pad_left, int hb, int wb, long long total_bytes, int n_units) {
-  constexpr int S = 4, SEG = 12, CBLK = 48, ROWS = 2;
-  extern __shared__ __align__(16) uint8_t smem_raw[];
-  bf16* orow_s = reinterpret_cast<bf16*>(smem_raw);  // [ROWS][wb][48]
-  const int pairs = (hb + ROWS - 1) / ROWS;
-  float m[3] = {0.f, 0.f, 0.f};
-  if (mean3 != nullptr) {
-    m[0] = mean3[0];
-    m[1] = mean3[1];
-    m[2] = mean3[2];
-  }
-  const int row_bytes = w * 3;
-  // persistent CTAs walk the (frame, block-row pair) units: 60 k one-shot CTAs of ~470 items each were bound by their
-  // launch / drain overhead, not by the 500 MB they move
-  // thread -> (block column bx = tid & 63, image row dy = tid >> 6 of the block row): no index divisions; 59 of 64
-  // lanes carry data for wb = 59
-  const int bx = threadIdx.x & 63, dy = threadIdx.x >> 6;
-  const int xb = bx * SEG - pad_left * 3;  // first source byte of the segment inside the frame row
-  const bool seg_any = bx < wb && xb + SEG > 0 && xb < row_bytes;
-  const bool seg_full = xb >= 0 && xb + SEG <= row_bytes;  // no padding byte inside the segment (all but the edges)
-  const uintptr_t lo = reinterpret_cast<uintptr_t>(frames), hi = lo + (uintptr_t)total_bytes;
-  for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
-    const int nn = unit / pairs;
-    const int by0 = (unit - nn * pairs) * ROWS;
-    const int nrows = min(ROWS, hb - by0);
-    const long long frame_off = (long long)nn * h * w * 3;
-    if (bx < wb) {
-#pragma unroll
-      for (int br = 0; br < ROWS; ++br) {
-        if (br >= nrows) break;
-        const int y = (by0 + br) * S - pad_top + dy;
-        uint32_t o[6] = {0u, 0u, 0u, 0u, 0u, 0u};
-        if (seg_any && y >= 0 && y < h) {
-          // absolute addresses: the frames pointer itself may be unaligned (a slice of a batch)
-          const uintptr_t a = lo + (uintptr_t)(frame_off + (long long)y * row_bytes + xb);  // may precede lo (xb < 0)
-          const uintptr_t a4 = a & ~(uintptr_t)3;
-          uint32_t wd[4];
-          if (a4 >= lo && a4 + 16 <= hi) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) wd[k] = __ldg(reinterpret_cast<const uint32_t*>(a4) + k);
-          } else {  // first / last bytes of the whole tensor
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              wd[k] = 0u;
-              for (int j = 0; j < 4; ++j) {
-                const uintptr_t pb = a4 + 4 * k + j;
-                if (pb >= lo && pb < hi) wd[k] |= (uint32_t)__ldg(reinterpret_cast<const uint8_t*>(pb)) << (8 * j);
-              }
-            }
-          }
-          const uint32_t sh = (uint32_t)(a - a4) * 8u;
-          const uint32_t b3[3] = {__funnelshift_r(wd[0], wd[1], sh), __funnelshift_r(wd[1], wd[2], sh),
-                                  __funnelshift_r(wd[2], wd[3], sh)};
-          float v[12];
-#pragma unroll
-          for (int e = 0; e < 12; ++e) {
-            // 0x4B0000bb = 2^23 + b exactly; channel of element e is e % 3 (segments start on a pixel boundary)
-            const uint32_t bits = __byte_perm(b3[e >> 2], 0x4B000000u, 0x7440u | (uint32_t)(e & 3));
-            v[e] = (__uint_as_float(bits) - 8388608.0f) - m[e % 3];
-          }
-          if (!seg_full) {  // bytes left of the frame row (xb < 0) or beyond it are padding
-#pragma unroll
-            for (int e = 0; e < 12; ++e)
-              if (xb + e < 0 || xb + e >= row_bytes) v[e] = 0.f;
-          }
-#pragma unroll
-          for (int i = 0; i < 6; ++i) {
-            const __nv_bfloat162 pk = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-            o[i] = *reinterpret_cast<const uint32_t*>(&pk);
-          }
-        }
-        uint2* dst = reinterpret_cast<uint2*>(orow_s + (br * wb + bx) * CBLK + dy * SEG);
-        dst[0] = make_uint2(o[0], o[1]);
-        dst[1] = make_uint2(o[2], o[3]);
-        dst[2] = make_uint2(o[4], o[5]);
-      }
-    }
-    __syncthreads();
-    uint4* dstg = reinterpret_cast<uint4*>(out + ((long long)nn * hb + by0) * wb * CBLK);
-    const int nvec = nrows * wb * CBLK / 8;
-    for (int i = threadIdx.x; i < nvec; i += blockDim.x) dstg[i] = reinterpret_cast<const uint4*>(orow_s)[i];
-  __syncthreads();  // the stage is rewritten by the next unit
-  }
-}
-
-// Register-only form of the fast staging: a thread owns one output block (frame, by, bx) = 4 image rows x 12 source
-// bytes -> 48 contiguous bf16 (96 bytes); no shared memory and no barriers (the staged form spent its time waiting on
-// two __syncthreads per 11 KB of output).  Loads of a warp walk 32 x 12 contiguous bytes of each of the four rows,
+// config-2 feed): with pad_left % 4 == 0 the 12 source bytes of the 4 pixels of a (block column, dy) pair are CONTIGUOUS
+// in the frame row and land on 12 CONTIGUOUS bf16 of the output row.  A thread owns one output block (frame, by, bx) =
+// 4 image rows x 12 source bytes -> 48 contiguous bf16 (96 bytes): four aligned 32-bit loads + funnel shifts per row
+// (the frame rows are 681 bytes, i.e. unaligned), exact uint8 -> fp32 through the 2^23 mantissa trick, no shared
+// memory and no barriers.  Loads of a warp walk 32 x 12 contiguous bytes of each of the four rows,
 // stores cover 32 x 96 contiguous bytes.
 __global__ void __launch_bounds__(128)
     frames_s2d_direct_kernel(const uint8_t* __restrict__ frames, const float* __restrict__ mean3, bf16* __restrict__ out,
@@ -1046,25 +955,13 @@ extern "C" int vl_frames_s2d_crop(const void* frames, int32_t is_u8, const float
   VL_REQUIRE(crops != nullptr || (hr == h && wr == w), "vl_frames_s2d: crop offsets are required when the stored frame is larger");
   const size_t smem = (size_t)wb * s * s * 3 * sizeof(bf16);
   VL_REQUIRE(smem <= 48 * 1024, "vl_frames_s2d: image row too wide (%zu bytes of shared memory)", smem);
-  if (is_u8 && crops == nullptr && pad_left % 4 == 0 && pad_top >= 0 && !getenv("VL_S2D_SLOW")) {
-    if (wb <= 64 && !(getenv("VL_S2D_MODE") && atoi(getenv("VL_S2D_MODE")) == 1)) {
-      const int n_rows = n * hb;
-      const int per_sm_d = getenv("VL_S2D_CTAS") ? atoi(getenv("VL_S2D_CTAS")) : 16;
-      const int want = (n_rows + 1) / 2;
-      const int grid_d = want < vl::num_sms() * per_sm_d ? want : vl::num_sms() * per_sm_d;
-      frames_s2d_direct_kernel<<<grid_d, 128, 0, stream>>>(reinterpret_cast<const uint8_t*>(frames), mean3,
-                                                          reinterpret_cast<bf16*>(out), h, w, pad_top, pad_left, hb, wb,
-                                                          (long long)n * h * w * 3, n_rows);
-      VL_LAUNCHED();
-      return 0;
-    }
-    const int pairs = (hb + 1) / 2;
-    const int n_units = n * pairs;
-    const int per_sm = getenv("VL_S2D_CTAS") ? atoi(getenv("VL_S2D_CTAS")) : 8;
-    const int grid_fast = n_units < vl::num_sms() * per_sm ? n_units : vl::num_sms() * per_sm;
-    frames_s2d_fast_kernel<<<grid_fast, 256, 2 * smem, stream>>>(reinterpret_cast<const uint8_t*>(frames), mean3,
-                                                                 reinterpret_cast<bf16*>(out), h, w, pad_top, pad_left,
-                                                                 hb, wb, (long long)n * h * w * 3, n_units);
+  if (is_u8 && crops == nullptr && pad_left % 4 == 0 && pad_top >= 0 && wb <= 64) {
+    const int n_rows = n * hb;
+    const int want = (n_rows + 1) / 2;
+    const int grid_d = want < vl::num_sms() * 16 ? want : vl::num_sms() * 16;
+    frames_s2d_direct_kernel<<<grid_d, 128, 0, stream>>>(reinterpret_cast<const uint8_t*>(frames), mean3,
+                                                        reinterpret_cast<bf16*>(out), h, w, pad_top, pad_left, hb, wb,
+                                                        (long long)n * h * w * 3, n_rows);
     VL_LAUNCHED();
     return 0;
   }
@@ -1132,9 +1029,8 @@ extern "C" int vl_lrn_pool_fwd(const void* x, void* y, void* argmax, int32_t n, 
   if (!getenv("VL_LRN_FWD_V2") && ((c == 96 && h == 57 && w == 57) || (c == 256 && h == 28 && w == 28))) {
     const int ring_bytes = 5 * (int)row_bytes;
     const int per_sm_smem = (227 * 1024) / (ring_bytes + 1024);
-    // 80 registers x 256 threads: three CTAs per SM; VL_LRN_FWD_CTAS=4 selects the 64-register build of the 96-channel
-    // instance (four CTAs per SM, a few spills)
-    const int want_mb = (c == 96 && getenv("VL_LRN_FWD_CTAS") && atoi(getenv("VL_LRN_FWD_CTAS")) == 4) ? 4 : 3;
+    // 80 registers x 256 threads: three CTAs per SM
+    const int want_mb = 3;
     const int per_sm = per_sm_smem < want_mb ? per_sm_smem : want_mb;
     const long long resident = (long long)vl::num_sms() * per_sm;
     // segments per frame: balance the waves against the one re-normalised row per extra segment
@@ -1148,10 +1044,9 @@ extern "C" int vl_lrn_pool_fwd(const void* x, void* y, void* argmax, int32_t n, 
       const double eff = (double)units / (double)(waves * resident) * (2.0 * p + 1) / (2.0 * p + real);
       if (eff > best_eff + 1e-9) best_eff = eff, best_segs = real;
     }
-    // VL_LRN_FWD_OVERLAP=1: pool row p-1 inside the barrier interval of row p.  Measured on one box: 360 us against
-    // 329 us (96 channels), 222 against 223 us (256 channels) - the kernel is bound by the MUFU / MIO queue and the
-    // issue slots, not by the phase separation; off by default.
-    const int overlap_mode = getenv("VL_LRN_FWD_OVERLAP") ? atoi(getenv("VL_LRN_FWD_OVERLAP")) : 0;
+    // (pooling row p-1 inside the barrier interval of row p was measured slower: 360 against 329 us for 96 channels -
+    // the kernel is bound by the MUFU / MIO queue and the issue slots, not by the phase separation)
+    const int overlap_mode = 0;
     const int seg_rows = (p + best_segs - 1) / best_segs;
     const long long units = (long long)n * best_segs;
     const int g = (int)(units < resident ? units : resident);
@@ -1167,9 +1062,7 @@ extern "C" int vl_lrn_pool_fwd(const void* x, void* y, void* argmax, int32_t n, 
         reinterpret_cast<const bf16*>(x), reinterpret_cast<bf16*>(y), reinterpret_cast<uint8_t*>(argmax), n, seg_rows, \
         best_segs, alpha, bias, overlap_mode);                                                                        \
   } while (0)
-    if (c == 96 && want_mb == 4)
-      VL_FWD3_LAUNCH(24, 4, 96, 57, 57, 256, 4);
-    else if (c == 96)
+    if (c == 96)
       VL_FWD3_LAUNCH(24, 4, 96, 57, 57, 256, 3);
     else
       VL_FWD3_LAUNCH(16, 16, 256, 28, 28, 256, 3);
@@ -1227,48 +1120,25 @@ extern "C" int vl_pool_lrn_bwd(const void* x, const void* dy, const void* argmax
       reinterpret_cast<bf16*>(dx), dbias, n, h, w, c, alpha, beta, bias
   (void)p;
   (void)q;
-  // fourth generation (2x2 pixel blocks, uniform control flow): the two AlexNet geometries, beta = 0.75
-  const int v4 = getenv("VL_LRN_BWD_V4") ? atoi(getenv("VL_LRN_BWD_V4")) : 2;
-  const long long gmul = getenv("VL_LRN_BWD_GRID") ? atoi(getenv("VL_LRN_BWD_GRID")) : 4;  // CTAs per SM in the grid
-  if (v4 && beta == 0.75f && c == 96 && h == 57 && w == 57) {
+  // fourth generation (2x2 pixel blocks, uniform control flow): the two AlexNet geometries, beta = 0.75.  Four CTAs
+  // per SM in the grid; 96 channels: 256 threads, two CTAs resident; 256 channels: 448 threads at 72 registers, two
+  // CTAs resident (243 us against 293 us with one CTA of 128 registers)
+  const long long gmul = 4;
+  if (beta == 0.75f && c == 96 && h == 57 && w == 57) {
     const long long units = (long long)n * 29;
-    if (v4 == 3) {  // 80 registers (a few spills), three CTAs per SM
-      const long long g = units < (long long)vl::num_sms() * 6 ? units : (long long)vl::num_sms() * 6;
-      pool_lrn_bwd_kernel4<12, 8, 96, 57, 57, 256, 3><<<(int)g, 256, 0, stream>>>(
-          reinterpret_cast<const bf16*>(x), reinterpret_cast<const bf16*>(dy), reinterpret_cast<const uint8_t*>(argmax),
-          reinterpret_cast<bf16*>(dx), dbias, n, alpha, bias);
-    } else if (v4 == 2) {
-      const long long g = units < (long long)vl::num_sms() * gmul ? units : (long long)vl::num_sms() * gmul;
-      pool_lrn_bwd_kernel4<12, 8, 96, 57, 57, 256, 2><<<(int)g, 256, 0, stream>>>(
-          reinterpret_cast<const bf16*>(x), reinterpret_cast<const bf16*>(dy), reinterpret_cast<const uint8_t*>(argmax),
-          reinterpret_cast<bf16*>(dx), dbias, n, alpha, bias);
-    } else {
-      const long long g = units < (long long)vl::num_sms() * 8 ? units : (long long)vl::num_sms() * 8;
-      pool_lrn_bwd_kernel4<24, 4, 96, 57, 57, 128, 4><<<(int)g, 128, 0, stream>>>(
-          reinterpret_cast<const bf16*>(x), reinterpret_cast<const bf16*>(dy), reinterpret_cast<const uint8_t*>(argmax),
-          reinterpret_cast<bf16*>(dx), dbias, n, alpha, bias);
-    }
+    const long long g = units < (long long)vl::num_sms() * gmul ? units : (long long)vl::num_sms() * gmul;
+    pool_lrn_bwd_kernel4<12, 8, 96, 57, 57, 256, 2><<<(int)g, 256, 0, stream>>>(
+        reinterpret_cast<const bf16*>(x), reinterpret_cast<const bf16*>(dy), reinterpret_cast<const uint8_t*>(argmax),
+        reinterpret_cast<bf16*>(dx), dbias, n, alpha, bias);
     VL_LAUNCHED();
     return 0;
   }
-  if (v4 && beta == 0.75f && c == 256 && h == 28 && w == 28) {
+  if (beta == 0.75f && c == 256 && h == 28 && w == 28) {
     const long long units = (long long)n * 14;
-    if (v4 >= 2) {  // 72 registers: two CTAs of 448 threads per SM (243 us against 293 us with one CTA, 128 registers)
-      const long long g = units < (long long)vl::num_sms() * gmul ? units : (long long)vl::num_sms() * gmul;
-      pool_lrn_bwd_kernel4<8, 32, 256, 28, 28, 448, 2><<<(int)g, 448, 0, stream>>>(
-          reinterpret_cast<const bf16*>(x), reinterpret_cast<const bf16*>(dy), reinterpret_cast<const uint8_t*>(argmax),
-          reinterpret_cast<bf16*>(dx), dbias, n, alpha, bias);
-    } else if (v4 == 4) {
-      const long long g = units < (long long)vl::num_sms() * gmul ? units : (long long)vl::num_sms() * gmul;
-      pool_lrn_bwd_kernel4<8, 32, 256, 28, 28, 448, 1><<<(int)g, 448, 0, stream>>>(
-          reinterpret_cast<const bf16*>(x), reinterpret_cast<const bf16*>(dy), reinterpret_cast<const uint8_t*>(argmax),
-          reinterpret_cast<bf16*>(dx), dbias, n, alpha, bias);
-    } else {
-      const long long g = units < (long long)vl::num_sms() * 6 ? units : (long long)vl::num_sms() * 6;
-      pool_lrn_bwd_kernel4<16, 16, 256, 28, 28, 224, 2><<<(int)g, 224, 0, stream>>>(
-          reinterpret_cast<const bf16*>(x), reinterpret_cast<const bf16*>(dy), reinterpret_cast<const uint8_t*>(argmax),
-          reinterpret_cast<bf16*>(dx), dbias, n, alpha, bias);
-    }
+    const long long g = units < (long long)vl::num_sms() * gmul ? units : (long long)vl::num_sms() * gmul;
+    pool_lrn_bwd_kernel4<8, 32, 256, 28, 28, 448, 2><<<(int)g, 448, 0, stream>>>(
+        reinterpret_cast<const bf16*>(x), reinterpret_cast<const bf16*>(dy), reinterpret_cast<const uint8_t*>(argmax),
+        reinterpret_cast<bf16*>(dx), dbias, n, alpha, bias);
     VL_LAUNCHED();
     return 0;
   }

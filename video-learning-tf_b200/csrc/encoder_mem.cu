@@ -56,74 +56,6 @@ __device__ __forceinline__ Bf16x8 pack8(const float (&f)[8]) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// conv1 patch matrix.  One CTA per (frame, output row): the kh input rows it needs are staged once in shared
-// memory as mean-subtracted bf16 with the SAME zero padding materialised, then every 16-byte chunk of the 57
-// patch rows is a gather of 8 shared-memory elements through a k -> (row, column) offset table.  Global reads
-// are row-contiguous, global writes are fully coalesced 16B vectors (the kernel is bound by the 2.5 GB it writes).
-// ------------------------------------------------------------------------------------------------
-template <bool U8>
-__global__ void __launch_bounds__(256)
-    conv1_patches_kernel(const void* __restrict__ frames_, const float* __restrict__ mean3, bf16* __restrict__ col,
-                         int h, int w, int kh, int kw, int stride, int pad_top, int pad_left, int p, int q, int k_ld,
-                         int pitch) {
-  extern __shared__ __align__(16) uint8_t smem_raw[];
-  bf16* rows = reinterpret_cast<bf16*>(smem_raw);                       // [kh][pitch]
-  uint16_t* koff = reinterpret_cast<uint16_t*>(rows + kh * pitch);     // [k_ld]
-  const int pp = blockIdx.x % p;
-  const int nn = blockIdx.x / p;
-  const int row_elems = kw * 3;
-  const int kvalid = kh * row_elems;
-  float m[3] = {0.f, 0.f, 0.f};
-  if (U8 && mean3 != nullptr) {
-    m[0] = mean3[0];
-    m[1] = mean3[1];
-    m[2] = mean3[2];
-  }
-  for (int k = threadIdx.x; k < k_ld; k += blockDim.x) {
-    int off = 0xFFFF;  // sentinel: zero column of the K padding
-    if (k < kvalid) {
-      const int r = k / row_elems;
-      off = r * pitch + (k - r * row_elems);
-    }
-    koff[k] = (uint16_t)off;
-  }
-  const int y0 = pp * stride - pad_top;
-  const int lead = pad_left * 3;
-  for (int idx = threadIdx.x; idx < kh * pitch; idx += blockDim.x) {
-    const int r = idx / pitch;
-    const int e = idx - r * pitch;
-    const int y = y0 + r;
-    const int xe = e - lead;  // element index inside the image row (x*3 + c)
-    float v = 0.f;
-    if (y >= 0 && y < h && xe >= 0 && xe < w * 3) {
-      const long long off = ((long long)nn * h + y) * (w * 3) + xe;
-      if (U8) {
-        const int c = xe % 3;
-        v = (float)reinterpret_cast<const uint8_t*>(frames_)[off] - m[c];
-      } else {
-        v = reinterpret_cast<const float*>(frames_)[off];
-      }
-    }
-    rows[idx] = __float2bfloat16_rn(v);
-  }
-  __syncthreads();
-  const int cpr = k_ld >> 3;
-  const long long row0 = ((long long)nn * p + pp) * q;
-  for (int idx = threadIdx.x; idx < q * cpr; idx += blockDim.x) {
-    const int qq = idx / cpr;
-    const int ch = idx - qq * cpr;
-    const int base = qq * stride * 3;
-    alignas(16) bf16 v[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int o = koff[ch * 8 + j];
-      v[j] = (o == 0xFFFF) ? __float2bfloat16_rn(0.f) : rows[o + base];
-    }
-    *reinterpret_cast<uint4*>(col + (row0 + qq) * k_ld + ch * 8) = *reinterpret_cast<const uint4*>(v);
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
 // LRN
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float pow_neg_beta(float s, float beta) {
@@ -779,29 +711,6 @@ int sweep_grid(long long work_items, int block) {
     vl::g_launches.fetch_add(1); \
     VL_CHECK_CUDA(cudaGetLastError()); \
   } while (0)
-
-extern "C" int vl_conv1_patches(const void* frames, int is_u8, const float* mean3, void* col, int32_t n, int32_t h,
-                                int32_t w, int32_t kh, int32_t kw, int32_t stride, int32_t pad_top, int32_t pad_left,
-                                int32_t p, int32_t q, int32_t k_ld, vl_stream_t stream_) {
-  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  VL_REQUIRE(frames && col && k_ld % 8 == 0 && k_ld >= kh * kw * 3, "vl_conv1_patches: bad arguments");
-  // widest element touched: ((q-1)*stride - pad_left + kw - 1) * 3 + 2, shifted by the left padding
-  int pitch = ((q - 1) * stride + kw) * 3;
-  if (pitch < (w + pad_left) * 3) pitch = (w + pad_left) * 3;
-  pitch = (pitch + 1) & ~1;
-  VL_REQUIRE(kh * pitch < 65535, "vl_conv1_patches: image row too wide for the 16-bit offset table");
-  const size_t smem = (size_t)kh * pitch * sizeof(bf16) + (size_t)k_ld * sizeof(uint16_t);
-  VL_REQUIRE(smem <= 48 * 1024, "vl_conv1_patches: %zu bytes of shared memory needed (> 48 KB)", smem);
-  const int grid = n * p;
-  if (is_u8)
-    conv1_patches_kernel<true><<<grid, 256, smem, stream>>>(frames, mean3, reinterpret_cast<bf16*>(col), h, w, kh, kw,
-                                                            stride, pad_top, pad_left, p, q, k_ld, pitch);
-  else
-    conv1_patches_kernel<false><<<grid, 256, smem, stream>>>(frames, mean3, reinterpret_cast<bf16*>(col), h, w, kh, kw,
-                                                             stride, pad_top, pad_left, p, q, k_ld, pitch);
-  VL_LAUNCHED();
-  return 0;
-}
 
 extern "C" int vl_lrn_fwd(const void* x, void* y, int64_t rows, int32_t c, int32_t radius, float alpha, float beta,
                           float bias, vl_stream_t stream_) {
