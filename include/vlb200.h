@@ -239,6 +239,23 @@ int vl_lstm_fwd(const float* gx, const float* w_h, float* acts, float* cs, float
  * the pre-activation gates) which feeds the tensor-core data/filter gradient GEMMs.  w_h_t = w_h^T [4h][h]. */
 int vl_lstm_bwd(const float* dh_seq, const float* acts, const float* cs, const float* w_h_t, void* dg,
                 int32_t batch, int32_t t_len, int32_t hidden, vl_stream_t stream);
+/* Captioning variants (lstm.py:102-143 evaluate_sequence with nonzero_per_sequence and init_state; :145-265
+ * generate_feedback_sequence): the same recurrence with an INITIAL STATE h0 / c0 [batch][h] (NULL = zero; the
+ * reference builds LSTMStateTuple(v, v) per layer from the visual vector, lstm.py:34-42), per-sequence LENGTHS
+ * (int32 [batch], NULL = all t_len; beyond its length a sequence carries its state through unchanged and emits zero
+ * outputs, as dynamic_rnn does) and the FINAL STATE h_last / c_last [batch][h].  t_len = 1 with h0 / c0 is one step
+ * of the greedy feedback decode.  Backward: dh_last / dc_last = gradient w.r.t. the final state, dh0 / dc0 (written
+ * when non-NULL) = gradient w.r.t. the initial state. */
+int vl_lstm_fwd_ex(const float* gx, const float* w_h, const float* h0, const float* c0, const int32_t* lengths,
+                   float* acts, float* cs, float* h_seq, void* h_seq_bf16, void* h_prev_bf16, float* h_last,
+                   float* c_last, int32_t batch, int32_t t_len, int32_t hidden, float forget_bias, vl_stream_t stream);
+int vl_lstm_bwd_ex(const float* dh_seq, const float* dh_last, const float* dc_last, const float* acts, const float* cs,
+                   const float* c0, const float* w_h_t, const int32_t* lengths, void* dg, float* dh0, float* dc0,
+                   int32_t batch, int32_t t_len, int32_t hidden, vl_stream_t stream);
+/* get_embedding_from_logits (lstm.py:257-265): index[r] = argmax(logits[r][:v]) (lowest index on ties, tf.arg_max),
+ * out[r][:] = embedding[index[r]][:] (fp32 and / or bf16 copy).  logits fp32 with row pitch ld. */
+int vl_argmax_gather(const float* logits, int32_t rows, int32_t v, int32_t ld, const float* embedding, int32_t e,
+                     int64_t* index, float* out, void* out_bf16, vl_stream_t stream);
 /* Persistent variants for hidden == 256: a cluster of 8 CTAs keeps the recurrent weights (fp32, kernel[d:], NOT
  * transposed for both directions) resident in shared memory for all timesteps of its 8 clips and exchanges h_t /
  * dh_t through distributed shared memory.  Same results as vl_lstm_fwd / vl_lstm_bwd. */

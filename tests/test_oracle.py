@@ -172,3 +172,47 @@ def test_depth_to_space_formulation_of_the_data_gradient(h, w, k, sh, sw, groups
                         if yy < h and xx < w:
                             got[:, yy, xx, g * cin_g:(g + 1) * cin_g] = blk[:, dyy, dxx]
     assert np.abs(got - dx_ref).max() < 1e-4 * max(1.0, np.abs(dx_ref).max())
+
+
+def test_caption_oracle_masking_and_feedback_semantics():
+    """oracle/caption_numpy.py against the semantics it restates (lstm.py:22-42,102-143,145-265): state tuple (v, v) on
+    every layer, dynamic_rnn masking (zero output, state carried through), feedback order of the three visual modes."""
+    from oracle import caption_numpy as C
+    rng = np.random.default_rng(3)
+    b, t_len, d, hd = 3, 4, 5, 8
+    kernels = [rng.standard_normal((d + hd, 4 * hd)).astype(np.float32) * 0.3,
+               rng.standard_normal((hd + hd, 4 * hd)).astype(np.float32) * 0.3]
+    biases = [rng.standard_normal(4 * hd).astype(np.float32) * 0.1 for _ in range(2)]
+    x = rng.standard_normal((b, t_len, d)).astype(np.float32)
+    init = rng.standard_normal((b, hd)).astype(np.float32)
+    out, st = C.evaluate_sequence(x, kernels, biases, [4, 2, 0], init)
+    assert not out[1, 2:].any() and not out[2].any() and out[0].all()
+    # a zero-length sequence keeps LSTMStateTuple(v, v) on both layers
+    assert np.array_equal(st[0][0][2], init[2]) and np.array_equal(st[1][1][2], init[2])
+    # a length-2 sequence equals the full evaluation of its first two steps
+    out2, st2 = C.evaluate_sequence(x[1:2, :2], kernels, biases, None, init[1:2])
+    assert np.allclose(out[1, :2], out2[0]) and np.allclose(st[1][0][1], st2[1][0][0])
+    # one step by hand: gates i, j, f, o with forget_bias 1 and c = h = v
+    g = x[0, 0] @ kernels[0][:d] + init[0] @ kernels[0][d:] + biases[0]
+    i, j, f, o = np.split(g, 4)
+    sig = lambda v: 1 / (1 + np.exp(-v))
+    c1 = init[0] * sig(f + 1.0) + sig(i) * np.tanh(j)
+    h1 = np.tanh(c1) * sig(o)
+    out1, _ = C.evaluate_sequence(x[:1, :1], kernels[:1], biases[:1], None, init[:1])
+    assert np.allclose(out1[0, 0], h1, atol=1e-6)
+    # feedback decode: input_bias consumes the visual vector as step 0 and stores seq_len - 1 words
+    vocab, e = 11, d
+    emb = rng.standard_normal((vocab, e)).astype(np.float32)
+    ow, ob = rng.standard_normal((hd, vocab)).astype(np.float32), rng.standard_normal(vocab).astype(np.float32)
+    start = rng.standard_normal(e).astype(np.float32)
+    vis = rng.standard_normal((b, e)).astype(np.float32)
+    w_bias = C.generate_feedback_sequence(vis, kernels, biases, ow, ob, start, emb, 5, "input_bias")
+    assert w_bias.shape == (b * 4,) and w_bias.dtype == np.int64
+    kc = [rng.standard_normal((e + e + hd, 4 * hd)).astype(np.float32) * 0.3, kernels[1]]
+    w_cat = C.generate_feedback_sequence(vis, kc, biases, ow, ob, start, emb, 5, "input_concat")
+    assert w_cat.shape == (b * 5,)
+    # items are independent and ordered item-major
+    w_one = C.generate_feedback_sequence(vis[1:2], kc, biases, ow, ob, start, emb, 5, "input_concat")
+    assert np.array_equal(w_cat[5:10], w_one)
+    with pytest.raises(ValueError, match="Undefined rnn visual input mode"):
+        C.generate_feedback_sequence(vis, kernels, biases, ow, ob, start, emb, 2, "nope")

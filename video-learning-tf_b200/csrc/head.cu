@@ -105,6 +105,61 @@ __global__ void segment_pool_bwd_relu_bf16_kernel(const float* __restrict__ dy, 
   }
 }
 
+// get_embedding_from_logits (lstm.py:257-265): one CTA per row; strided scan, then a block-wide (value, index)
+// reduction with the lowest index winning ties (tf.arg_max); the winner's embedding row is copied out.
+__global__ void __launch_bounds__(256)
+    argmax_gather_kernel(const float* __restrict__ logits, int v, int ld, const float* __restrict__ embedding, int e,
+                         long long* __restrict__ index, float* __restrict__ out, bf16* __restrict__ out_bf16) {
+  __shared__ float sval[8];
+  __shared__ int sidx[8];
+  __shared__ int winner;
+  const int r = blockIdx.x;
+  const float* z = logits + (long long)r * ld;
+  float m = -INFINITY;
+  int mi = 0x7fffffff;
+  for (int k = threadIdx.x; k < v; k += blockDim.x) {
+    const float x = z[k];
+    if (x > m) {  // strictly greater: within a thread indices grow, so the first maximum is kept
+      m = x;
+      mi = k;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float om = __shfl_xor_sync(0xffffffffu, m, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, mi, o);
+    if (om > m || (om == m && oi < mi)) {
+      m = om;
+      mi = oi;
+    }
+  }
+  if ((threadIdx.x & 31) == 0) {
+    sval[threadIdx.x >> 5] = m;
+    sidx[threadIdx.x >> 5] = mi;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float bm = sval[0];
+    int bi = sidx[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
+      if (sval[w] > bm || (sval[w] == bm && sidx[w] < bi)) {
+        bm = sval[w];
+        bi = sidx[w];
+      }
+    winner = bi;
+    if (index != nullptr) index[r] = bi;
+  }
+  __syncthreads();
+  if (embedding != nullptr) {
+    const float* src = embedding + (long long)winner * e;
+    for (int k = threadIdx.x; k < e; k += blockDim.x) {
+      const float x = src[k];
+      if (out != nullptr) out[(long long)r * e + k] = x;
+      if (out_bf16 != nullptr) out_bf16[(long long)r * e + k] = __float2bfloat16_rn(x);
+    }
+  }
+}
+
 // ---- Philox4x32-10 ----
 __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
   const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
@@ -290,6 +345,18 @@ extern "C" int vl_segment_pool_bwd_relu_bf16(const float* dy, const void* act, i
   VL_REQUIRE(mode == VL_POOL_AVG || mode == VL_POOL_LAST, "vl_segment_pool_bwd_relu_bf16: only avg/last have gradients");
   segment_pool_bwd_relu_bf16_kernel<<<sweep_grid((long long)num_seg * fixed_len * d, 256), 256, 0, stream>>>(
       dy, reinterpret_cast<const bf16*>(act), fixed_len, num_seg, d, mode, reinterpret_cast<bf16*>(dx));
+  VL_LAUNCHED();
+  return 0;
+}
+
+extern "C" int vl_argmax_gather(const float* logits, int32_t rows, int32_t v, int32_t ld, const float* embedding,
+                                int32_t e, int64_t* index, float* out, void* out_bf16, vl_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  VL_REQUIRE(logits && rows > 0 && v > 0 && ld >= v, "vl_argmax_gather: bad arguments");
+  VL_REQUIRE(embedding == nullptr || (e > 0 && (out != nullptr || out_bf16 != nullptr)),
+             "vl_argmax_gather: an embedding needs an output");
+  argmax_gather_kernel<<<rows, 256, 0, stream>>>(logits, v, ld, embedding, e, reinterpret_cast<long long*>(index), out,
+                                                 reinterpret_cast<bf16*>(out_bf16));
   VL_LAUNCHED();
   return 0;
 }

@@ -23,21 +23,32 @@ typedef __nv_bfloat16 bf16;
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
+// Optional (captioning variants, lstm.py:102-143): h0 / c0 = initial state [batch][hidden] (zero when NULL),
+// lengths[b] = valid timesteps of sequence b (dynamic_rnn's sequence_length: beyond it the state is carried
+// through unchanged and the emitted output is zero), h_last / c_last = final state [batch][hidden].
 template <int CB>
 __global__ void lstm_fwd_kernel(const float* __restrict__ gx, const float* __restrict__ w_h, float* __restrict__ acts,
                                 float* __restrict__ cs, float* __restrict__ h_seq, bf16* __restrict__ h_seq_bf16,
-                                bf16* __restrict__ h_prev_bf16, int batch, int t_len, int hidden, float forget_bias) {
+                                bf16* __restrict__ h_prev_bf16, int batch, int t_len, int hidden, float forget_bias,
+                                const float* __restrict__ h0, const float* __restrict__ c0,
+                                const int32_t* __restrict__ lengths, float* __restrict__ h_last,
+                                float* __restrict__ c_last) {
   extern __shared__ float hs[];  // [2][CB][hidden]
   const int j = threadIdx.x;
   const int b0 = blockIdx.x * CB;
   const int h4 = 4 * hidden;
   float c[CB];
+  int len[CB];
 #pragma unroll
   for (int cb = 0; cb < CB; ++cb) {
-    c[cb] = 0.f;
-    hs[cb * hidden + j] = 0.f;
+    const int b = b0 + cb;
+    const bool live = b < batch;
+    c[cb] = (live && c0 != nullptr) ? c0[(long long)b * hidden + j] : 0.f;
+    hs[cb * hidden + j] = (live && h0 != nullptr) ? h0[(long long)b * hidden + j] : 0.f;
+    len[cb] = (live && lengths != nullptr) ? min(lengths[b], t_len) : t_len;
   }
   __syncthreads();
+  const bool recur_at_0 = h0 != nullptr;
   for (int t = 0; t < t_len; ++t) {
     const float* hcur = hs + (t & 1) * CB * hidden;
     float* hnext = hs + ((t & 1) ^ 1) * CB * hidden;
@@ -56,7 +67,7 @@ __global__ void lstm_fwd_kernel(const float* __restrict__ gx, const float* __res
         for (int q = 0; q < 4; ++q) acc[cb][q] = 0.f;
       }
     }
-    if (t > 0) {
+    if (t > 0 || recur_at_0) {
 #pragma unroll 4
       for (int k = 0; k < hidden; ++k) {
         const float* wr = w_h + (long long)k * h4 + j;
@@ -74,13 +85,17 @@ __global__ void lstm_fwd_kernel(const float* __restrict__ gx, const float* __res
 #pragma unroll
     for (int cb = 0; cb < CB; ++cb) {
       const int b = b0 + cb;
+      const bool valid = t < len[cb];
       const float si = sigmoidf_(acc[cb][0]);
       const float tj = tanhf(acc[cb][1]);
       const float sf = sigmoidf_(acc[cb][2] + forget_bias);
       const float so = sigmoidf_(acc[cb][3]);
-      c[cb] = c[cb] * sf + si * tj;
-      const float h = tanhf(c[cb]) * so;
-      hnext[cb * hidden + j] = h;
+      const float c_new = c[cb] * sf + si * tj;
+      const float h_new = tanhf(c_new) * so;
+      if (valid) c[cb] = c_new;
+      const float h_state = valid ? h_new : hcur[cb * hidden + j];  // beyond the length: state copied through
+      const float h_out = valid ? h_new : 0.f;                       // ... and a zero output (dynamic_rnn)
+      hnext[cb * hidden + j] = h_state;
       if (b < batch) {
         const long long row = (long long)b * t_len + t;
         if (acts != nullptr) {
@@ -91,8 +106,12 @@ __global__ void lstm_fwd_kernel(const float* __restrict__ gx, const float* __res
           a[3 * hidden + j] = so;
         }
         if (cs != nullptr) cs[row * hidden + j] = c[cb];
-        if (h_seq != nullptr) h_seq[row * hidden + j] = h;
-        if (h_seq_bf16 != nullptr) h_seq_bf16[row * hidden + j] = __float2bfloat16_rn(h);
+        if (h_seq != nullptr) h_seq[row * hidden + j] = h_out;
+        if (h_seq_bf16 != nullptr) h_seq_bf16[row * hidden + j] = __float2bfloat16_rn(h_out);
+        if (t == t_len - 1) {
+          if (h_last != nullptr) h_last[(long long)b * hidden + j] = h_state;
+          if (c_last != nullptr) c_last[(long long)b * hidden + j] = c[cb];
+        }
       }
     }
     __syncthreads();
@@ -101,20 +120,37 @@ __global__ void lstm_fwd_kernel(const float* __restrict__ gx, const float* __res
 
 // One CTA per clip, reverse time.  dgs (this step's gate gradients) is exchanged through shared memory so that
 // thread j can form dh_{t-1}[j] = sum_n dg[n] * w_h[j][n] with coalesced reads of w_h^T.
+// Optional: lengths (steps beyond a sequence's length pass the state gradient through and emit zero gate gradients),
+// c0 (initial cell state), dh_last / dc_last (gradient w.r.t. the final state), dh0 / dc0 (gradient w.r.t. the initial
+// state, written when non-NULL: the recursion then also runs at t = 0).
 __global__ void lstm_bwd_kernel(const float* __restrict__ dh_seq, const float* __restrict__ acts,
                                 const float* __restrict__ cs, const float* __restrict__ w_h_t, bf16* __restrict__ dg,
-                                int batch, int t_len, int hidden) {
+                                int batch, int t_len, int hidden, const int32_t* __restrict__ lengths,
+                                const float* __restrict__ c0, const float* __restrict__ dh_last,
+                                const float* __restrict__ dc_last, float* __restrict__ dh0, float* __restrict__ dc0) {
   extern __shared__ float dgs[];  // [4*hidden]
   const int j = threadIdx.x;
   const int b = blockIdx.x;
   const int h4 = 4 * hidden;
-  float dh_next = 0.f, dc_next = 0.f;
+  const int len = lengths != nullptr ? min(lengths[b], t_len) : t_len;
+  float dh_next = dh_last != nullptr ? dh_last[(long long)b * hidden + j] : 0.f;
+  float dc_next = dc_last != nullptr ? dc_last[(long long)b * hidden + j] : 0.f;
+  const bool want_init = dh0 != nullptr;
   for (int t = t_len - 1; t >= 0; --t) {
     const long long row = (long long)b * t_len + t;
+    bf16* out = dg + row * h4;
+    if (t >= len) {  // block-uniform: padded step, the state (and its gradient) passes through
+      const bf16 z = __float2bfloat16_rn(0.f);
+      out[j] = z;
+      out[hidden + j] = z;
+      out[2 * hidden + j] = z;
+      out[3 * hidden + j] = z;
+      continue;
+    }
     const float* a = acts + row * h4;
     const float si = a[j], tj = a[hidden + j], sf = a[2 * hidden + j], so = a[3 * hidden + j];
     const float ct = cs[row * hidden + j];
-    const float cprev = t > 0 ? cs[(row - 1) * hidden + j] : 0.f;
+    const float cprev = t > 0 ? cs[(row - 1) * hidden + j] : (c0 != nullptr ? c0[(long long)b * hidden + j] : 0.f);
     const float tc = tanhf(ct);
     const float dh = dh_seq[row * hidden + j] + dh_next;
     const float d_o = dh * tc * so * (1.f - so);
@@ -127,30 +163,35 @@ __global__ void lstm_bwd_kernel(const float* __restrict__ dh_seq, const float* _
     dgs[hidden + j] = d_j;
     dgs[2 * hidden + j] = d_f;
     dgs[3 * hidden + j] = d_o;
-    bf16* out = dg + row * h4;
     out[j] = __float2bfloat16_rn(d_i);
     out[hidden + j] = __float2bfloat16_rn(d_j);
     out[2 * hidden + j] = __float2bfloat16_rn(d_f);
     out[3 * hidden + j] = __float2bfloat16_rn(d_o);
     __syncthreads();
     float acc = 0.f;
-    if (t > 0) {
+    if (t > 0 || want_init) {
 #pragma unroll 8
       for (int n = 0; n < h4; ++n) acc = fmaf(dgs[n], __ldg(w_h_t + (long long)n * hidden + j), acc);
     }
     dh_next = acc;
     __syncthreads();
   }
+  if (want_init) {
+    dh0[(long long)b * hidden + j] = dh_next;
+    if (dc0 != nullptr) dc0[(long long)b * hidden + j] = dc_next;
+  }
 }
 
 }  // namespace
 
-extern "C" int vl_lstm_fwd(const float* gx, const float* w_h, float* acts, float* cs, float* h_seq, void* h_seq_bf16,
-                           void* h_prev_bf16, int32_t batch, int32_t t_len, int32_t hidden, float forget_bias,
-                           vl_stream_t stream_) {
+extern "C" int vl_lstm_fwd_ex(const float* gx, const float* w_h, const float* h0, const float* c0,
+                              const int32_t* lengths, float* acts, float* cs, float* h_seq, void* h_seq_bf16,
+                              void* h_prev_bf16, float* h_last, float* c_last, int32_t batch, int32_t t_len,
+                              int32_t hidden, float forget_bias, vl_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   VL_REQUIRE(gx && w_h && batch > 0 && t_len > 0, "vl_lstm_fwd: bad arguments");
   VL_REQUIRE(hidden % 32 == 0 && hidden <= 1024, "vl_lstm_fwd: hidden must be a multiple of 32 and <= 1024");
+  VL_REQUIRE((h0 == nullptr) == (c0 == nullptr), "vl_lstm_fwd: h0 and c0 come together (LSTMStateTuple)");
   const int sms = vl::num_sms();
   int cb = 1;
   if (batch > sms * 4) cb = 8;
@@ -161,8 +202,8 @@ extern "C" int vl_lstm_fwd(const float* gx, const float* w_h, float* acts, float
   bf16* hb = reinterpret_cast<bf16*>(h_seq_bf16);
   bf16* hp = reinterpret_cast<bf16*>(h_prev_bf16);
 #define VL_LSTM_LAUNCH(CB)                                                                                          \
-  lstm_fwd_kernel<CB><<<grid, hidden, smem, stream>>>(gx, w_h, acts, cs, h_seq, hb, hp, batch, t_len, hidden, \
-                                                      forget_bias)
+  lstm_fwd_kernel<CB><<<grid, hidden, smem, stream>>>(gx, w_h, acts, cs, h_seq, hb, hp, batch, t_len, hidden,       \
+                                                      forget_bias, h0, c0, lengths, h_last, c_last)
   if (cb == 1) VL_LSTM_LAUNCH(1);
   else if (cb == 2) VL_LSTM_LAUNCH(2);
   else if (cb == 4) VL_LSTM_LAUNCH(4);
@@ -173,17 +214,32 @@ extern "C" int vl_lstm_fwd(const float* gx, const float* w_h, float* acts, float
   return 0;
 }
 
-extern "C" int vl_lstm_bwd(const float* dh_seq, const float* acts, const float* cs, const float* w_h_t, void* dg,
-                           int32_t batch, int32_t t_len, int32_t hidden, vl_stream_t stream_) {
+extern "C" int vl_lstm_fwd(const float* gx, const float* w_h, float* acts, float* cs, float* h_seq, void* h_seq_bf16,
+                           void* h_prev_bf16, int32_t batch, int32_t t_len, int32_t hidden, float forget_bias,
+                           vl_stream_t stream_) {
+  return vl_lstm_fwd_ex(gx, w_h, nullptr, nullptr, nullptr, acts, cs, h_seq, h_seq_bf16, h_prev_bf16, nullptr, nullptr,
+                        batch, t_len, hidden, forget_bias, stream_);
+}
+
+extern "C" int vl_lstm_bwd_ex(const float* dh_seq, const float* dh_last, const float* dc_last, const float* acts,
+                              const float* cs, const float* c0, const float* w_h_t, const int32_t* lengths, void* dg,
+                              float* dh0, float* dc0, int32_t batch, int32_t t_len, int32_t hidden,
+                              vl_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   VL_REQUIRE(dh_seq && acts && cs && w_h_t && dg && batch > 0 && t_len > 0, "vl_lstm_bwd: bad arguments");
   VL_REQUIRE(hidden % 32 == 0 && hidden <= 1024, "vl_lstm_bwd: hidden must be a multiple of 32 and <= 1024");
   const size_t smem = (size_t)4 * hidden * sizeof(float);
   lstm_bwd_kernel<<<batch, hidden, smem, stream>>>(dh_seq, acts, cs, w_h_t, reinterpret_cast<bf16*>(dg), batch, t_len,
-                                                   hidden);
+                                                   hidden, lengths, c0, dh_last, dc_last, dh0, dc0);
   vl::g_launches.fetch_add(1);
   VL_CHECK_CUDA(cudaGetLastError());
   return 0;
+}
+
+extern "C" int vl_lstm_bwd(const float* dh_seq, const float* acts, const float* cs, const float* w_h_t, void* dg,
+                           int32_t batch, int32_t t_len, int32_t hidden, vl_stream_t stream_) {
+  return vl_lstm_bwd_ex(dh_seq, nullptr, nullptr, acts, cs, nullptr, w_h_t, nullptr, dg, nullptr, nullptr, batch, t_len,
+                        hidden, stream_);
 }
 
 // =================================================================================================

@@ -564,10 +564,10 @@ class Engine(object):
 
     def prefetch(self, frames_pinned, onehot_pinned, slot):
         """Enqueue the H2D copy of one batch (pinned host tensors: uint8 frames [n,H,W,3], int32 one-hot [b,C]) on the
-        copy stream into device slot `slot` (0/1) and return (frames_dev, onehot_dev, copied, consumed): the compute
+        copy stream into device slot `slot` (any small index; one buffer pair per slot) and return (frames_dev, onehot_dev, copied, consumed): the compute
         stream must wait for the event `copied` before `train_step(frames_dev, onehot_dev, ...)` and record
         `consumed` after it (the next copy into this slot waits for it); with two slots the copy of batch i+1
-        overlaps the step of batch i."""
+        overlaps the step of batch i, with three the copy engine never waits for a slot."""
         if not hasattr(self, "_copy_stream"):
             self._copy_stream = torch.cuda.Stream(device=self.dev)
             self._slots = {}
