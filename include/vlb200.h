@@ -288,6 +288,12 @@ int vl_segment_pool_fwd_bf16(const void* x, int32_t fixed_len, int32_t num_seg, 
 int vl_segment_pool_bwd_relu_bf16(const float* dy, const void* act, int32_t fixed_len, int32_t num_seg, int32_t d,
                                   int32_t mode, void* dx, vl_stream_t stream);
 
+/* Multi-input pipelines (tf_util.py:136-147 apply_tensor_list_fusion, methods avg / maximum): element-wise mean
+ * (sum in list order, one division) or maximum over a HOST array of k <= 8 DEVICE pointers to fp32 tensors of n
+ * elements each; mode = VL_POOL_AVG / VL_POOL_MAX. */
+int vl_fuse_list(const float* const* inputs, int32_t k, int64_t n, int32_t mode, float* y, void* y_bf16,
+                 vl_stream_t stream);
+
 /* tf.nn.dropout (lstm.py:50-56): y = x * mask, mask in {0, 1/keep}.  The mask is generated on device from
  * (seed, offset) with Philox4x32-10 and returned so that the backward pass (and the oracle) can reuse it. */
 int vl_dropout_mask(float* mask, int64_t n, float keep_prob, uint64_t seed, uint64_t offset, vl_stream_t stream);

@@ -96,6 +96,7 @@ def _declare(L):
         "vl_lstm_fwd_ex": [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, f32, vp],
         "vl_lstm_bwd_ex": [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp],
         "vl_argmax_gather": [vp, i32, i32, i32, vp, i32, vp, vp, vp, vp],
+        "vl_fuse_list": [vp, i32, i64, i32, vp, vp, vp],
         "vl_segment_pool_fwd": [vp, vp, i32, i32, i32, i32, vp, vp, vp],
         "vl_segment_pool_bwd": [vp, vp, i32, i32, i32, i32, vp, vp],
         "vl_segment_pool_fwd_bf16": [vp, i32, i32, i32, i32, vp, vp, vp],
@@ -118,7 +119,7 @@ def _declare(L):
 
 EXPORTS = ["vl_last_error", "vl_version", "vl_device_sm_count", "vl_launch_count", "vl_zero", "vl_gemm", "vl_conv_flat", "vl_pack_dgrad_kmajor", "vl_pack_dgrad_d2s",
            "vl_lrn_fwd", "vl_lrn_bwd", "vl_maxpool_fwd", "vl_maxpool_bwd", "vl_colsum", "vl_pack_bf16",
-           "vl_cast_f32_to_bf16", "vl_transpose_f32", "vl_gather_bf16", "vl_lstm_fwd", "vl_lstm_bwd", "vl_lstm_fwd_ex", "vl_lstm_bwd_ex", "vl_argmax_gather", "vl_lrn_pool_fwd", "vl_pool_lrn_bwd",
+           "vl_cast_f32_to_bf16", "vl_transpose_f32", "vl_gather_bf16", "vl_lstm_fwd", "vl_lstm_bwd", "vl_lstm_fwd_ex", "vl_lstm_bwd_ex", "vl_argmax_gather", "vl_fuse_list", "vl_lrn_pool_fwd", "vl_pool_lrn_bwd",
            "vl_lstm_fwd_cluster", "vl_lstm_bwd_cluster", "vl_frames_s2d", "vl_frames_s2d_crop", "vl_pack_bf16_t", "vl_s2d_pack_filter", "vl_s2d_unpack_grad",
            "vl_lrn_pool_fwd_generic", "vl_pool_lrn_bwd_generic", "vl_segment_pool_fwd",
            "vl_segment_pool_bwd", "vl_segment_pool_fwd_bf16", "vl_segment_pool_bwd_relu_bf16", "vl_dropout_mask", "vl_mul", "vl_softmax_ce", "vl_grad_sqnorms", "vl_grad_sqnorms_workspace",

@@ -9,6 +9,7 @@
 #include "../../include/vlb200.h"
 
 #include <atomic>
+#include <cstring>
 
 namespace vl {
 extern std::atomic<long long> g_launches;
@@ -157,6 +158,27 @@ __global__ void __launch_bounds__(256)
       if (out != nullptr) out[(long long)r * e + k] = x;
       if (out_bf16 != nullptr) out_bf16[(long long)r * e + k] = __float2bfloat16_rn(x);
     }
+  }
+}
+
+// apply_tensor_list_fusion (tf_util.py:136-147): element-wise mean / maximum over a list of k same-shaped tensors
+// (tf.reduce_mean / tf.reduce_max over axis 0 of the stacked list).  mean = sum in list order, then one division.
+struct FuseList {
+  const float* src[8];
+  int k;
+};
+__global__ void fuse_list_kernel(const FuseList in, long long n, int mode, float* __restrict__ y,
+                                 bf16* __restrict__ y_bf16) {
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+       idx += (long long)gridDim.x * blockDim.x) {
+    float acc = in.src[0][idx];
+    for (int j = 1; j < in.k; ++j) {
+      const float v = in.src[j][idx];
+      acc = mode == VL_POOL_MAX ? fmaxf(acc, v) : __fadd_rn(acc, v);
+    }
+    if (mode != VL_POOL_MAX) acc = __fdiv_rn(acc, (float)in.k);
+    if (y) y[idx] = acc;
+    if (y_bf16) y_bf16[idx] = __float2bfloat16_rn(acc);
   }
 }
 
@@ -345,6 +367,23 @@ extern "C" int vl_segment_pool_bwd_relu_bf16(const float* dy, const void* act, i
   VL_REQUIRE(mode == VL_POOL_AVG || mode == VL_POOL_LAST, "vl_segment_pool_bwd_relu_bf16: only avg/last have gradients");
   segment_pool_bwd_relu_bf16_kernel<<<sweep_grid((long long)num_seg * fixed_len * d, 256), 256, 0, stream>>>(
       dy, reinterpret_cast<const bf16*>(act), fixed_len, num_seg, d, mode, reinterpret_cast<bf16*>(dx));
+  VL_LAUNCHED();
+  return 0;
+}
+
+extern "C" int vl_fuse_list(const float* const* inputs, int32_t k, int64_t n, int32_t mode, float* y, void* y_bf16,
+                            vl_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  VL_REQUIRE(inputs && k >= 1 && k <= 8 && n > 0 && (y || y_bf16), "vl_fuse_list: bad arguments (1..8 inputs)");
+  VL_REQUIRE(mode == VL_POOL_AVG || mode == VL_POOL_MAX, "Unknown fusion method: [%d]", mode);
+  FuseList in;
+  memset(&in, 0, sizeof(in));
+  in.k = k;
+  for (int j = 0; j < k; ++j) {
+    VL_REQUIRE(inputs[j] != nullptr, "vl_fuse_list: input %d is NULL", j);
+    in.src[j] = inputs[j];
+  }
+  fuse_list_kernel<<<sweep_grid(n, 256), 256, 0, stream>>>(in, n, mode, y, reinterpret_cast<bf16*>(y_bf16));
   VL_LAUNCHED();
   return 0;
 }

@@ -696,6 +696,13 @@ class Engine(object):
         feat = self._encoder_fwd(frames, is_u8, n, training, self._stage_crops(crops, frames, n))
         return self._head_fwd(feat, n, training)
 
+    def forward_features(self, frames, crops=None):
+        """The dcnn feature vectors of every frame (bf16 device tensor [frames, dim] of the configured
+        frame_encoding_layer): the output of a classifier-less pipeline (model.py:110-112) that a later pipeline
+        consumes (fusion.py)."""
+        frames, is_u8, n = self._stage_frames(frames)
+        return self._encoder_fwd(frames, is_u8, n, False, self._stage_crops(crops, frames, n))
+
     def forward(self, frames, crops=None):
         """`sess.run(model.logits, fdict)` (run_task.py:95): float32 ndarray [clips, C] on the host."""
         return self.forward_device(frames, training=False, crops=crops).cpu().numpy()
