@@ -27,6 +27,10 @@ const char* vl_last_error(void);
 int vl_version(void);
 /* Number of SMs of the current device (tile schedulers size their persistent grids with it). */
 int vl_device_sm_count(void);
+/* Shared memory (bytes per SM, rounded up to 1 KB, <= 96 KB) that the persistent contraction kernels (vl_gemm,
+ * vl_conv_flat) leave unused from now on, so that CTAs of the issue-bound LRN / pool kernels launched on another stream
+ * can be resident next to a contraction CTA instead of queueing behind it.  0 (default): the ring takes everything. */
+int vl_set_smem_reserve(int32_t bytes);
 /* Total number of kernel launches issued through this library since load (bench.py: gpu_launches). */
 int64_t vl_launch_count(void);
 /* cudaMemsetAsync(ptr, 0, bytes) on `stream`: the gradient arena is cleared once per step (tf.gradients starts from

@@ -177,3 +177,36 @@ def test_checkpoint_roundtrip_and_snap_format(tmp_path):
     with open(os.path.join(str(tmp_path), "checkpoints", "checkpoint")) as f:
         first = f.readline().strip()  # TensorFlow's layout: the reference's resume_snap reads this line (feeder.py:148-156)
     assert first == 'model_checkpoint_path: "%s"' % kept[-1]
+
+
+def test_fusion_variants_map_to_engine_configs(tmp_path):
+    """Model.build_pipeline's variants beyond the BASELINE workflows (model.py:103-117,137-151; lstm.py:81-93) ->
+    EngineConfig; `reshape` (tf_util.py:24-27) is rejected with the reference's text."""
+    from vlb200 import engine as E
+    from vlb200.settings import pipeline_engine_config
+
+    def net(**kw):
+        base = dict(input=["main"], input_fusion=None, representation="dcnn", frame_encoding_layer="fc7", classifier="fc",
+                    lstm_params=None, frame_fusion=None, weights_file=None)
+        base.update(kw)
+        return types.SimpleNamespace(**base)
+    cfg = pipeline_engine_config(net(classifier="lstm", lstm_params=[64, 2, "state"]), 11, 4, "sgd", 10, 0.5)
+    assert (cfg.workflow, cfg.fusion) == ("lrcn", "state")
+    names = [n for n, _ in E.variable_shapes(cfg)]
+    assert "fc_convert_w" in names and "output_fc_w" not in names  # convert_dim_fc's default name (model.py:142-143)
+    cfg = pipeline_engine_config(net(frame_fusion=["early", "avg"]), 11, 4, "sgd", 10, 0.0)
+    assert (cfg.workflow, cfg.early_fusion, cfg.fusion, cfg.frame_encoding_layer) == ("fc", True, "avg", "fc7")
+    assert dict(E.variable_shapes(cfg))["fc_convert_w"] == (4096, 11)
+    cfg = pipeline_engine_config(net(frame_encoding_layer="fc6", frame_fusion=["late", "last"]), 11, 4, "sgd", 10, 0.0)
+    assert (cfg.workflow, cfg.early_fusion, cfg.fusion, cfg.frame_encoding_layer) == ("fc", False, "last", "fc6")
+    assert "dcnn/fc7W" not in dict(E.variable_shapes(cfg))
+    cfg = pipeline_engine_config(net(frame_encoding_layer="fc8", frame_fusion=["early", "avg"]), 11, 4, "sgd", 10, 0.0)
+    assert cfg.workflow == "singleframe"  # pooled fc8 logits: early and late fusion coincide (no op in between)
+    with pytest.raises(Exception, match="Undefined frame fusion type : reshape"):
+        pipeline_engine_config(net(classifier="lstm", lstm_params=[64, 1, "reshape"]), 11, 4, "sgd", 10, 0.0)
+    with pytest.raises(Exception, match="needs frame_fusion"):
+        pipeline_engine_config(net(), 11, 4, "sgd", 10, 0.0)
+    with pytest.raises(Exception, match="late fusion with no classifier"):
+        pipeline_engine_config(net(classifier=None, frame_fusion=["late", "avg"]), 11, 4, "sgd", 10, 0.0)
+    with pytest.raises(Exception, match="Multi-input"):
+        pipeline_engine_config(net(input=["main", "aux"], input_fusion="concat"), 11, 4, "sgd", 10, 0.0)

@@ -62,6 +62,8 @@ def _declare(L):
     L.vl_version.restype = i32
     L.vl_device_sm_count.restype = i32
     L.vl_launch_count.restype = i64
+    L.vl_set_smem_reserve.restype = i32
+    L.vl_set_smem_reserve.argtypes = [i32]
     L.vl_grad_sqnorms_workspace.restype = i64
     L.vl_grad_sqnorms_workspace.argtypes = [i64, i32]
     u64 = ctypes.c_uint64
@@ -117,7 +119,7 @@ def _declare(L):
         fn.argtypes = argtypes
 
 
-EXPORTS = ["vl_last_error", "vl_version", "vl_device_sm_count", "vl_launch_count", "vl_zero", "vl_gemm", "vl_conv_flat", "vl_pack_dgrad_kmajor", "vl_pack_dgrad_d2s",
+EXPORTS = ["vl_set_smem_reserve", "vl_last_error", "vl_version", "vl_device_sm_count", "vl_launch_count", "vl_zero", "vl_gemm", "vl_conv_flat", "vl_pack_dgrad_kmajor", "vl_pack_dgrad_d2s",
            "vl_lrn_fwd", "vl_lrn_bwd", "vl_maxpool_fwd", "vl_maxpool_bwd", "vl_colsum", "vl_pack_bf16",
            "vl_cast_f32_to_bf16", "vl_transpose_f32", "vl_gather_bf16", "vl_lstm_fwd", "vl_lstm_bwd", "vl_lstm_fwd_ex", "vl_lstm_bwd_ex", "vl_argmax_gather", "vl_fuse_list", "vl_lrn_pool_fwd", "vl_pool_lrn_bwd",
            "vl_lstm_fwd_cluster", "vl_lstm_bwd_cluster", "vl_frames_s2d", "vl_frames_s2d_crop", "vl_pack_bf16_t", "vl_s2d_pack_filter", "vl_s2d_unpack_grad",

@@ -39,6 +39,7 @@ const char* last_error();
   } while (0)
 
 int num_sms();
+int smem_reserve();  // bytes of shared memory per SM the persistent contraction kernels leave to other kernels
 
 }  // namespace vl
 

@@ -610,7 +610,9 @@ extern "C" int vl_conv_flat(const vl_conv_flat_desc* d, const void* x, const voi
   if (p.epi_groups > EPI_GROUPS) p.epi_groups = EPI_GROUPS;
   p.stage_bufs = 2;
   int STAGE_BYTES = p.direct ? 0 : p.epi_groups * p.stage_bufs * 16 * 128 * 2;  // transposition stages per group
-  int w_avail = SMEM_LIMIT - 1024 - BAR_REGION - STAGE_BYTES - 1024 - p.x_stages * p.x_stage_bytes;
+  // (vl::smem_reserve(): shared memory left to CTAs of other kernels on the same SM, see vl_set_smem_reserve)
+  const int smem_limit = SMEM_LIMIT - vl::smem_reserve();
+  int w_avail = smem_limit - 1024 - BAR_REGION - STAGE_BYTES - 1024 - p.x_stages * p.x_stage_bytes;
   // filter box: only the rows that exist (8-row swizzle atoms); the UMMA reads 128 rows, the surplus lanes are
   // never stored
   int w_box_rows = d->w_rows < 128 ? ((d->w_rows + 7) / 8) * 8 : 128;

@@ -889,7 +889,9 @@ extern "C" int vl_gemm(const vl_gemm_desc* d, const void* a, const void* b, void
   p.b_stage_bytes = BN * 128;
   if (p.row_shift) p.b_stage_bytes = (64 + cg.kw - 1) * 128;  // one staged input row serves the kw taps: smaller stages, deeper ring
   p.stage_bytes = p.msub * A_SUB_BYTES + ((p.b_stage_bytes + 1023) / 1024) * 1024;
-  int stages = (SMEM_LIMIT - 1024 - BAR_REGION) / p.stage_bytes;
+  // shared memory left free for CTAs of OTHER kernels on the same SM (vl_set_smem_reserve): the issue-bound LRN / pool
+  // gradient kernels need 2 KB per CTA and can then run next to a persistent contraction CTA instead of after it
+  int stages = (SMEM_LIMIT - vl::smem_reserve() - 1024 - BAR_REGION) / p.stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   VL_REQUIRE(stages >= 2, "vl_gemm: not enough shared memory for 2 stages");
   p.num_stages = stages;

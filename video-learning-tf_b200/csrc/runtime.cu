@@ -31,7 +31,16 @@ int num_sms() {
   return n;
 }
 
+static std::atomic<int> g_smem_reserve{0};
+int smem_reserve() { return g_smem_reserve.load(); }
+
 }  // namespace vl
+
+extern "C" int vl_set_smem_reserve(int32_t bytes) {
+  VL_REQUIRE(bytes >= 0 && bytes <= 96 * 1024, "vl_set_smem_reserve: 0..96 KB");
+  vl::g_smem_reserve.store((bytes + 1023) / 1024 * 1024);
+  return 0;
+}
 
 extern "C" const char* vl_last_error(void) { return vl::last_error(); }
 extern "C" int vl_version(void) { return 100; }

@@ -686,6 +686,7 @@ class Engine(object):
         return ("fc8", "dcnn/fc8b") if self.cfg.workflow == "singleframe" else ("fc_convert", "fc_convert_b")
 
     _injected_mask = None
+    bwd_smem_reserve = 0  # bytes (see train_step); set from the A/B measurement in profiles/r02_step_ab.txt
 
     def forward_device(self, frames, training=False, crops=None):
         """Enqueue the forward pass; returns the device logits [clips, C] (fp32).  `crops` (int32 [n, 3]: y0, x0, mirror)
@@ -953,8 +954,18 @@ class Engine(object):
         nv.call("vl_softmax_ce", logits, A["labels"][:b], b, c, 1.0 / self._global_clips, A["row_loss"],
                 self.scalars[4:6], A["dlogits"][:b], A["dlogits_bf"][:b], self.c_pad)
         self._zero_grads(n)
-        dfeat = self._head_bwd(n)
-        self._encoder_bwd(dfeat, n)
+        # During the backward pass the persistent contraction kernels leave a few KB of shared memory per SM unused:
+        # the issue-bound LRN / pool gradient CTAs (2 KB each, main stream) then become resident NEXT TO the filter-
+        # gradient CTAs of the side stream instead of queueing behind 148 CTAs that own all the shared memory
+        reserve = int(os.environ.get("VL_BWD_SMEM_RESERVE", str(self.bwd_smem_reserve)))
+        if reserve:
+            nv.lib().vl_set_smem_reserve(reserve)
+        try:
+            dfeat = self._head_bwd(n)
+            self._encoder_bwd(dfeat, n)
+        finally:
+            if reserve:
+                nv.lib().vl_set_smem_reserve(0)
         return self._finish_step(lr, apply_update)
 
     def _finish_step(self, lr, apply_update):

@@ -265,7 +265,9 @@ def pipeline_engine_config(net, num_classes, fpc, optimizer, clip_norm, dropout_
         error("A pipeline with an fc classifier and fpc %d needs frame_fusion [early|late, avg|last]: labels are per "
               "clip (dataset_.py:400-408)" % fpc)
     layer = net.frame_encoding_layer if net.frame_encoding_layer in ("fc6", "fc7") else "fc8"
-    if layer == "fc8" and early is None:
-        return EngineConfig(workflow="singleframe", fusion=late or defs.fusion_method.avg, **common)
+    if layer == "fc8":
+        # fc8 logits per frame: the fc classifier is the identity (model.py:115-117), so fusing before it (early) or
+        # after it (late) is the same reduction over the clip's frames
+        return EngineConfig(workflow="singleframe", fusion=late or early, **common)
     return EngineConfig(workflow="fc", frame_encoding_layer=layer, fusion=late or early, early_fusion=early is not None,
                         **common)
