@@ -345,7 +345,13 @@ def run_ours(args):
     # ---- end to end from host buffers: every step copies its uint8 frames (+ int32 labels) from PINNED host memory
     # (H2D inside the timed region, double buffered on a copy stream so that the copy of step i+1 overlaps the
     # compute of step i) and reads the step result back (D2H: the step scalars / the logits) ----
-    pin_frames = torch.from_numpy(frames_host).pin_memory()
+    # VL_BENCH_WC=1: write-combined pinned staging buffers (vl_host_alloc) instead of torch's cached pinned memory
+    if os.environ.get("VL_BENCH_WC", "0") == "1":
+        pin_frames = nv.host_staging_tensor(frames_host.shape, torch.uint8, write_combined=True)
+        pin_frames.copy_(torch.from_numpy(frames_host))
+        assert pin_frames.is_pinned()
+    else:
+        pin_frames = torch.from_numpy(frames_host).pin_memory()
     pin_onehot = torch.from_numpy(onehot_host).pin_memory()
     logits_host = torch.empty(clips, NUM_CLASSES, dtype=torch.float32).pin_memory()
 
@@ -451,6 +457,7 @@ def run_ours(args):
                 "h2d_bytes_per_step": int(frames_host.nbytes + (0 if forward_only else onehot_host.nbytes)),
                 "d2h_bytes_per_step": int(logits_host.numel() * 4) if forward_only else 32,
                 "h2d_gbs_per_rank_all_ranks_copying": h2d_gbs,
+                "host_staging": "write-combined pinned" if os.environ.get("VL_BENCH_WC", "0") == "1" else "pinned",
                 "input": "uint8 frames + int32 one-hot labels in pinned host memory, H2D on a copy stream "
                          "(three device slots: two copies in flight) inside the timed region; Engine.prefetch + Engine.%s" % (
                              "forward_device" if forward_only else "train_step")},

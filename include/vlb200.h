@@ -31,6 +31,10 @@ int vl_device_sm_count(void);
  * vl_conv_flat) leave unused from now on, so that CTAs of the issue-bound LRN / pool kernels launched on another stream
  * can be resident next to a contraction CTA instead of queueing behind it.  0 (default): the ring takes everything. */
 int vl_set_smem_reserve(int32_t bytes);
+/* Pinned host staging memory for the frame feed (cudaHostAlloc, portable).  write_combined != 0: not snooped by the CPU
+ * caches (the host only writes the frames into it, the copy engine reads them); returns NULL on failure. */
+void* vl_host_alloc(int64_t bytes, int32_t write_combined);
+int vl_host_free(void* p);
 /* Total number of kernel launches issued through this library since load (bench.py: gpu_launches). */
 int64_t vl_launch_count(void);
 /* cudaMemsetAsync(ptr, 0, bytes) on `stream`: the gradient arena is cleared once per step (tf.gradients starts from

@@ -62,6 +62,10 @@ def _declare(L):
     L.vl_version.restype = i32
     L.vl_device_sm_count.restype = i32
     L.vl_launch_count.restype = i64
+    L.vl_host_alloc.restype = ctypes.c_void_p
+    L.vl_host_alloc.argtypes = [i64, i32]
+    L.vl_host_free.restype = i32
+    L.vl_host_free.argtypes = [vp]
     L.vl_set_smem_reserve.restype = i32
     L.vl_set_smem_reserve.argtypes = [i32]
     L.vl_grad_sqnorms_workspace.restype = i64
@@ -119,7 +123,7 @@ def _declare(L):
         fn.argtypes = argtypes
 
 
-EXPORTS = ["vl_set_smem_reserve", "vl_last_error", "vl_version", "vl_device_sm_count", "vl_launch_count", "vl_zero", "vl_gemm", "vl_conv_flat", "vl_pack_dgrad_kmajor", "vl_pack_dgrad_d2s",
+EXPORTS = ["vl_host_alloc", "vl_host_free", "vl_set_smem_reserve", "vl_last_error", "vl_version", "vl_device_sm_count", "vl_launch_count", "vl_zero", "vl_gemm", "vl_conv_flat", "vl_pack_dgrad_kmajor", "vl_pack_dgrad_d2s",
            "vl_lrn_fwd", "vl_lrn_bwd", "vl_maxpool_fwd", "vl_maxpool_bwd", "vl_colsum", "vl_pack_bf16",
            "vl_cast_f32_to_bf16", "vl_transpose_f32", "vl_gather_bf16", "vl_lstm_fwd", "vl_lstm_bwd", "vl_lstm_fwd_ex", "vl_lstm_bwd_ex", "vl_argmax_gather", "vl_fuse_list", "vl_lrn_pool_fwd", "vl_pool_lrn_bwd",
            "vl_lstm_fwd_cluster", "vl_lstm_bwd_cluster", "vl_frames_s2d", "vl_frames_s2d_crop", "vl_pack_bf16_t", "vl_s2d_pack_filter", "vl_s2d_unpack_grad",
@@ -190,3 +194,20 @@ def call(name, *args):
         else:
             conv.append(a)
     _traced(name, args, lambda: check(getattr(lib(), name)(*conv, stream_handle())))
+
+
+def host_staging_tensor(shape, dtype, write_combined=False):
+    """A pinned host tensor for the frame feed backed by vl_host_alloc (torch sees cudaHostAlloc memory as pinned, so
+    `copy_(non_blocking=True)` from it is asynchronous).  write_combined: see include/vlb200.h; fill it with
+    `tensor.copy_(...)` / numpy writes only, never read it back on the host."""
+    import numpy as np
+    import torch
+    n = int(np.prod(shape))
+    itemsize = torch.empty(0, dtype=dtype).element_size()
+    p = lib().vl_host_alloc(n * itemsize, 1 if write_combined else 0)
+    if not p:
+        raise NativeError("vlb200: %s" % lib().vl_last_error().decode())
+    buf = (ctypes.c_uint8 * (n * itemsize)).from_address(p)
+    t = torch.frombuffer(buf, dtype=dtype, count=n).view(*shape)
+    t._vl_host_ptr = p  # (kept alive for the life of the process: staging buffers are allocated once)
+    return t

@@ -42,6 +42,24 @@ extern "C" int vl_set_smem_reserve(int32_t bytes) {
   return 0;
 }
 
+// Pinned host staging memory.  write_combined = 1: cudaHostAllocWriteCombined - not snooped by the CPU caches, which
+// leaves more of the host's memory / PCIe bandwidth to the device reads when several ranks copy at once; the host must
+// only WRITE to it (reads are uncached and slow).
+extern "C" void* vl_host_alloc(int64_t bytes, int32_t write_combined) {
+  void* p = nullptr;
+  const unsigned flags = cudaHostAllocPortable | (write_combined ? cudaHostAllocWriteCombined : 0u);
+  if (bytes <= 0 || cudaHostAlloc(&p, (size_t)bytes, flags) != cudaSuccess) {
+    vl::set_error("vl_host_alloc: cudaHostAlloc of %lld bytes failed", (long long)bytes);
+    return nullptr;
+  }
+  return p;
+}
+
+extern "C" int vl_host_free(void* p) {
+  if (p != nullptr) VL_CHECK_CUDA(cudaFreeHost(p));
+  return 0;
+}
+
 extern "C" const char* vl_last_error(void) { return vl::last_error(); }
 extern "C" int vl_version(void) { return 100; }
 extern "C" int vl_device_sm_count(void) { return vl::num_sms(); }
