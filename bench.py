@@ -319,12 +319,14 @@ def run_ours(args):
         barrier()
         return max_over_ranks(e0.elapsed_time(e1))
 
+    # frames_ready=True: the device-resident inputs are complete before the timed region starts (the engine's input
+    # staging of step i+1 may then run next to the optimiser tail of step i)
     if forward_only:
         def step(i):
-            eng.forward_device(frames_dev, training=False)
+            eng.forward_device(frames_dev, training=False, frames_ready=True)
     else:
         def step(i):
-            eng.train_step(frames_dev, onehot_dev, lr_table_value(eng.global_step))
+            eng.train_step(frames_dev, onehot_dev, lr_table_value(eng.global_step), frames_ready=True)
 
     # ---- device-resident throughput (value): EXACTLY --steps timed steps ----
     sampler = ClockSampler(local_rank) if rank == 0 else None
@@ -363,13 +365,13 @@ def run_ours(args):
             fd, od, ev, done = queue.pop(0)
             if i + SLOTS - 1 < nsteps:
                 queue.append(eng.prefetch(pin_frames, pin_onehot, (i + SLOTS - 1) % SLOTS))
-            torch.cuda.current_stream().wait_event(ev)
+            torch.cuda.current_stream().wait_event(ev)  # (labels; the frames are handed over through frames_ready)
             if forward_only:
-                logits_host.copy_(eng.forward_device(fd, training=False), non_blocking=True)
+                logits_host.copy_(eng.forward_device(fd, training=False, frames_ready=ev), non_blocking=True)
                 done.record()
                 torch.cuda.current_stream().synchronize()  # the caller holds this step's logits before the next one
             else:
-                eng.train_step(fd, od, lr_table_value(eng.global_step))
+                eng.train_step(fd, od, lr_table_value(eng.global_step), frames_ready=ev)
                 done.record()
 
     e2e_steps = max(2, args.steps)

@@ -223,7 +223,10 @@ class Engine(object):
         self._scalars_ready = None
         self._norm_stream = torch.cuda.Stream(device=self.dev)  # early gradient norms (+ the early all-reduce wait)
         self._late_norms_ready = None
-        self._streams = (self._side, self._side2, self._norm_stream)
+        self._stage_stream = torch.cuda.Stream(device=self.dev)  # input staging (independent of the weights)
+        self._xs2d_free = None     # recorded after the last reader of the staging buffer (conv1 filter gradient)
+        self._frames_ready = None  # optional event of the caller: the frames are complete (else: the current stream)
+        self._streams = (self._side, self._side2, self._norm_stream, self._stage_stream)
         self._alloc_shadows()
         self._alloc_activations()
         self.load_state_dict(params if params is not None else init_variables(cfg))
@@ -602,9 +605,32 @@ class Engine(object):
         (p1h, p1w), (p2h, p2w), (p5h, p5w) = sp["pool1"], sp["pool2"], sp["pool5"]
         s1s = sp["conv1_s2d"]
         xs = A["x_s2d"][:n]
-        nv.call("vl_frames_s2d_crop", frames, 1 if is_u8 else 0, self._mean_dev(), xs, n, int(frames.shape[1]),
-                int(frames.shape[2]), crops, self.cfg.height, self.cfg.width, s1.stride, s1.pad_top, s1.pad_left,
-                s1s.h, s1s.w)
+        # The staging kernel depends on the frames only, not on the weights: it runs on its own stream and waits for
+        # (a) the frames (whatever the caller's stream has enqueued so far) and (b) the last reader of the staging
+        # buffer (conv1's filter gradient of the previous step) - NOT for the optimiser tail of the previous step, so
+        # the HBM-bound staging of step i+1 runs next to the norm / update / operand-refresh kernels of step i.
+        main = torch.cuda.current_stream()
+        overlap = self._stage_stream is not main and os.environ.get("VL_STAGE_OVERLAP", "1") != "0"
+        st = self._stage_stream if overlap else main
+        if overlap:
+            if self._frames_ready is None:  # unknown producer: everything enqueued on the caller's stream so far
+                ev = torch.cuda.Event()
+                ev.record(main)
+                st.wait_event(ev)
+            elif self._frames_ready is not True:  # the caller's event (e.g. the H2D copy of Engine.prefetch)
+                st.wait_event(self._frames_ready)
+            if self._xs2d_free is not None:
+                st.wait_event(self._xs2d_free)
+        with torch.cuda.stream(st):
+            nv.call("vl_frames_s2d_crop", frames, 1 if is_u8 else 0, self._mean_dev(), xs, n, int(frames.shape[1]),
+                    int(frames.shape[2]), crops, self.cfg.height, self.cfg.width, s1.stride, s1.pad_top, s1.pad_left,
+                    s1s.h, s1s.w)
+            if overlap:
+                staged = torch.cuda.Event()
+                staged.record(st)
+        if overlap:
+            main.wait_event(staged)
+        self._frames_ready = None
         a1 = A["a1"][:n]
         K.conv_fwd_flat(s1s, xs, sh["conv1_fwd"], self.var("dcnn/conv1b"), a1, relu=True,
                         flops=K.conv_flops(s1, n))  # tap-shifted kernel; algorithmic FLOPs of the 11x11x3 layer
@@ -688,9 +714,11 @@ class Engine(object):
     _injected_mask = None
     bwd_smem_reserve = 0  # bytes (see train_step); set from the A/B measurement in profiles/r02_step_ab.txt
 
-    def forward_device(self, frames, training=False, crops=None):
+    def forward_device(self, frames, training=False, crops=None, frames_ready=None):
         """Enqueue the forward pass; returns the device logits [clips, C] (fp32).  `crops` (int32 [n, 3]: y0, x0, mirror)
-        applies the reference's read-time crop / mirror (dataset_.py:444-461,498-500) on the device."""
+        applies the reference's read-time crop / mirror (dataset_.py:444-461,498-500) on the device.  frames_ready: see
+        train_step."""
+        self._frames_ready = frames_ready if isinstance(frames, torch.Tensor) and frames.is_cuda else None
         frames, is_u8, n = self._stage_frames(frames)
         if n % self.cfg.fpc != 0:
             raise ValueError("number of frames (%d) is not a multiple of num_frames_per_clip (%d)" % (n, self.cfg.fpc))
@@ -898,6 +926,8 @@ class Engine(object):
             K.conv_wgrad_t(s2, A["p1"][:n], G["da2"][:n], self.var2d("dcnn/conv2W", self.grads))
         if len(halves) > 1:
             main.wait_stream(self._side2)
+        self._xs2d_free = torch.cuda.Event()
+        self._xs2d_free.record()  # every conv1 filter-gradient launch (the last reader of x_s2d) is enqueued before this
         nv.call("vl_s2d_unpack_grad", self.dws1, self.var("dcnn/conv1W", self.grads), s1.kh, s1.kw, 3, 96, s1.stride)
         torch.cuda.current_stream().wait_stream(self._side)  # join: every filter gradient is in the arena
 
@@ -909,17 +939,23 @@ class Engine(object):
         used by bench.py to time each contraction launch in isolation for the roofline."""
         if serial:
             cur = torch.cuda.current_stream()
-            self._side, self._side2, self._norm_stream = cur, cur, cur
+            self._side, self._side2, self._norm_stream, self._stage_stream = cur, cur, cur, cur
         else:
-            self._side, self._side2, self._norm_stream = self._streams
+            self._side, self._side2, self._norm_stream, self._stage_stream = self._streams
 
-    def train_step(self, frames, onehot, lr, dropout_mask=None, apply_update=True, crops=None, global_clips=None):
+    def train_step(self, frames, onehot, lr, dropout_mask=None, apply_update=True, crops=None, global_clips=None,
+                   frames_ready=None):
         """One `sess.run([loss, lr, global_step, optimizer])` (run_task.py:44, train.py:199-222).
 
         frames: host/device frames of `clips * fpc` images; onehot: int32 [clips, C] (utils_.labels_to_one_hot).
         global_clips: clips of the GLOBAL batch over all data-parallel ranks (default: local clips x world); the
         loss is the mean over the global batch (train.py:123) whatever the shard sizes are.
+        frames_ready (device-resident frames only): a CUDA event after which the frames are complete (the H2D copy of
+        Engine.prefetch), or True when they have been complete all along; the input staging then waits for exactly
+        that instead of for everything enqueued on the caller's stream, i.e. it overlaps the optimiser tail of the
+        previous step.  None: no assumption.
         Returns (loss, lr, global_step, accuracy, grads_norm) with global_step already incremented."""
+        self._frames_ready = frames_ready if isinstance(frames, torch.Tensor) and frames.is_cuda else None
         cfg, A = self.cfg, self.A
         if self.G is None:
             self._alloc_backward()
