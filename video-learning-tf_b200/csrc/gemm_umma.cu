@@ -30,7 +30,8 @@ typedef __nv_bfloat16 bf16;
 constexpr int BM = 128;                     // UMMA M (cta_group::1)
 constexpr int BK = 64;                      // bf16 elements per k-block = one 128B swizzle row
 constexpr int A_SUB_BYTES = BM * BK * 2;    // 16 KB per 128-row sub-tile and k-block
-constexpr int NUM_THREADS = 192;            // warp0 TMA, warp1 MMA (+TMEM alloc), warps 2..5 epilogue
+constexpr int EPI_GROUPS = 2;               // epilogue groups of four warps (one warp per TMEM lane quadrant and group)
+constexpr int NUM_THREADS = 64 + EPI_GROUPS * 128;  // warp0 TMA, warp1 MMA (+TMEM alloc), then the epilogue warps
 constexpr int TMEM_COLS = 512;              // 2 accumulator stages x 256 fp32 columns
 constexpr int ACC_STRIDE_COLS = 256;
 constexpr int MAX_STAGES = 8;
@@ -137,7 +138,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], 4);
+      mbar_init(&tmem_empty[s], 4 * EPI_GROUPS);
     }
     fence_barrier_init();
   }
@@ -397,7 +398,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     }
   } else {
     // ===================== epilogue warps (TMEM -> registers -> HBM) =====================
+    // Two groups of four warps share a tile: warp % 4 selects the TMEM lane quadrant, (warp - 2) / 4 the group; group g
+    // drains the 16-column chunks g, g + 2, g + 4, ...  A single warp sustains ~650 cycles per chunk, so the short-K
+    // products (fc filter gradients: 16 k-blocks per 128 x 256 fp32 tile; conv5; the LSTM / head matrices) were bound by
+    // four warps draining 16 chunks per sub-tile while the tensor pipe waited for the accumulator stage.
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    const int grp = (warp - 2) >> 2;
     const int epi_tid = threadIdx.x - 64;
     int local = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
@@ -410,11 +416,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
       const int gcol0 = t.g * p.c_goff + n0;  // global column of tile column 0
       // stage this tile's bias slice in shared memory once (instead of one global load per element)
       if (p.bias != nullptr) {
-        asm volatile("bar.sync 1, 128;" ::: "memory");  // previous tile's readers are done
+        asm volatile("bar.sync 1, %0;" ::"n"(EPI_GROUPS * 128) : "memory");  // previous tile's readers are done
         // split-K (atomic fp32 output): only the split that owns the first k-block adds the bias
-        for (int j = epi_tid; j < BN; j += 128)
+        for (int j = epi_tid; j < BN; j += EPI_GROUPS * 128)
           sbias[j] = (n0 + j < p.N && t.kb_begin == 0) ? __ldg(p.bias + gcol0 + j) : 0.f;
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(EPI_GROUPS * 128) : "memory");
       }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
@@ -578,26 +584,30 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
           }
         };
 
-        // software pipelined TMEM drain: the load of chunk i+1 is in flight while chunk i is processed
+        // software pipelined TMEM drain over this group's chunks (stride 16 * EPI_GROUPS columns): the load of the
+        // group's next chunk is in flight while the current one is processed; ReLU-gradient masks one chunk ahead
+        constexpr int CSTEP = 16 * EPI_GROUPS;
         uint32_t va[16], vb[16];
-        uint4 ma[2], mb[2], na[2], nb[2];
-        ma[0] = ma[1] = mb[0] = mb[1] = na[0] = na[1] = nb[0] = nb[1] = make_uint4(0, 0, 0, 0);
-        fetch_mask(0, ma);
-        fetch_mask(16, mb);
-        tmem_ld_x16(taddr, va);
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-          fetch_mask(c0 + 32, na);
-          fetch_mask(c0 + 48, nb);
+        uint4 ma[2], mb[2];
+        ma[0] = ma[1] = mb[0] = mb[1] = make_uint4(0, 0, 0, 0);
+        const int cfirst = grp * 16;
+        if (cfirst < BN) {
+          fetch_mask(cfirst, ma);
+          tmem_ld_x16(taddr + cfirst, va);
+        }
+        for (int c0 = cfirst; c0 < BN; c0 += 2 * CSTEP) {
+          const bool has_b = c0 + CSTEP < BN;
+          if (has_b) fetch_mask(c0 + CSTEP, mb);
           tmem_ld_wait();
-          const bool has_b = c0 + 16 < BN;
-          if (has_b) tmem_ld_x16(taddr + c0 + 16, vb);
+          if (has_b) tmem_ld_x16(taddr + c0 + CSTEP, vb);
           process(va, c0, ma);
           if (has_b) {
+            const bool has_a = c0 + 2 * CSTEP < BN;
+            if (has_a) fetch_mask(c0 + 2 * CSTEP, ma);
             tmem_ld_wait();
-            if (c0 + 32 < BN) tmem_ld_x16(taddr + c0 + 32, va);
-            process(vb, c0 + 16, mb);
+            if (has_a) tmem_ld_x16(taddr + c0 + 2 * CSTEP, va);
+            process(vb, c0 + CSTEP, mb);
           }
-          ma[0] = na[0], ma[1] = na[1], mb[0] = nb[0], mb[1] = nb[1];
         }
       }
       tc_fence_before();
