@@ -535,6 +535,7 @@ class Engine(object):
                 from .resize import DeviceResizer
                 self._resizer = DeviceResizer(self.dev)
             frames = self._resizer.resize(frames, int(self.read_resize[0]), int(self.read_resize[1]))
+            self._frames_ready = None  # produced on the caller's stream just now
         return frames, frames.dtype == torch.uint8, n
 
     def set_read_resize(self, hw):
@@ -560,6 +561,7 @@ class Engine(object):
                     (c[:, 1] + self.cfg.width > wr).any():
                 raise ValueError("crop window leaves the stored %dx%d frame" % (hr, wr))
             self._crops_dev[:n].copy_(crops, non_blocking=True)
+            self._frames_ready = None  # the offsets travel on the caller's stream: the staging must wait for it
             return self._crops_dev[:n]
         # device-resident offsets: not validated here (that would synchronise); the staging kernel clamps them
         # into the stored frame, so an out-of-range window cannot read outside the buffer
