@@ -31,7 +31,8 @@ constexpr int BM = 128;                     // UMMA M (cta_group::1)
 constexpr int BK = 64;                      // bf16 elements per k-block = one 128B swizzle row
 constexpr int A_SUB_BYTES = BM * BK * 2;    // 16 KB per 128-row sub-tile and k-block
 constexpr int EPI_GROUPS = 2;               // epilogue groups of four warps (one warp per TMEM lane quadrant and group)
-constexpr int NUM_THREADS = 64 + EPI_GROUPS * 128;  // warp0 TMA, warp1 MMA (+TMEM alloc), then the epilogue warps
+constexpr int PROD2_WARP = 2 + EPI_GROUPS * 4;   // second TMA producer (odd k-blocks), after the epilogue warps
+constexpr int NUM_THREADS = 64 + EPI_GROUPS * 128 + 32;  // warp0 TMA, warp1 MMA (+TMEM alloc), epilogue warps, warp PROD2 TMA
 constexpr int TMEM_COLS = 512;              // 2 accumulator stages x 256 fp32 columns
 constexpr int ACC_STRIDE_COLS = 256;
 constexpr int MAX_STAGES = 8;
@@ -79,6 +80,7 @@ struct KParams {
   int ksteps_tail;  // UMMA K-steps (of 16) that carry data in the last channel chunk of a tap / last dense k-block
   int mn_step_rows, mn_step_rem;  // transposed im2col: 64 pixels = mn_step_rows image rows + mn_step_rem pixels
   int dbg;  // development probes (VL_GEMM_DBG): 1 = no MMA, 2 = no A loads, 4 = no B loads, 8 = no stores
+  int producers;  // 1: warp 0 stages every k-block; 2: warp 0 the even, warp PROD2_WARP the odd k-blocks (see the producer)
 };
 
 __device__ __forceinline__ void tma_load_tiled_4d_u32(uint32_t dst, const CUtensorMap* m, uint32_t bar, int32_t c0,
@@ -160,8 +162,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
   const int BN = p.BN;
   const uint32_t a_tile_bytes = (uint32_t)msub * A_SUB_BYTES;
 
-  if (warp == 0) {
-    // ===================== TMA producer =====================
+  if (warp == 0 || (warp == PROD2_WARP && p.producers == 2)) {
+    // ===================== TMA producer(s) =====================
+    // A producer iteration costs ~90 dependent single-warp instructions (barrier wait, R2UR moves of the box
+    // coordinates, one UTMALDG per box, walk advance): ~390 cycles, which is as long as the four UMMAs of a short k-block
+    // (filter gradients: 128 x 192..256 x 64 per k-block; profiles/r02_bwd_stage_decomposition.txt).  With two producer
+    // warps every k-block is staged by exactly one of them (running k-block counter parity); both walk the full
+    // contraction state, only the owner waits for the slot and issues the loads.
+    const int prod_id = warp == 0 ? 0 : 1;
+    const bool two_prod = p.producers == 2;
+    int kcount = 0;  // running k-block counter over all tiles of this CTA
     // The k-block loop stays free of integer divisions: the (tap, channel-chunk) and pixel coordinates advance
     // with adds and compares only; the per-tile set-up uses multiply-shift division.
     const int cchunks = p.cchunks, kw = p.kw, taps = p.taps;
@@ -246,12 +256,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
                                : (BMODE == VL_B_IM2COL_MN ? (p.row_shift ? (uint32_t)(64 + p.kw - 1) * 128u : 8192u * b_valid)
                                                           : (uint32_t)p.b_stage_bytes);
       const uint32_t bytes = b_bytes + a_bytes;
-      for (int kb = t.kb_begin; kb < t.kb_end; ++kb) {
-        mbar_wait_u32(empty_u32 + stage * 8, phase ^ 1u);
+      for (int kb = t.kb_begin; kb < t.kb_end; ++kb, ++kcount) {
+        const bool mine = !two_prod || (kcount & 1) == prod_id;
+        if (mine) mbar_wait_u32(empty_u32 + stage * 8, phase ^ 1u);
         const uint32_t sA = tiles_u32 + stage * stage_bytes;
         const uint32_t sB = sA + a_tile_bytes;
         const uint32_t fb = full_u32 + stage * 8;
-        if (elect_one()) {
+        if (mine && elect_one()) {
           mbar_expect_tx_u32(fb, bytes);
           // ---- A ----
           if (ld_a) {
@@ -396,7 +407,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
       if (elect_one()) umma_commit_u32(smem_u32(&tmem_full[acc]));  // accumulator complete -> epilogue
       __syncwarp();
     }
-  } else {
+  } else if (warp < PROD2_WARP) {
     // ===================== epilogue warps (TMEM -> registers -> HBM) =====================
     // Two groups of four warps share a tile: warp % 4 selects the TMEM lane quadrant, (warp - 2) / 4 the group; group g
     // drains the 16-column chunks g, g + 2, g + 4, ...  A single warp sustains ~650 cycles per chunk, so the short-K
@@ -615,7 +626,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
     }
   }
-
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -882,6 +892,9 @@ extern "C" int vl_gemm(const vl_gemm_desc* d, const void* a, const void* b, void
   {
     const char* e = getenv("VL_GEMM_DBG");
     p.dbg = e ? atoi(e) : 0;
+    const char* e2 = getenv("VL_GEMM_PRODUCERS");
+    p.producers = e2 ? atoi(e2) : 2;
+    if (p.producers != 1) p.producers = 2;
   }
   // ---- epilogue ----
   p.C = c;
