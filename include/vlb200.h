@@ -342,6 +342,32 @@ int vl_adam_update(float* params, const float* grads, float* m, float* v, int64_
                    float beta2, float eps, int32_t step, const float* scalars, float grad_prescale,
                    vl_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * fp32-accuracy forward mode (csrc/fp32_path.cu; host side: video-learning-tf_b200/fp32_path.py).
+ * The reference evaluates its graph in fp32 (models/alexnet/alexnet.py:60-280, models/lstm/lstm.py:59-143); the tensor
+ * cores take bf16 operands.  For the "<= 1e-3 relative in fp32" tolerance every fp32 tensor X is split into
+ * X_hi = bf16(X), X_lo = bf16(X - X_hi) and X * W is evaluated as X_hi W_hi + X_lo W_hi + X_hi W_lo by ONE vl_gemm over
+ * operands concatenated along the contraction axis: [X_hi | X_lo | X_hi] x [W_hi ; W_hi ; W_lo] (fp32 accumulation and
+ * output, bias / ReLU in the epilogue).  These entry points build those operands and run the non-contraction layers in
+ * fp32.
+ * ---------------------------------------------------------------------------------------------- */
+/* x[rows][c] fp32 (c = groups * cg) -> out[rows][3c] bf16, group g = [hi(cg) | lo(cg) | hi(cg)] at column g * 3 * cg. */
+int vl_split3_act(const float* x, void* out, int64_t rows, int32_t c, int32_t groups, vl_stream_t stream);
+/* w[rows][cols] fp32 ([in, out] layout of tf.nn.xw_plus_b, alexnet.py:228,248,275) -> out[3 * rows][dst_ld] bf16 =
+ * [hi ; hi ; lo], columns >= cols zero. */
+int vl_split3_weight(const float* w, void* out, int64_t rows, int32_t cols, int32_t dst_ld, vl_stream_t stream);
+/* vl_gather_bf16 with a hi / lo selector: dst[i] = hi or lo part (bit 30 of table[i] set: lo) of src[table[i] & 0x3fffffff],
+ * 0 where table[i] < 0.  Builds the permuted K-major convolution filters [W_hi | W_hi | W_lo] of the mode in one launch. */
+int vl_gather_split_bf16(const float* src, const int32_t* table, void* dst, int64_t n, vl_stream_t stream);
+/* vl_frames_s2d_crop with an fp32 result (same arguments and semantics; dataset_.py:444-461,498-500,521-530). */
+int vl_frames_s2d_f32(const void* frames, int32_t is_u8, const float* mean3, float* out, int32_t n, int32_t hr, int32_t wr,
+                      const int32_t* crops, int32_t h, int32_t w, int32_t s, int32_t pad_top, int32_t pad_left, int32_t hb,
+                      int32_t wb, vl_stream_t stream);
+/* tf.nn.lrn (alexnet.py:80-89,121-130) + tf.nn.max_pool 3x3 / 2 VALID (alexnet.py:98,139,211) on fp32 NHWC tensors:
+ * y[n][(h-3)/2+1][(w-3)/2+1][c]; with_lrn == 0: max-pool only (pool5). */
+int vl_lrn_pool_fwd_f32(const float* x, float* y, int32_t n, int32_t h, int32_t w, int32_t c, int32_t radius, float alpha,
+                        float beta, float bias, int32_t with_lrn, vl_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -116,6 +116,11 @@ def _declare(L):
         "vl_sgd_update": [vp, vp, i64, f32, vp, f32, vp],
         "vl_sgd_update_shadow": [vp, vp, i64, f32, vp, f32, i32, vp, vp, vp, vp],
         "vl_adam_update": [vp, vp, vp, vp, i64, f32, f32, f32, f32, i32, vp, f32, vp],
+        "vl_split3_act": [vp, vp, i64, i32, i32, vp],
+        "vl_split3_weight": [vp, vp, i64, i32, i32, vp],
+        "vl_gather_split_bf16": [vp, vp, vp, i64, vp],
+        "vl_frames_s2d_f32": [vp, i32, vp, vp, i32, i32, i32, vp, i32, i32, i32, i32, i32, i32, i32, vp],
+        "vl_lrn_pool_fwd_f32": [vp, vp, i32, i32, i32, i32, i32, f32, f32, f32, i32, vp],
     }
     for name, argtypes in sigs.items():
         fn = getattr(L, name)
@@ -129,7 +134,8 @@ EXPORTS = ["vl_host_alloc", "vl_host_free", "vl_set_smem_reserve", "vl_last_erro
            "vl_lstm_fwd_cluster", "vl_lstm_bwd_cluster", "vl_frames_s2d", "vl_frames_s2d_crop", "vl_pack_bf16_t", "vl_s2d_pack_filter", "vl_s2d_unpack_grad",
            "vl_lrn_pool_fwd_generic", "vl_pool_lrn_bwd_generic", "vl_segment_pool_fwd",
            "vl_segment_pool_bwd", "vl_segment_pool_fwd_bf16", "vl_segment_pool_bwd_relu_bf16", "vl_dropout_mask", "vl_mul", "vl_softmax_ce", "vl_grad_sqnorms", "vl_grad_sqnorms_workspace",
-           "vl_clip_scalars", "vl_resize_bilinear_u8", "vl_sgd_update", "vl_sgd_update_shadow", "vl_adam_update"]
+           "vl_clip_scalars", "vl_resize_bilinear_u8", "vl_sgd_update", "vl_sgd_update_shadow", "vl_adam_update",
+           "vl_split3_act", "vl_split3_weight", "vl_gather_split_bf16", "vl_frames_s2d_f32", "vl_lrn_pool_fwd_f32"]
 
 
 def check(status):

@@ -376,6 +376,7 @@ class Engine(object):
         """fp32 master -> bf16 tensor-core operands (after load and after every optimiser step).  plain_done: the
         same-layout copies (fc6, fc7, LSTM kernels) were already written by vl_sgd_update_shadow."""
         sh = self.sh
+        self.weights_version = getattr(self, "weights_version", 0) + 1  # derived operand sets (fp32_path) rebuild lazily
         nv.call("vl_gather_bf16", self.params, self._shadow_table, self._shadow_arena, self._shadow_arena.numel())
         for name in ("fc6", "fc7"):
             if name in sh and not plain_done:
@@ -735,8 +736,21 @@ class Engine(object):
         return self._encoder_fwd(frames, is_u8, n, False, self._stage_crops(crops, frames, n))
 
     def forward(self, frames, crops=None):
-        """`sess.run(model.logits, fdict)` (run_task.py:95): float32 ndarray [clips, C] on the host."""
+        """`sess.run(model.logits, fdict)` (run_task.py:95): float32 ndarray [clips, C] on the host.
+        VLB200_FP32=1 in the environment routes it (and with it the validation workflow of run_task / tfshim) through
+        the fp32-accuracy mode."""
+        if os.environ.get("VLB200_FP32", "0") == "1":
+            return self.forward_fp32(frames, crops)
         return self.forward_device(frames, training=False, crops=crops).cpu().numpy()
+
+    def forward_fp32(self, frames, crops=None):
+        """The same logits in fp32 ACCURACY (<= 1e-3 relative against the reference's fp32 graph; north-star tolerance):
+        every tensor stays fp32 and the contractions run as hi / lo bf16 split products on the tensor cores
+        (fp32_path.py).  About 3x the cost of `forward`; for validation read-outs."""
+        if getattr(self, "_fp32", None) is None:
+            from .fp32_path import Fp32Path
+            self._fp32 = Fp32Path(self)
+        return self._fp32.forward_device(frames, crops=crops).cpu().numpy()
 
     # ------------------------------------------------------------------------------------------
     # backward

@@ -64,3 +64,42 @@ def col_padded(rows, cols, dst_ld):
     """vl_pack_bf16 with one group: dst[r][c] = src[r][c] for c < cols, zero padded to dst_ld columns."""
     r, c = np.meshgrid(np.arange(rows), np.arange(dst_ld), indexing="ij")
     return np.where(c < cols, r * cols + c, -1).reshape(-1)
+
+
+# ------------------------------------------------------------------------------------------------
+# fp32-accuracy mode (fp32_path.py): K-major filters [W_hi | W_hi | W_lo] along the input-channel axis.
+# Table entries index the fp32 source; bit 30 selects the lo part (vl_gather_split_bf16).
+# ------------------------------------------------------------------------------------------------
+LO_FLAG = 1 << 30
+
+
+def split3_kmajor(taps, cin_g, cout, dst_grp):
+    """dst[col][tap * dst_grp + part * cin_g + c] = {hi, hi, lo}[part] of src[tap * cin_g + c][col] (src = HWIO seen as
+    [taps * cin_g, cout]); columns beyond 3 * cin_g of a tap are zero padding."""
+    assert dst_grp >= 3 * cin_g
+    col, kk = np.meshgrid(np.arange(cout), np.arange(taps * dst_grp), indexing="ij")
+    tap, rr = kk // dst_grp, kk % dst_grp
+    part, c = rr // cin_g, rr % cin_g
+    valid = rr < 3 * cin_g
+    idx = (tap * cin_g + c) * cout + col
+    idx = np.where(part == 2, idx | LO_FLAG, idx)
+    return np.where(valid, idx, -1).reshape(-1)
+
+
+def split3_s2d_kmajor(kh, kw, cin, cout, s, dst_grp):
+    """The same for the space-to-depth conv1: dst[o][tap * dst_grp + part * (s*s*cin) + (dy*s+dx)*cin + c] =
+    {hi, hi, lo}[part] of src[s*tr+dy][s*ts+dx][c][o] (-1 where the tap leaves the kh x kw filter)."""
+    kb_h, kb_w = -(-kh // s), -(-kw // s)
+    blk = s * s * cin
+    assert dst_grp >= 3 * blk
+    o, row = np.meshgrid(np.arange(cout), np.arange(kb_h * kb_w * dst_grp), indexing="ij")
+    tap, rr = row // dst_grp, row % dst_grp
+    part, j = rr // blk, rr % blk
+    tr, ts = tap // kb_w, tap % kb_w
+    c, dd = j % cin, j // cin
+    dy, dx = dd // s, dd % s
+    r, q = s * tr + dy, s * ts + dx
+    valid = (rr < 3 * blk) & (r < kh) & (q < kw)
+    idx = ((r * kw + q) * cin + c) * cout + o
+    idx = np.where(part == 2, idx | LO_FLAG, idx)
+    return np.where(valid, idx, -1).reshape(-1)
