@@ -935,6 +935,185 @@ __global__ void __launch_bounds__(THREADS, MINB)
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Fourth generation of the fused forward: registers and warp shuffles only - no shared memory, no CTA barrier (the top
+// stall of the row-ring kernel), every lrn(x) evaluated (almost) once, separable pooling.
+//
+// A WARP walks down the image rows of a strip of input columns.  A group of LPP lanes holds one pixel's channel slice
+// (NE channels per lane, LPP * NE per slice, SLICES slices per pixel: the channel halo of a slice's outer lanes is read
+// straight from global memory, the inner halos travel by shuffle); group u of the warp owns the input column pair
+// (2q, 2q+1) of pooled column q = U * cb + u and receives column 2q+2 - the first column of group u+1, already normalised
+// and packed - by one shuffle per bf16 pair.  The last group (u = G-1) only feeds its left neighbour, so U = G-1 of the
+// G groups produce output (for the two AlexNet geometries: Q = 28 = 4 x 7 and Q = 13 <= 2 x 7).  Per input row the
+// three-column maximum and its column code are formed once (horizontal pass); the vertical pass merges the rows 2p, 2p+1,
+// 2p+2 of pooled row p and row 2p+2 is carried over as row 0 of pooled row p+1.  Strict '>' in (row, column) scan order
+// keeps TF's first-maximum rule.  The next row's pixels are fetched before the current row is processed.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t gt_bf16x2(uint32_t a, uint32_t b) {
+  uint32_t m;
+  asm("set.gt.u32.bf16x2 %0, %1, %2;" : "=r"(m) : "r"(a), "r"(b));
+  return m;
+}
+__device__ __forceinline__ uint32_t max_bf16x2(uint32_t a, uint32_t b) {
+  uint32_t m;
+  asm("max.bf16x2 %0, %1, %2;" : "=r"(m) : "r"(a), "r"(b));
+  return m;
+}
+
+template <int NE, int LPP, int SLICES, int C_, int H_, int W_>
+__global__ void __launch_bounds__(128, 4)
+    lrn_pool_fwd_kernel4(const bf16* __restrict__ x, bf16* __restrict__ y, uint8_t* __restrict__ arg, int n, int seg_rows,
+                         int segs, float alpha, float bias) {
+  constexpr int P = (H_ - 3) / 2 + 1, Q = (W_ - 3) / 2 + 1;
+  constexpr int G = 32 / LPP, U = G - 1;
+  constexpr int WPR = (Q + U - 1) / U;  // column blocks (warps) per image row
+  constexpr int CS = LPP * NE;          // channels of a slice
+  constexpr int NP = NE / 2;            // bf16 pairs per lane
+  constexpr int ROW = W_ * C_;
+  static_assert(CS * SLICES == C_ && NE % 8 == 0, "slices x lanes x channels per lane must cover the channel axis");
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int u = lane / LPP, l = lane % LPP;
+  const long long items = (long long)n * segs * SLICES * WPR;
+  for (long long item = (long long)blockIdx.x * 4 + wib; item < items; item += (long long)gridDim.x * 4) {
+    long long rest = item;
+    const int cb = (int)(rest % WPR);
+    rest /= WPR;
+    const int sl = (int)(rest % SLICES);
+    rest /= SLICES;
+    const int sg = (int)(rest % segs);
+    const int nn = (int)(rest / segs);
+    const int p0 = sg * seg_rows, p1 = min(P, p0 + seg_rows);
+    if (p0 >= p1) continue;
+    const int q = U * cb + u;  // pooled column of this group
+    const int col0 = 2 * q;    // owned input columns col0, col0 + 1
+    const bool ok0 = col0 < W_, ok1 = col0 + 1 < W_;
+    const bool out_ok = u < U && q < Q;
+    const int ch0 = sl * CS + l * NE;
+    const bool halo_l = SLICES > 1 && l == 0 && sl > 0;
+    const bool halo_r = SLICES > 1 && l == LPP - 1 && sl < SLICES - 1;
+    const bf16* xcol = x + (long long)nn * (H_ * ROW) + (long long)col0 * C_ + ch0;
+
+    // raw pixels of one input row: the two owned columns (+ the packed channel halo pairs of the slice's outer lanes)
+    struct RowRegs {
+      uint32_t px[2][NP];
+      uint32_t hl[2], hr[2];
+    };
+    auto fetch = [&](int r, RowRegs& t) {
+      const bf16* rp = xcol + (long long)r * ROW;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const bool ok = c == 0 ? ok0 : ok1;
+        if (ok) {
+          load_pairs<NE>(rp + c * C_, t.px[c]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < NP; ++i) t.px[c][i] = 0u;
+        }
+        t.hl[c] = (halo_l && ok) ? __ldg(reinterpret_cast<const uint32_t*>(rp + c * C_ - 2)) : 0u;
+        t.hr[c] = (halo_r && ok) ? __ldg(reinterpret_cast<const uint32_t*>(rp + c * C_ + NE)) : 0u;
+      }
+    };
+    // lrn of one pixel slice -> packed bf16 pairs
+    auto normalise = [&](const uint32_t (&xr)[NP], uint32_t hl, uint32_t hr, uint32_t (&o)[NP]) {
+      float v[NE], e[NE + 4];
+#pragma unroll
+      for (int i = 0; i < NP; ++i) {
+        v[2 * i] = __uint_as_float(xr[i] << 16);
+        v[2 * i + 1] = __uint_as_float(xr[i] & 0xffff0000u);
+      }
+#pragma unroll
+      for (int j = 0; j < NE; ++j) e[2 + j] = v[j] * v[j];
+      float lf0 = __shfl_up_sync(0xffffffffu, e[NE], 1, LPP);
+      float lf1 = __shfl_up_sync(0xffffffffu, e[NE + 1], 1, LPP);
+      float rt0 = __shfl_down_sync(0xffffffffu, e[2], 1, LPP);
+      float rt1 = __shfl_down_sync(0xffffffffu, e[3], 1, LPP);
+      if (l == 0) {
+        const float a = __uint_as_float(hl << 16), b = __uint_as_float(hl & 0xffff0000u);
+        lf0 = a * a;
+        lf1 = b * b;
+      }
+      if (l == LPP - 1) {
+        const float a = __uint_as_float(hr << 16), b = __uint_as_float(hr & 0xffff0000u);
+        rt0 = a * a;
+        rt1 = b * b;
+      }
+      e[0] = lf0, e[1] = lf1, e[NE + 2] = rt0, e[NE + 3] = rt1;
+      // window sums with 2 adds per channel and no cancellation: for even j, q4 = e[j+1..j+4] (two pair sums at odd
+      // offsets, each shared by two q4), w[j] = e[j] + q4, w[j+1] = q4 + e[j+5]
+      float pr[NP + 1];
+#pragma unroll
+      for (int k = 0; k <= NP; ++k) pr[k] = e[2 * k + 1] + e[2 * k + 2];
+#pragma unroll
+      for (int i = 0; i < NP; ++i) {
+        const float q4 = pr[i] + pr[i + 1];
+        const float w0 = e[2 * i] + q4, w1 = q4 + e[2 * i + 5];
+        const float r0s = rsqrt_approx(fmaf(alpha, w0, bias));
+        const float r1s = rsqrt_approx(fmaf(alpha, w1, bias));
+        const __nv_bfloat162 pk =
+            __floats2bfloat162_rn(v[2 * i] * (r0s * sqrt_approx(r0s)), v[2 * i + 1] * (r1s * sqrt_approx(r1s)));
+        o[i] = *reinterpret_cast<const uint32_t*>(&pk);
+      }
+    };
+    // one input row: normalise the two owned columns, take column 2q+2 from the next group, three-column maximum + code
+    auto hrow = [&](const RowRegs& t, uint32_t (&hb)[NP], uint32_t (&hc)[NP]) {
+      uint32_t n0[NP], n1[NP];
+      normalise(t.px[0], t.hl[0], t.hr[0], n0);
+      normalise(t.px[1], t.hl[1], t.hr[1], n1);
+#pragma unroll
+      for (int i = 0; i < NP; ++i) {
+        const uint32_t n2 = __shfl_down_sync(0xffffffffu, n0[i], LPP);
+        const uint32_t m1 = gt_bf16x2(n1[i], n0[i]);
+        uint32_t b = max_bf16x2(n0[i], n1[i]);
+        uint32_t c = m1 & 0x00010001u;
+        const uint32_t m2 = gt_bf16x2(n2, b);
+        b = max_bf16x2(b, n2);
+        c = (c & ~m2) | (0x00020002u & m2);
+        hb[i] = b, hc[i] = c;
+      }
+    };
+
+    // two row buffers used alternately (no register copies): at the top of iteration p, ra holds input row 2p+1
+    RowRegs ra, rb;
+    uint32_t ab[NP], ac[NP], hb[NP], hc[NP];
+    fetch(2 * p0, rb);
+    fetch(2 * p0 + 1, ra);
+    hrow(rb, ab, ac);  // window row 0 of pooled row p0
+    for (int p = p0; p < p1; ++p) {
+      // window row 1
+      fetch(2 * p + 2, rb);
+      hrow(ra, hb, hc);
+#pragma unroll
+      for (int i = 0; i < NP; ++i) {
+        const uint32_t m = gt_bf16x2(hb[i], ab[i]);
+        ab[i] = max_bf16x2(ab[i], hb[i]);
+        ac[i] = (ac[i] & ~m) | ((hc[i] + 0x00030003u) & m);
+      }
+      // window row 2 (= window row 0 of pooled row p + 1)
+      if (p + 1 < p1) fetch(2 * p + 3, ra);
+      hrow(rb, hb, hc);
+#pragma unroll
+      for (int i = 0; i < NP; ++i) {
+        const uint32_t m = gt_bf16x2(hb[i], ab[i]);
+        ab[i] = max_bf16x2(ab[i], hb[i]);
+        ac[i] = (ac[i] & ~m) | ((hc[i] + 0x00060006u) & m);
+      }
+      if (out_ok) {
+        const long long opix = (((long long)nn * P + p) * Q + q) * C_ + ch0;
+        store_pairs<NE>(y + opix, ab);
+#pragma unroll
+        for (int k = 0; k < NE / 8; ++k) {
+          const uint32_t lo = __byte_perm(ac[4 * k], ac[4 * k + 1], 0x6420);
+          const uint32_t hi = __byte_perm(ac[4 * k + 2], ac[4 * k + 3], 0x6420);
+          *reinterpret_cast<uint2*>(arg + opix + 8 * k) = make_uint2(lo, hi);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < NP; ++i) ab[i] = hb[i], ac[i] = hc[i];
+    }
+  }
+}
+
 }  // namespace
 
 #define VL_LAUNCHED()                  \
@@ -1026,6 +1205,29 @@ extern "C" int vl_lrn_pool_fwd(const void* x, void* y, void* argmax, int32_t n, 
   for (int r = 1; r <= p; ++r)
     if ((size_t)(2 * r + 1) * row_bytes <= strip_limit) rows_out = r;
   // third generation (row ring, compile-time geometry): the two AlexNet instances
+  // fourth generation (registers + shuffles, no shared memory): the two AlexNet instances
+  if (!getenv("VL_LRN_FWD_V2") && !getenv("VL_LRN_FWD_V3") &&
+      ((c == 96 && h == 57 && w == 57) || (c == 256 && h == 28 && w == 28))) {
+    const int segs = c == 96 ? 4 : 2;  // row segments per image: one re-normalised input row per extra segment
+    const int seg_rows = (p + segs - 1) / segs;
+    const int wpr = c == 96 ? 4 : 2, slices = c == 96 ? 1 : 4;
+    const long long items = (long long)n * segs * slices * wpr;
+    const long long want = (items + 3) / 4;
+    const long long cap = (long long)vl::num_sms() * (getenv("VL_LRN_FWD_CTAS") ? atoi(getenv("VL_LRN_FWD_CTAS")) : 16);
+    const int g = (int)(want < cap ? want : cap);
+    // (measured, profiles/r02_lrn_fwd4.txt: 5 / 6 CTAs per SM only by spilling - slower; a grid of 16 CTAs per SM lets
+    // the block scheduler even out the tail)
+    if (c == 96)
+      lrn_pool_fwd_kernel4<24, 4, 1, 96, 57, 57><<<g, 128, 0, stream>>>(
+          reinterpret_cast<const bf16*>(x), reinterpret_cast<bf16*>(y), reinterpret_cast<uint8_t*>(argmax), n, seg_rows, segs,
+          alpha, bias);
+    else
+      lrn_pool_fwd_kernel4<16, 4, 4, 256, 28, 28><<<g, 128, 0, stream>>>(
+          reinterpret_cast<const bf16*>(x), reinterpret_cast<bf16*>(y), reinterpret_cast<uint8_t*>(argmax), n, seg_rows, segs,
+          alpha, bias);
+    VL_LAUNCHED();
+    return 0;
+  }
   if (!getenv("VL_LRN_FWD_V2") && ((c == 96 && h == 57 && w == 57) || (c == 256 && h == 28 && w == 28))) {
     const int ring_bytes = 5 * (int)row_bytes;
     const int per_sm_smem = (227 * 1024) / (ring_bytes + 1024);
