@@ -133,8 +133,17 @@ __device__ __forceinline__ void window5n(const float (&v)[NE], int l, float (&w)
   for (int j = 0; j < NE; ++j) e[2 + j] = v[j];
   e[NE + 2] = rt[0];
   e[NE + 3] = rt[1];
+  // 2 adds per channel (was 3 after common-subexpression elimination): for even j, q4 = e[j+1..j+4] from two pair sums at
+  // odd offsets (each shared by two q4), w[j] = e[j] + q4, w[j+1] = q4 + e[j+5]; NE is even
+  float pr[NE / 2 + 1];
 #pragma unroll
-  for (int j = 0; j < NE; ++j) w[j] = ((e[j] + e[j + 1]) + e[j + 2]) + (e[j + 3] + e[j + 4]);
+  for (int k = 0; k <= NE / 2; ++k) pr[k] = e[2 * k + 1] + e[2 * k + 2];
+#pragma unroll
+  for (int i = 0; i < NE / 2; ++i) {
+    const float q4 = pr[i] + pr[i + 1];
+    w[2 * i] = e[2 * i] + q4;
+    w[2 * i + 1] = q4 + e[2 * i + 5];
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
