@@ -1,5 +1,5 @@
-"""Fused LRN + pool forward: register / shuffle kernel (fourth generation, default) against the shared-memory row-ring
-kernel (VL_LRN_FWD_V3=1) on both AlexNet geometries: pooled values and argmax codes compared, then timed."""
+"""Fused LRN + pool forward: register / shuffle kernel (fourth generation, default) against the shared-memory strip
+kernel (VL_LRN_FWD_V2=1; the row-ring kernel of profiles/r02_lrn_fwd4.txt has been removed) on both AlexNet geometries: pooled values and argmax codes compared, then timed."""
 import os, sys
 sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", ".."))
 import torch
@@ -24,11 +24,11 @@ for (h, c) in ((57, 96), (28, 256)):
     x = (torch.randn(n, h, h, c, device="cuda") * 60).clamp_(min=0).to(torch.bfloat16)
     fwd_bytes = n * c * (h * h * 2 + p * p * 3)
     outs = {}
-    for mode in ("v3", "v4"):
+    for mode in ("v3", "v4"):  # "v3" = the reference kernel of the comparison (strip kernel)
         if mode == "v3":
-            os.environ["VL_LRN_FWD_V3"] = "1"
+            os.environ["VL_LRN_FWD_V2"] = "1"
         else:
-            os.environ.pop("VL_LRN_FWD_V3", None)
+            os.environ.pop("VL_LRN_FWD_V2", None)
         y = torch.full((n, p, p, c), float("nan"), device="cuda", dtype=torch.bfloat16)
         arg = torch.full((n, p, p, c), 255, device="cuda", dtype=torch.uint8)
         nv.call("vl_lrn_pool_fwd", x, y, arg, n, h, h, c, *LRN)
@@ -42,9 +42,9 @@ for (h, c) in ((57, 96), (28, 256)):
     y = torch.empty(n, p, p, c, device="cuda", dtype=torch.bfloat16)
     arg = torch.empty(n, p, p, c, device="cuda", dtype=torch.uint8)
     for rep in range(2):
-        for mode, env in (("v3 row ring", {"VL_LRN_FWD_V3": "1"}), ("v4 grid 4/SM", {"VL_LRN_FWD_CTAS": "4"}),
+        for mode, env in (("v2 strip kernel", {"VL_LRN_FWD_V2": "1"}), ("v4 grid 4/SM", {"VL_LRN_FWD_CTAS": "4"}),
                           ("v4 grid 8/SM", {"VL_LRN_FWD_CTAS": "8"}), ("v4 grid 16/SM", {}), ("v4 grid 32/SM", {"VL_LRN_FWD_CTAS": "32"})):
-            for k in ("VL_LRN_FWD_V3", "VL_LRN_FWD_CTAS"):
+            for k in ("VL_LRN_FWD_V2", "VL_LRN_FWD_CTAS"):
                 os.environ.pop(k, None)
             os.environ.update(env)
             us = t(lambda: nv.call("vl_lrn_pool_fwd", x, y, arg, n, h, h, c, *LRN))

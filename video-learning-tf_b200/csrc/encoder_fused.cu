@@ -6,9 +6,9 @@
 //                          frames_s2d_kernel: crop / mirror / fp32 feed)
 //   vl_s2d_pack_filter     conv1 HWIO fp32 filter -> bf16 [9 taps x 64, cout] operand of that convolution
 //   vl_s2d_unpack_grad     filter gradient of the 3x3x48 convolution -> HWIO gradient of the 11x11x3 filter
-//   vl_lrn_pool_fwd        LRN + 3x3/2 max-pool (alexnet.py:80-98,121-139): lrn_pool_fwd_kernel3 streams the rows of
-//                          the two AlexNet geometries through a five-row ring in shared memory; lrn_pool_fwd_kernel2
-//                          (strip per CTA, run-time extents) serves every other shape
+//   vl_lrn_pool_fwd        LRN + 3x3/2 max-pool (alexnet.py:80-98,121-139): lrn_pool_fwd_kernel4 (registers and warp
+//                          shuffles only, separable pooling) for the two AlexNet geometries; lrn_pool_fwd_kernel2
+//                          (strip per CTA in shared memory, run-time extents) serves every other shape
 //   vl_pool_lrn_bwd        MaxPoolGrad -> LRNGrad -> ReluGrad (+ bias gradient): pool_lrn_bwd_kernel4 (2 x 2 pixel
 //                          blocks, packed gather) for the two AlexNet geometries, pool_lrn_bwd_kernel2 (per pixel,
 //                          run-time extents) otherwise
@@ -801,151 +801,6 @@ __global__ void __launch_bounds__(THREADS, MINB)
 
 
 // ------------------------------------------------------------------------------------------------
-// Third generation of the fused forward: a CTA streams the input rows of one (frame, segment of pooled rows) through a
-// ring of five row slots in shared memory.  Iteration p normalises input rows 2p+1 and 2p+2 (row 2p is left over from
-// iteration p-1), one barrier, then pools output row p from rows 2p..2p+2; the rows of iteration p+1 land in the two
-// slots last read by iteration p-1, so one barrier per iteration is enough.  Every input row of a segment is
-// normalised exactly once (the strip kernel re-evaluated 1 row in 9), the geometry is a compile-time constant (no
-// index divisions), the x rows of the next iteration are fetched into registers before the pooling step, and with
-// 55-72 KB per CTA three to four CTAs per SM interleave their MUFU-heavy and ALU-heavy steps.
-// ------------------------------------------------------------------------------------------------
-template <int NE, int LPP, int C_, int H_, int W_, int THREADS, int MINB>
-__global__ void __launch_bounds__(THREADS, MINB)
-    lrn_pool_fwd_kernel3(const bf16* __restrict__ x, bf16* __restrict__ y, uint8_t* __restrict__ arg, int n, int seg_rows,
-                         int segs, float alpha, float bias, int overlap) {
-  constexpr int P = (H_ - 3) / 2 + 1, Q = (W_ - 3) / 2 + 1;
-  constexpr int RING = 5;
-  constexpr int ROW = W_ * C_;                       // elements per image row
-  constexpr int GROUPS = THREADS / LPP;              // pixels normalised per pass
-  constexpr int PASSES = (2 * W_ + GROUPS - 1) / GROUPS;  // passes over a pair of rows
-  constexpr int CPR = C_ / 8;                        // 16-byte chunks per pixel
-  constexpr int POOL_TASKS = Q * CPR;
-  static_assert(LPP * NE == C_ && NE % 8 == 0, "lanes x channels per lane must cover the channel axis exactly");
-  extern __shared__ __align__(16) uint8_t smem_raw[];
-  bf16* ring = reinterpret_cast<bf16*>(smem_raw);  // [RING][W][C]
-  const int l = threadIdx.x % LPP;
-  const int grp = threadIdx.x / LPP;
-  const int units = n * segs;
-  for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
-    const int nn = unit / segs;
-    const int sg = unit - nn * segs;
-    const int p0 = sg * seg_rows;
-    const int p1 = min(P, p0 + seg_rows);
-    const bf16* ximg = x + (long long)nn * (H_ * ROW) + l * NE;
-    // normalise `cnt` consecutive input rows starting at row `r0` from registers `xr` into ring slots starting at `s0`
-    uint32_t xr[PASSES][NE / 2];
-    auto fetch = [&](int r0, int cnt) {
-#pragma unroll
-      for (int ps = 0; ps < PASSES; ++ps) {
-        const int pix = ps * GROUPS + grp;
-        if (pix < cnt * W_) {
-          load_pairs<NE>(ximg + (long long)r0 * ROW + pix * C_, xr[ps]);
-        } else {
-#pragma unroll
-          for (int i = 0; i < NE / 2; ++i) xr[ps][i] = 0u;
-        }
-      }
-    };
-    auto normalise = [&](int s0, int cnt) {
-#pragma unroll
-      for (int ps = 0; ps < PASSES; ++ps) {
-        const int pix = ps * GROUPS + grp;
-        float v[NE], sq[NE], ssum[NE];
-#pragma unroll
-        for (int i = 0; i < NE / 2; ++i) {
-          v[2 * i] = __uint_as_float(xr[ps][i] << 16);
-          v[2 * i + 1] = __uint_as_float(xr[ps][i] & 0xffff0000u);
-        }
-#pragma unroll
-        for (int j = 0; j < NE; ++j) sq[j] = v[j] * v[j];
-        window5n<LPP, NE>(sq, l, ssum);
-        uint32_t o[NE / 2];
-#pragma unroll
-        for (int i = 0; i < NE / 2; ++i) {
-          const float r0s = rsqrt_approx(fmaf(alpha, ssum[2 * i], bias));
-          const float r1s = rsqrt_approx(fmaf(alpha, ssum[2 * i + 1], bias));
-          const __nv_bfloat162 pk =
-              __floats2bfloat162_rn(v[2 * i] * (r0s * sqrt_approx(r0s)), v[2 * i + 1] * (r1s * sqrt_approx(r1s)));
-          o[i] = *reinterpret_cast<const uint32_t*>(&pk);
-        }
-        if (pix < cnt * W_) {
-          const int rr = pix >= W_ ? 1 : 0;  // which of the (up to) two rows
-          int slot = s0 + rr;
-          if (slot >= RING) slot -= RING;
-          store_pairs<NE>(ring + slot * ROW + (pix - rr * W_) * C_ + l * NE, o);
-        }
-      }
-    };
-    __syncthreads();  // the previous unit's pooling reads are finished
-    // pool one output row from three ring rows
-    auto pool_row = [&](int p, const bf16* r0, const bf16* r1, const bf16* r2) {
-      const bf16* rows3[3] = {r0, r1, r2};
-      for (int t = threadIdx.x; t < POOL_TASKS; t += THREADS) {
-        const int ch = t % CPR;
-        const int qq = t / CPR;
-        uint32_t best[4], bidx[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          best[i] = 0xFF80FF80u;  // (-inf, -inf)
-          bidx[i] = 0;
-        }
-#pragma unroll
-        for (int r = 0; r < 3; ++r) {
-          const bf16* rp = rows3[r] + (2 * qq) * C_ + ch * 8;
-#pragma unroll
-          for (int s2c = 0; s2c < 3; ++s2c) {
-            const uint4 vv = *reinterpret_cast<const uint4*>(rp + s2c * C_);
-            const uint32_t v4[4] = {vv.x, vv.y, vv.z, vv.w};
-            const uint32_t code2 = (uint32_t)(r * 3 + s2c) * 0x00010001u;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              // strict >: the first maximum in (h, w) scan order wins, like TF
-              uint32_t m, mx;
-              asm("set.gt.u32.bf16x2 %0, %1, %2;" : "=r"(m) : "r"(v4[i]), "r"(best[i]));
-              asm("max.bf16x2 %0, %1, %2;" : "=r"(mx) : "r"(best[i]), "r"(v4[i]));
-              best[i] = mx;
-              bidx[i] = (bidx[i] & ~m) | (code2 & m);
-            }
-          }
-        }
-        const long long opix = ((long long)nn * P + p) * Q + qq;
-        *reinterpret_cast<uint4*>(y + opix * C_ + ch * 8) = make_uint4(best[0], best[1], best[2], best[3]);
-        const uint32_t lo = __byte_perm(bidx[0], bidx[1], 0x6420);
-        const uint32_t hi = __byte_perm(bidx[2], bidx[3], 0x6420);
-        *reinterpret_cast<uint2*>(arg + opix * C_ + ch * 8) = make_uint2(lo, hi);
-      }
-    };
-    int slot_top = 0;  // ring slot of input row 2p
-    fetch(2 * p0, 1);
-    normalise(0, 1);
-    fetch(2 * p0 + 1, 2);
-    // Iteration p normalises rows 2p+1 / 2p+2 AND pools output row p-1 (complete since the previous barrier) inside one
-    // barrier interval: the warps of a CTA are spread over MUFU-heavy and ALU-heavy code instead of marching through
-    // the two phases in lock step.  Ring of five rows: 2p-2 .. 2p+2.
-    int prev0 = 0, prev1 = 0, prev2 = 0;
-    for (int p = p0; p < p1; ++p) {
-      int s1 = slot_top + 1;
-      if (s1 >= RING) s1 -= RING;
-      int s2 = s1 + 1;
-      if (s2 >= RING) s2 -= RING;
-      normalise(s1, 2);  // rows 2p+1, 2p+2
-      if (p + 1 < p1) fetch(2 * p + 3, 2);
-      if (overlap) {
-        if (p > p0) pool_row(p - 1, ring + prev0 * ROW, ring + prev1 * ROW, ring + prev2 * ROW);
-        __syncthreads();
-      } else {
-        __syncthreads();
-        pool_row(p, ring + slot_top * ROW, ring + s1 * ROW, ring + s2 * ROW);
-      }
-      prev0 = slot_top, prev1 = s1, prev2 = s2;
-      slot_top = s2;
-    }
-    if (overlap) pool_row(p1 - 1, ring + prev0 * ROW, ring + prev1 * ROW, ring + prev2 * ROW);
-  }
-}
-
-
-// ------------------------------------------------------------------------------------------------
 // Fourth generation of the fused forward: registers and warp shuffles only - no shared memory, no CTA barrier (the top
 // stall of the row-ring kernel), every lrn(x) evaluated (almost) once, separable pooling.
 //
@@ -1215,8 +1070,7 @@ extern "C" int vl_lrn_pool_fwd(const void* x, void* y, void* argmax, int32_t n, 
     if ((size_t)(2 * r + 1) * row_bytes <= strip_limit) rows_out = r;
   // third generation (row ring, compile-time geometry): the two AlexNet instances
   // fourth generation (registers + shuffles, no shared memory): the two AlexNet instances
-  if (!getenv("VL_LRN_FWD_V2") && !getenv("VL_LRN_FWD_V3") &&
-      ((c == 96 && h == 57 && w == 57) || (c == 256 && h == 28 && w == 28))) {
+  if (!getenv("VL_LRN_FWD_V2") && ((c == 96 && h == 57 && w == 57) || (c == 256 && h == 28 && w == 28))) {
     const int segs = c == 96 ? 4 : 2;  // row segments per image: one re-normalised input row per extra segment
     const int seg_rows = (p + segs - 1) / segs;
     const int wpr = c == 96 ? 4 : 2, slices = c == 96 ? 1 : 4;
@@ -1234,50 +1088,6 @@ extern "C" int vl_lrn_pool_fwd(const void* x, void* y, void* argmax, int32_t n, 
       lrn_pool_fwd_kernel4<16, 4, 4, 256, 28, 28><<<g, 128, 0, stream>>>(
           reinterpret_cast<const bf16*>(x), reinterpret_cast<bf16*>(y), reinterpret_cast<uint8_t*>(argmax), n, seg_rows, segs,
           alpha, bias);
-    VL_LAUNCHED();
-    return 0;
-  }
-  if (!getenv("VL_LRN_FWD_V2") && ((c == 96 && h == 57 && w == 57) || (c == 256 && h == 28 && w == 28))) {
-    const int ring_bytes = 5 * (int)row_bytes;
-    const int per_sm_smem = (227 * 1024) / (ring_bytes + 1024);
-    // 80 registers x 256 threads: three CTAs per SM
-    const int want_mb = 3;
-    const int per_sm = per_sm_smem < want_mb ? per_sm_smem : want_mb;
-    const long long resident = (long long)vl::num_sms() * per_sm;
-    // segments per frame: balance the waves against the one re-normalised row per extra segment
-    int best_segs = 1;
-    double best_eff = 0.0;
-    for (int sgs = 1; sgs <= 4; ++sgs) {
-      const int sr = (p + sgs - 1) / sgs;
-      const int real = (p + sr - 1) / sr;
-      const long long units = (long long)n * real;
-      const long long waves = (units + resident - 1) / resident;
-      const double eff = (double)units / (double)(waves * resident) * (2.0 * p + 1) / (2.0 * p + real);
-      if (eff > best_eff + 1e-9) best_eff = eff, best_segs = real;
-    }
-    // (pooling row p-1 inside the barrier interval of row p was measured slower: 360 against 329 us for 96 channels -
-    // the kernel is bound by the MUFU / MIO queue and the issue slots, not by the phase separation)
-    const int overlap_mode = 0;
-    const int seg_rows = (p + best_segs - 1) / best_segs;
-    const long long units = (long long)n * best_segs;
-    const int g = (int)(units < resident ? units : resident);
-#define VL_FWD3_LAUNCH(NE_, LPP_, C__, H__, W__, T_, MB_)                                                                 \
-  do {                                                                                                                \
-    static bool attr = false;                                                                                         \
-    if (!attr) {                                                                                                      \
-      VL_CHECK_CUDA(cudaFuncSetAttribute(lrn_pool_fwd_kernel3<NE_, LPP_, C__, H__, W__, T_, MB_>,                          \
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, ring_bytes));                   \
-      attr = true;                                                                                                    \
-    }                                                                                                                 \
-    lrn_pool_fwd_kernel3<NE_, LPP_, C__, H__, W__, T_, MB_><<<g, T_, ring_bytes, stream>>>(                                \
-        reinterpret_cast<const bf16*>(x), reinterpret_cast<bf16*>(y), reinterpret_cast<uint8_t*>(argmax), n, seg_rows, \
-        best_segs, alpha, bias, overlap_mode);                                                                        \
-  } while (0)
-    if (c == 96)
-      VL_FWD3_LAUNCH(24, 4, 96, 57, 57, 256, 3);
-    else
-      VL_FWD3_LAUNCH(16, 16, 256, 28, 28, 256, 3);
-#undef VL_FWD3_LAUNCH
     VL_LAUNCHED();
     return 0;
   }
