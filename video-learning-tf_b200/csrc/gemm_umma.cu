@@ -349,7 +349,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (one elected lane; warp-uniform control) =====================
-    const uint32_t idesc = p.idesc;
+    const uint32_t idesc_full = p.idesc;
     const uint64_t a_hi = (static_cast<uint64_t>(p.a_desc_hi) << 32) | (static_cast<uint64_t>(p.a_lbo_enc) << 16);
     const uint64_t b_hi = (static_cast<uint64_t>(p.b_desc_hi) << 32) | (static_cast<uint64_t>(p.b_lbo_enc) << 16);
     const uint32_t a_kstep = p.a_kstep_enc, b_kstep = p.b_kstep_enc;
@@ -366,6 +366,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + acc * ACC_STRIDE_COLS;
       uint32_t accumulate = 0;
+      // transposed-im2col B: the last n-block may hold fewer (tap, channel chunk) columns than BN (conv2: 25 taps =
+      // 6 x 4 + 1); its UMMAs are issued with N = 64 x the valid chunks instead of multiplying unloaded shared memory
+      uint32_t idesc = idesc_full;
+      if (BMODE == VL_B_IM2COL_MN && !p.row_shift) {
+        const int per_blk = BN >> 6;
+        const int valid = min(per_blk, p.taps * p.cchunks - t.n_blk * per_blk);
+        idesc = (idesc_full & ~(0x3Fu << 17)) | ((uint32_t)(valid * 64 >> 3) << 17);
+      }
       int cc = t.kb_begin % cchunks_mma;
       for (int kb = t.kb_begin; kb < t.kb_end; ++kb) {
         const bool tail = (++cc == cchunks_mma);
