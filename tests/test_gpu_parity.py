@@ -753,6 +753,33 @@ def _oracle_backward_on_device_state(eng, cfg, params, frames, onehot, mask):
     return grads, float(O.global_norm(grads))
 
 
+def test_half_batch_forward_chains_equal_the_single_chain(vl, monkeypatch):
+    """The forward convolution stack runs as two half-batch chains on two streams from 256 frames on (engine._encoder_fwd);
+    logits and one train step must be bit-identical to the single chain (VL_FWD_HALVES=0): same kernels, same per-frame
+    tile arithmetic, only the stream schedule differs."""
+    E = vl["E"]
+    clips, fpc, c = 16, 16, 101  # 256 frames: the smallest batch that takes the two-chain path
+    cfg = E.EngineConfig(workflow="lrcn", fusion="avg", fpc=fpc, num_classes=c, lstm_hidden=256, clip_norm=10,
+                         dropout_keep_prob=0.0, optimizer="sgd", mean=(99.197148, 105.293620, 109.503945))
+    params = E.init_variables(cfg, seed=21)
+    rng = np.random.default_rng(4)
+    frames = rng.integers(0, 256, size=(clips * fpc, 227, 227, 3), dtype=np.uint8)
+    onehot = np.zeros((clips, c), np.int32)
+    onehot[np.arange(clips), rng.integers(0, c, clips)] = 1
+    out = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("VL_FWD_HALVES", mode)
+        eng = E.Engine(cfg, max_clips=clips, params=params)
+        logits = eng.forward(frames)
+        step = eng.train_step(frames, onehot, 1e-3)
+        out[mode] = (logits, step, eng.state_dict()["dcnn/conv1W"])
+        del eng
+    assert np.array_equal(out["1"][0], out["0"][0])
+    assert out["1"][1][0] == out["0"][1][0] and out["1"][1][3] == out["0"][1][3]  # loss, accuracy
+    # conv1's filter gradient is a split-K red.add sum (order varies run to run): compare within rounding
+    assert rel(out["1"][2], out["0"][2]) < 1e-5
+
+
 def test_full_size_properties_config2(vl):
     """BASELINE.json configs[1] at its FULL size (64 clips x 16 frames per GPU), where the oracle would take minutes:
     size-independent properties of the path.
