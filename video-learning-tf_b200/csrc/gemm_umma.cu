@@ -570,8 +570,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
                   w[j] &= keep;
                 }
               }
-              *reinterpret_cast<uint4*>(out) = make_uint4(w[0], w[1], w[2], w[3]);
-              *reinterpret_cast<uint4*>(out + 8) = make_uint4(w[4], w[5], w[6], w[7]);
+              if ((reinterpret_cast<uintptr_t>(out) & 31) == 0) {  // one full 32-byte sector per thread
+                asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(out), "r"(w[0]), "r"(w[1]),
+                             "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+                             : "memory");
+              } else {
+                *reinterpret_cast<uint4*>(out) = make_uint4(w[0], w[1], w[2], w[3]);
+                *reinterpret_cast<uint4*>(out + 8) = make_uint4(w[4], w[5], w[6], w[7]);
+              }
             } else {
 #pragma unroll
               for (int j = 0; j < 16; ++j)
@@ -592,9 +598,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
                   if (j < ncols) atomicAdd(out + j, f[j]);
               }
             } else if (vec_ok && ncols == 16) {
+              if ((reinterpret_cast<uintptr_t>(out) & 31) == 0) {
+                // 32-byte stores: a thread's 64 bytes leave as two FULL sectors instead of four half-sector writes (the
+                // rows of a warp are c_ld floats apart, so nothing else fills the other half of a sector)
 #pragma unroll
-              for (int j = 0; j < 4; ++j)
-                *reinterpret_cast<float4*>(out + 4 * j) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                for (int j = 0; j < 2; ++j)
+                  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(out + 8 * j), "f"(f[8 * j]),
+                               "f"(f[8 * j + 1]), "f"(f[8 * j + 2]), "f"(f[8 * j + 3]), "f"(f[8 * j + 4]), "f"(f[8 * j + 5]),
+                               "f"(f[8 * j + 6]), "f"(f[8 * j + 7])
+                               : "memory");
+              } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  *reinterpret_cast<float4*>(out + 4 * j) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+              }
             } else {
 #pragma unroll
               for (int j = 0; j < 16; ++j)
