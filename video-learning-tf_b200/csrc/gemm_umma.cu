@@ -480,8 +480,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
         auto fetch_mask = [&](int c0, uint4 (&m)[2]) {
           if (mask_vec && c0 < BN && n0 + c0 + 16 <= p.N) {
             const bf16* mrow = p.mask + grow * p.mask_ld + gcol0 + c0;
-            m[0] = __ldg(reinterpret_cast<const uint4*>(mrow));
-            m[1] = __ldg(reinterpret_cast<const uint4*>(mrow + 8));
+            if ((reinterpret_cast<uintptr_t>(mrow) & 31) == 0) {  // one 32-byte (full sector) read per thread
+              asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                           : "=r"(m[0].x), "=r"(m[0].y), "=r"(m[0].z), "=r"(m[0].w), "=r"(m[1].x), "=r"(m[1].y), "=r"(m[1].z),
+                             "=r"(m[1].w)
+                           : "l"(mrow));
+            } else {
+              m[0] = __ldg(reinterpret_cast<const uint4*>(mrow));
+              m[1] = __ldg(reinterpret_cast<const uint4*>(mrow + 8));
+            }
           }
         };
         auto process = [&](const uint32_t (&v)[16], int c0, const uint4 (&mpre)[2]) {
