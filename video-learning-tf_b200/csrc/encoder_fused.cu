@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(128)
     frames_s2d_direct_kernel(const uint8_t* __restrict__ frames, const float* __restrict__ mean3, bf16* __restrict__ out,
                              int h, int w, int pad_top, int pad_left, int hb, int wb, long long total_bytes,
-                             int n_rows /* n * hb */) {
+                             int n_rows /* n * hb */, int wide) {
   constexpr int S = 4, SEG = 12, CBLK = 48;
   float m[3] = {0.f, 0.f, 0.f};
   if (mean3 != nullptr) {
@@ -292,9 +292,20 @@ __global__ void __launch_bounds__(128)
         o[dy * 6 + i] = ok[dy] ? *reinterpret_cast<const uint32_t*>(&pk) : 0u;
       }
     }
-    uint4* dst = reinterpret_cast<uint4*>(out + ((long long)rowi * wb + bx) * CBLK);
+    bf16* dstp = out + ((long long)rowi * wb + bx) * CBLK;
+    if (wide && (reinterpret_cast<uintptr_t>(dstp) & 31) == 0) {
+      // three 32-byte stores: the lanes of a warp are 96 bytes apart, so a 16-byte store fills only half a sector
 #pragma unroll
-    for (int k = 0; k < 6; ++k) dst[k] = make_uint4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
+      for (int k = 0; k < 3; ++k)
+        asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dstp + 16 * k), "r"(o[8 * k]),
+                     "r"(o[8 * k + 1]), "r"(o[8 * k + 2]), "r"(o[8 * k + 3]), "r"(o[8 * k + 4]), "r"(o[8 * k + 5]),
+                     "r"(o[8 * k + 6]), "r"(o[8 * k + 7])
+                     : "memory");
+    } else {
+      uint4* dst = reinterpret_cast<uint4*>(dstp);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) dst[k] = make_uint4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
+    }
   }
 }
 
@@ -1004,7 +1015,8 @@ extern "C" int vl_frames_s2d_crop(const void* frames, int32_t is_u8, const float
     const int grid_d = want < vl::num_sms() * 16 ? want : vl::num_sms() * 16;
     frames_s2d_direct_kernel<<<grid_d, 128, 0, stream>>>(reinterpret_cast<const uint8_t*>(frames), mean3,
                                                         reinterpret_cast<bf16*>(out), h, w, pad_top, pad_left, hb, wb,
-                                                        (long long)n * h * w * 3, n_rows);
+                                                        (long long)n * h * w * 3, n_rows,
+                                                        getenv("VL_S2D_WIDE") ? atoi(getenv("VL_S2D_WIDE")) : 1);
     VL_LAUNCHED();
     return 0;
   }
