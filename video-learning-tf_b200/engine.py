@@ -613,7 +613,8 @@ class Engine(object):
         # buffer (conv1's filter gradient of the previous step) - NOT for the optimiser tail of the previous step, so
         # the HBM-bound staging of step i+1 runs next to the norm / update / operand-refresh kernels of step i.
         main = torch.cuda.current_stream()
-        overlap = self._stage_stream is not main and os.environ.get("VL_STAGE_OVERLAP", "1") != "0"
+        # (stream OBJECTS differ from call to call of torch.cuda.current_stream(): compare the handles)
+        overlap = self._stage_stream.cuda_stream != main.cuda_stream and os.environ.get("VL_STAGE_OVERLAP", "1") != "0"
         st = self._stage_stream if overlap else main
         if overlap:
             if self._frames_ready is None:  # unknown producer: everything enqueued on the caller's stream so far
@@ -656,7 +657,8 @@ class Engine(object):
         # (only one: the contraction kernels hold 41 K of the 64 K registers).  Measured (profiles/r02_step_ab.txt):
         # forward 2.04 -> 1.99 ms, train step -0.2 % (min) / -1.7 % (median) in a same-box A/B.
         fwd2 = self._side2
-        if n >= 256 and n % 2 == 0 and fwd2 is not main and os.environ.get("VL_FWD_HALVES", "1") == "1":
+        if n >= 256 and n % 2 == 0 and fwd2.cuda_stream != main.cuda_stream and \
+                os.environ.get("VL_FWD_HALVES", "1") == "1":
             ev = torch.cuda.Event()
             ev.record(main)
             fwd2.wait_event(ev)
